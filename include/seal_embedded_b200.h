@@ -1,0 +1,202 @@
+/*
+ * seal_embedded_b200.h — C ABI of the B200-native CKKS encode+encrypt library.
+ *
+ * Two layers, both `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) The reference's own public API, symbol for symbol, so the library drops in for
+ *      SEAL-Embedded's device library on the encrypt path
+ *      (reference: device/lib/seal_embedded.h:91-130):
+ *          se_setup_custom / se_setup / se_setup_default   seal_embedded.h:91-118
+ *          se_encrypt_seeded / se_encrypt                  seal_embedded.h:120-124
+ *          se_cleanup                                      seal_embedded.h:126-130
+ *      with the caller-visible structs Parms (parameters.h:43-67), Modulus (modulus.h:22-30),
+ *      SE_PTRS (ckks_common.h:36-52) and SE_PARMS (seal_embedded.h:52-56) laid out as in the
+ *      reference's default (SE_USE_MALLOC, 32-bit ZZ) configuration.
+ *
+ *  (2) The batch extension the reference lacks (one call = many independent ciphertexts), in a
+ *      host-pointer and a device-pointer flavour, plus stage-level entry points used by the parity
+ *      tests and the NTT micro-benchmark.  These are the `seb_*` functions.
+ *
+ * All functions return 0 (SE_SUCCESS) or a negative SE_ERR_* code unless stated otherwise;
+ * seb_last_error() gives the text of the last failure on the calling thread.
+ * One process drives one GPU (select it with seb_create's `device` or SE_B200_DEVICE before
+ * se_setup).  A context is not thread-safe, like the reference (seal_embedded.c:18-22).
+ */
+#ifndef SEAL_EMBEDDED_B200_H
+#define SEAL_EMBEDDED_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/types.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* (1) reference-compatible API                                                               */
+/* ------------------------------------------------------------------------------------------ */
+typedef uint32_t ZZ; /* defines.h:373 */
+typedef float flpt;  /* defines.h:376 */
+
+#define SE_PRNG_SEED_BYTE_COUNT 64 /* defines.h:67 */
+
+#define SE_SUCCESS 0 /* seal_embedded.h:35-40 */
+#define SE_ERR_NO_MEMORY -12
+#define SE_ERR_INVALD_ARGUMENT -22
+#define SE_ERR_UNKNOWN -1000
+#define SE_ERR_MINIMUM -9999
+/* extension codes (inside the reference's reserved range) */
+#define SE_ERR_CUDA -1001        /* a CUDA call failed */
+#define SE_ERR_ENCODE_RANGE -1002 /* ckks_encode_base would have returned false */
+#define SE_ERR_NO_KEY -1003      /* key material missing for the requested encryption type */
+
+typedef struct Modulus /* modulus.h:22-30 */
+{
+    ZZ value;
+    ZZ const_ratio[2]; /* floor(2^64/q): [0] low word, [1] high word */
+} Modulus;
+
+typedef struct /* parameters.h:43-67 (SE_USE_MALLOC, no SE_REVERSE_CT_GEN_ENABLED) */
+{
+    size_t coeff_count;
+    size_t logn;
+    Modulus *moduli;
+    Modulus *curr_modulus;
+    size_t curr_modulus_idx;
+    size_t nprimes;
+    double scale;
+    bool is_asymmetric;
+    bool pk_from_file;
+    bool sample_s;
+    bool small_s;
+    bool small_u;
+} Parms;
+
+/* ckks_common.h:36-52.  Host-side views; see INTEGRATION.md for which are populated:
+ * values, c0_ptr, c1_ptr (valid during the send callback), index_map_ptr and ternary (the packed
+ * secret key in symmetric mode) are; the MCU scratch pointers are NULL. */
+typedef struct SE_PTRS
+{
+    void *conj_vals;  /* `double complex *` in the reference */
+    void *ifft_roots; /* `double complex *` in the reference */
+    flpt *values;
+    ZZ *ternary;
+    int64_t *conj_vals_int_ptr;
+    ZZ *c0_ptr;
+    ZZ *c1_ptr;
+    uint16_t *index_map_ptr;
+    ZZ *ntt_roots_ptr;
+    ZZ *ntt_pte_ptr;
+    int8_t *e1_ptr;
+} SE_PTRS;
+
+typedef struct /* seal_embedded.h:52-56 */
+{
+    Parms *parms;
+    SE_PTRS *se_ptrs;
+} SE_PARMS;
+
+typedef enum { SE_SYM_ENCR, SE_ASYM_ENCR } EncryptType; /* seal_embedded.h:58 */
+
+typedef size_t (*SEND_FNCT_PTR)(void *, size_t);                    /* seal_embedded.h:65 */
+typedef ssize_t (*RND_FNCT_PTR)(void *, size_t, unsigned int flags); /* seal_embedded.h:73 */
+
+SE_PARMS *se_setup_custom(size_t degree, size_t nprimes, const ZZ *modulus_vals, const ZZ *ratios,
+                          double scale, EncryptType encrypt_type);
+SE_PARMS *se_setup(size_t degree, size_t nprimes, double scale, EncryptType encrypt_type);
+SE_PARMS *se_setup_default(EncryptType encrypt_type);
+bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR network_send_function,
+                       void *v, size_t vlen_bytes, bool print, SE_PARMS *se_parms);
+bool se_encrypt(SEND_FNCT_PTR network_send_function, void *v, size_t vlen_bytes, bool print,
+                SE_PARMS *se_parms);
+void se_cleanup(SE_PARMS *se_parms);
+
+/* Batch extension at the se_* level (host buffers).  Each item b encrypts v[b*vlen .. +vlen)
+ * (vlen <= n/2 floats, zero padded) with seeds[b*64 .. +64) (and shareable_seeds in symmetric
+ * mode; NULL seeds are drawn from getrandom()).  out receives, per item, the byte stream
+ * se_encrypt would have sent: [nprimes][2][n] words = c0_p0, c1_p0, c0_p1, ...
+ * (seal_embedded.c:196-203).  Symmetric c1 is `a` unless se_b200_set_reference_quirk(1).
+ * Returns false if any item failed to encode (reference: ckks_common.c:195-204). */
+bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seeds, const flpt *v,
+                             size_t vlen, size_t batch, ZZ *out, SE_PARMS *se_parms);
+/* Reproduce se_encrypt's symmetric byte stream exactly, where the c1 buffer handed to the send
+ * callback holds ntt(m+e) (ckks_sym.c:86-88 aliasing).  Default 0: c1 = a. */
+void se_b200_set_reference_quirk(int on);
+/* The context behind the static SE_PARMS (for the seb_* calls below); NULL before se_setup. */
+struct seb_ctx *se_b200_context(SE_PARMS *se_parms);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (2) batch / device-pointer extension                                                       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct seb_ctx seb_ctx;
+
+const char *seb_last_error(void);
+
+/* primes == NULL: the reference's default chain for (n, nprimes) (parameters.c:129-230) with its
+ * tabulated 2n-th roots (ntt.c:199-291) and default scale when scale <= 0.  With explicit primes,
+ * psis[i] must be a primitive 2n-th root of unity mod primes[i].  device < 0: keep the current
+ * CUDA device. */
+seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes, const uint32_t *psis,
+                    double scale, int asym, int device);
+void seb_destroy(seb_ctx *ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own */
+int seb_set_stream(seb_ctx *ctx, void *cuda_stream);
+/* pk0, pk1: host [nprimes][n], NTT form (files pk{0,1}_ntt_<n>_<q>.dat, fileops.c:172-204) */
+int seb_set_public_key(seb_ctx *ctx, const uint32_t *pk0, const uint32_t *pk1);
+/* sk: host n/4 bytes, 2 bits per coefficient (file sk_<n>.dat, fileops.c:140-170) */
+int seb_set_secret_key(seb_ctx *ctx, const uint8_t *sk_packed);
+/* pre-size the per-batch scratch (otherwise grown on demand) */
+int seb_reserve(seb_ctx *ctx, size_t batch);
+
+size_t seb_degree(const seb_ctx *ctx);
+size_t seb_nprimes(const seb_ctx *ctx);
+double seb_scale(const seb_ctx *ctx);
+uint32_t seb_prime(const seb_ctx *ctx, size_t i);
+/* number of kernels this library has launched so far on this context */
+uint64_t seb_launch_count(const seb_ctx *ctx);
+
+/* ---- full path, device pointers, asynchronous on the context's stream ---- */
+/* d_values [batch][vlen] fp32, d_seeds [batch][64], d_out [batch][nprimes][2][n] u32.
+ * All pointers 16-byte aligned. */
+int seb_encrypt_asym_device(seb_ctx *ctx, const float *d_values, size_t vlen, const uint8_t *d_seeds,
+                            size_t batch, uint32_t *d_out);
+int seb_encrypt_sym_device(seb_ctx *ctx, const float *d_values, size_t vlen,
+                           const uint8_t *d_shareable_seeds, const uint8_t *d_seeds, size_t batch,
+                           uint32_t *d_out, int ref_quirk);
+/* synchronises the stream; returns how many items of the last *_device call failed to encode
+ * (>= 0) or a negative error */
+int seb_encode_failures(seb_ctx *ctx);
+
+/* ---- full path, host pointers: pinned staging, chunked, H2D/compute/D2H overlapped ---- */
+int seb_encrypt_asym_host(seb_ctx *ctx, const float *values, size_t vlen, const uint8_t *seeds,
+                          size_t batch, uint32_t *out);
+int seb_encrypt_sym_host(seb_ctx *ctx, const float *values, size_t vlen,
+                         const uint8_t *shareable_seeds, const uint8_t *seeds, size_t batch,
+                         uint32_t *out, int ref_quirk);
+
+/* ---- stage level (device pointers, asynchronous) ---- */
+/* ckks_encode_base: d_pt [batch][n] int64 */
+int seb_encode_device(seb_ctx *ctx, const float *d_values, size_t vlen, size_t batch, int64_t *d_pt);
+/* ckks_asym_init samplers: d_u [batch][n/4], d_e [batch][2][n] int8 (e0 then e1), d_ctr [batch]
+ * = PRNG counter after u (e0 uses the next n/16 counters, e1 the n/16 after those) */
+int seb_sample_asym_device(seb_ctx *ctx, const uint8_t *d_seeds, size_t batch, uint8_t *d_u, int8_t *d_e,
+                           uint32_t *d_ctr);
+/* CBD polynomials from counter d_ctr[b] (NULL: 0): d_e [batch][npoly][n] */
+int seb_sample_cbd_device(seb_ctx *ctx, const uint8_t *d_seeds, const uint32_t *d_ctr, size_t npoly,
+                          size_t batch, int8_t *d_e);
+/* sample_poly_uniform under prime prime_idx: row b written at d_out + b*ct_stride (n words);
+ * d_ctr [batch] is read and advanced */
+int seb_sample_uniform_device(seb_ctx *ctx, const uint8_t *d_seeds, uint32_t *d_ctr, size_t prime_idx,
+                              size_t batch, uint32_t *d_out, size_t ct_stride);
+/* ntt_inpl, in place: d_polys [batch][nprimes][n] (polynomial k uses prime k % nprimes) */
+int seb_ntt_device(seb_ctx *ctx, uint32_t *d_polys, size_t batch);
+/* first 136-byte block of SHAKE256(seed_i || LE64(counter_i)): d_out [count][17] u64 */
+int seb_prng_blocks_device(seb_ctx *ctx, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
+                           uint64_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

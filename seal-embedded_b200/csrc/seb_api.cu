@@ -1,0 +1,709 @@
+// seb_api.cu — context, setup-time tables and the `seb_*` C ABI (include/seal_embedded_b200.h, part 2).
+//
+// Host code here is the GPU-side counterpart of the reference's L0 layer: parameter chains
+// (device/lib/parameters.c:129-230), const_ratio (modulus.c:23-56), psi per (n,q)
+// (ntt.c:199-291), root tables (ntt.c:40-52), index map (ckks_common.c:32-68) and IFFT twiddles
+// (fft.c:27-45) are rebuilt once per context and kept resident in HBM.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/seal_embedded_b200.h"
+#include "seb_kernels.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *seb_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                         \
+    do                                                                                                   \
+    {                                                                                                    \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                        __LINE__);                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// parameter tables (facts of the reference's default parameter sets)
+// ---------------------------------------------------------------------------------------------
+static const uint32_t k_primes27[3]  = {134012929u, 134111233u, 134176769u};
+static const uint32_t k_primes30[13] = {1053818881u, 1054015489u, 1054212097u, 1055260673u, 1056178177u,
+                                        1056440321u, 1058209793u, 1060175873u, 1060700161u, 1060765697u,
+                                        1061093377u, 1062469633u, 1062535169u};
+
+// parameters.c:191-227: legal (n, nprimes) and the chain used
+static bool default_primes(size_t n, size_t np, uint32_t *out)
+{
+    const uint32_t *src = k_primes30;
+    size_t maxp         = 0;
+    switch (n)
+    {
+        case 1024:
+        case 2048: src = k_primes27; maxp = 1; break;
+        case 4096: maxp = 3; break;
+        case 8192: maxp = 6; break;
+        case 16384: maxp = 13; break;
+        default: return false;
+    }
+    if (np < 1 || np > maxp) return false;
+    for (size_t i = 0; i < np; i++) out[i] = src[i];
+    return true;
+}
+
+// ntt.c:213-289
+static uint32_t default_psi(size_t n, uint32_t q)
+{
+    static const uint32_t psi4k27[3]  = {7470u, 3856u, 24149u};
+    static const uint32_t psi4k30[3]  = {503422u, 16768u, 7305u};
+    static const uint32_t psi8k[6]    = {374229u, 123363u, 79941u, 38869u, 162146u, 81884u};
+    static const uint32_t psi16k[13]  = {13040u, 507u,   1595u,   68507u,  3073u,   6854u, 44467u,
+                                         16117u, 27607u, 222391u, 105471u, 310222u, 2005u};
+    if (n == 1024) return q == 134012929u ? 142143u : 0u;
+    if (n == 2048) return q == 134012929u ? 85250u : 0u;
+    if (n == 4096)
+        for (int i = 0; i < 3; i++)
+        {
+            if (q == k_primes27[i]) return psi4k27[i];
+            if (q == k_primes30[i]) return psi4k30[i];
+        }
+    if (n == 8192)
+        for (int i = 0; i < 6; i++)
+            if (q == k_primes30[i]) return psi8k[i];
+    if (n == 16384)
+        for (int i = 0; i < 13; i++)
+            if (q == k_primes30[i]) return psi16k[i];
+    return 0u;
+}
+
+static inline uint32_t mulmod(uint32_t a, uint32_t b, uint32_t q) { return (uint32_t)(((uint64_t)a * b) % q); }
+static uint32_t powmod(uint32_t a, uint64_t e, uint32_t q)
+{
+    uint32_t r = 1;
+    while (e)
+    {
+        if (e & 1) r = mulmod(r, a, q);
+        a = mulmod(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+static inline uint32_t shoup(uint32_t w, uint32_t q) { return (uint32_t)(((uint64_t)w << 32) / q); }
+static inline size_t bitrev(size_t x, int bits)
+{
+    size_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct Scratch  // per in-flight chunk
+{
+    size_t cap       = 0;  // ciphertexts
+    int64_t *pt      = nullptr;
+    int8_t *e        = nullptr;
+    uint8_t *u       = nullptr;
+    uint32_t *ctr    = nullptr;
+    uint32_t *ctr_a  = nullptr;
+    int *fail        = nullptr;
+    // host-API staging
+    size_t io_cap    = 0;
+    float *d_values  = nullptr;
+    uint8_t *d_seeds = nullptr, *d_sseeds = nullptr;
+    uint32_t *d_out  = nullptr;
+    float *h_values  = nullptr;
+    uint8_t *h_seeds = nullptr, *h_sseeds = nullptr;
+    uint32_t *h_out  = nullptr;
+    int *h_fail      = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done    = nullptr;
+};
+
+struct seb_ctx
+{
+    int device = 0;
+    size_t n = 0, np = 0;
+    int logn = 0;
+    bool asym = false;
+    double scale = 0;
+    uint32_t primes[SEB_MAX_PRIMES] = {0};
+    uint32_t psis[SEB_MAX_PRIMES]   = {0};
+    SebModuli mods;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // resident tables
+    uint2 *d_roots      = nullptr;  // [np][n]
+    double2 *d_tw       = nullptr;  // [n]
+    uint16_t *d_src_map = nullptr;  // [n]
+    uint2 *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n] Shoup pairs
+    uint2 *d_ntt_s = nullptr;                  // [np][n] Shoup pairs
+    bool have_pk = false, have_sk = false;
+    Scratch slot[2];
+    size_t last_batch = 0;
+    uint64_t launches = 0;
+};
+
+static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
+{
+    if (batch <= s.cap) return 0;
+    cudaFree(s.pt);
+    cudaFree(s.e);
+    cudaFree(s.u);
+    cudaFree(s.ctr);
+    cudaFree(s.ctr_a);
+    cudaFree(s.fail);
+    s.cap = 0;
+    CU(cudaMalloc(&s.pt, batch * c->n * sizeof(int64_t)));
+    CU(cudaMalloc(&s.e, batch * 2 * c->n));
+    CU(cudaMalloc(&s.u, batch * (c->n / 4)));
+    CU(cudaMalloc(&s.ctr, batch * sizeof(uint32_t)));
+    CU(cudaMalloc(&s.ctr_a, batch * sizeof(uint32_t)));
+    CU(cudaMalloc(&s.fail, batch * sizeof(int)));
+    s.cap = batch;
+    return 0;
+}
+
+static void free_scratch(Scratch &s)
+{
+    cudaFree(s.pt);
+    cudaFree(s.e);
+    cudaFree(s.u);
+    cudaFree(s.ctr);
+    cudaFree(s.ctr_a);
+    cudaFree(s.fail);
+    cudaFree(s.d_values);
+    cudaFree(s.d_seeds);
+    cudaFree(s.d_sseeds);
+    cudaFree(s.d_out);
+    cudaFreeHost(s.h_values);
+    cudaFreeHost(s.h_seeds);
+    cudaFreeHost(s.h_sseeds);
+    cudaFreeHost(s.h_out);
+    cudaFreeHost(s.h_fail);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    s = Scratch();
+}
+
+static int build_tables(seb_ctx *c)
+{
+    const size_t n = c->n;
+    // NTT roots, bit-reversed powers of psi in Shoup form (ntt.c:40-52, uintmodarith.h:293-297)
+    std::vector<uint2> roots(c->np * n);
+    for (size_t p = 0; p < c->np; p++)
+    {
+        const uint32_t q = c->primes[p], psi = c->psis[p];
+        uint32_t pw      = 1;
+        for (size_t i = 0; i < n; i++)
+        {
+            roots[p * n + bitrev(i, c->logn)] = make_uint2(pw, shoup(pw, q));
+            pw                                = mulmod(pw, psi, q);
+        }
+    }
+    CU(cudaMalloc(&c->d_roots, roots.size() * sizeof(uint2)));
+    CU(cudaMemcpy(c->d_roots, roots.data(), roots.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+
+    // IFFT twiddles from the host libm, same expression as fft.c:27-45 (+ conj at fft.c:129)
+    std::vector<double2> tw(n);
+    const size_t m = 2 * n;
+    tw[0]          = make_double2(1.0, 0.0);
+    for (size_t i = 1; i < n; i++)
+    {
+        const size_t k     = bitrev(i, c->logn) & (m - 1);
+        const double angle = 2 * M_PI * (double)k / (double)m;
+        tw[i]              = make_double2(cos(angle), -sin(angle));
+    }
+    CU(cudaMalloc(&c->d_tw, n * sizeof(double2)));
+    CU(cudaMemcpy(c->d_tw, tw.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+
+    // index map (ckks_common.c:32-68) inverted: position -> slot
+    std::vector<uint16_t> src(n);
+    uint64_t pos = 1;
+    for (size_t i = 0; i < n / 2; i++)
+    {
+        const size_t a            = (size_t)((pos - 1) / 2);
+        const size_t b            = n - 1 - a;
+        src[bitrev(a, c->logn)]   = (uint16_t)i;
+        src[bitrev(b, c->logn)]   = (uint16_t)i;
+        pos                       = (pos * 3) & (m - 1);
+    }
+    CU(cudaMalloc(&c->d_src_map, n * sizeof(uint16_t)));
+    CU(cudaMemcpy(c->d_src_map, src.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes, const uint32_t *psis,
+                               double scale, int asym, int device)
+{
+    int logn = 0;
+    while (((size_t)1 << logn) < n) logn++;
+    if (((size_t)1 << logn) != n || logn < 10 || logn > 14 || nprimes < 1 || nprimes > SEB_MAX_PRIMES)
+    {
+        fail(SE_ERR_INVALD_ARGUMENT, "unsupported parameters n=%zu nprimes=%zu", n, nprimes);
+        return nullptr;
+    }
+    seb_ctx *c = new seb_ctx();
+    c->n       = n;
+    c->np      = nprimes;
+    c->logn    = logn;
+    c->asym    = asym != 0;
+    if (primes)
+    {
+        for (size_t i = 0; i < nprimes; i++)
+        {
+            c->primes[i] = primes[i];
+            c->psis[i]   = psis ? psis[i] : default_psi(n, primes[i]);
+        }
+    }
+    else
+    {
+        if (!default_primes(n, nprimes, c->primes))
+        {
+            fail(SE_ERR_INVALD_ARGUMENT, "no default parameter set for n=%zu nprimes=%zu", n, nprimes);
+            delete c;
+            return nullptr;
+        }
+        for (size_t i = 0; i < nprimes; i++) c->psis[i] = default_psi(n, c->primes[i]);
+    }
+    for (size_t i = 0; i < nprimes; i++)
+    {
+        const uint32_t q = c->primes[i], psi = c->psis[i];
+        // q < 2^30 keeps lazy values below 2^32; psi^n = -1 makes psi a primitive 2n-th root
+        if (q < 3 || q >= (1u << 30) || psi == 0 || powmod(psi, n, q) != q - 1)
+        {
+            fail(SE_ERR_INVALD_ARGUMENT, "prime %u / root %u unusable for n=%zu", q, psi, n);
+            delete c;
+            return nullptr;
+        }
+        const uint64_t ratio = (uint64_t)(((unsigned __int128)1 << 64) / q);
+        c->mods.m[i]         = SebModulus{q, 2 * q, (uint32_t)ratio, (uint32_t)(ratio >> 32)};
+    }
+    // parameters.c:197-225: the default scale is tied to the degree
+    c->scale = scale > 0 ? scale : (n == 1024 ? 1048576.0 : 33554432.0);
+
+    auto bail = [&](const char *what, cudaError_t e) -> seb_ctx * {
+        fail(SE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        seb_destroy(c);
+        return nullptr;
+    };
+    cudaError_t e;
+    if (device >= 0 && (e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaGetDevice(&c->device)) != cudaSuccess) return bail("cudaGetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    c->stream = c->own_stream;
+    if ((e = seb_encode_configure(logn)) != cudaSuccess) return bail("encode kernel attributes", e);
+    if ((e = seb_encrypt_configure(logn)) != cudaSuccess) return bail("encrypt kernel attributes", e);
+    if (build_tables(c) != 0)
+    {
+        seb_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" void seb_destroy(seb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slot) free_scratch(s);
+    cudaFree(c->d_roots);
+    cudaFree(c->d_tw);
+    cudaFree(c->d_src_map);
+    cudaFree(c->d_pk0);
+    cudaFree(c->d_pk1);
+    cudaFree(c->d_ntt_s);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int seb_set_stream(seb_ctx *c, void *cuda_stream)
+{
+    if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+extern "C" size_t seb_degree(const seb_ctx *c) { return c ? c->n : 0; }
+extern "C" size_t seb_nprimes(const seb_ctx *c) { return c ? c->np : 0; }
+extern "C" double seb_scale(const seb_ctx *c) { return c ? c->scale : 0; }
+extern "C" uint32_t seb_prime(const seb_ctx *c, size_t i) { return (c && i < c->np) ? c->primes[i] : 0; }
+extern "C" uint64_t seb_launch_count(const seb_ctx *c) { return c ? c->launches : 0; }
+
+static int upload_shoup(seb_ctx *c, const uint32_t *host, uint2 **dst)
+{
+    std::vector<uint2> tab(c->np * c->n);
+    for (size_t p = 0; p < c->np; p++)
+        for (size_t i = 0; i < c->n; i++)
+        {
+            const uint32_t w = host[p * c->n + i];
+            if (w >= c->primes[p]) return fail(SE_ERR_INVALD_ARGUMENT, "key coefficient %u >= modulus", w);
+            tab[p * c->n + i] = make_uint2(w, shoup(w, c->primes[p]));
+        }
+    if (!*dst) CU(cudaMalloc(dst, tab.size() * sizeof(uint2)));
+    CU(cudaMemcpy(*dst, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int seb_set_public_key(seb_ctx *c, const uint32_t *pk0, const uint32_t *pk1)
+{
+    if (!c || !pk0 || !pk1) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(c->device));
+    int r = upload_shoup(c, pk0, &c->d_pk0);
+    if (r) return r;
+    r = upload_shoup(c, pk1, &c->d_pk1);
+    if (r) return r;
+    c->have_pk = true;
+    return 0;
+}
+
+// ntt(s) is the same for every ciphertext, so it is computed once here instead of per
+// encryption as the reference does (ckks_sym.c:254-268).
+extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
+{
+    if (!c || !sk) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->n;
+    std::vector<uint32_t> s(c->np * n);
+    for (size_t p = 0; p < c->np; p++)
+        for (size_t i = 0; i < n; i++)
+        {
+            const uint32_t t = (sk[i / 4] >> (6 - 2 * (i % 4))) & 3u;  // sample.c:89-96
+            if (t > 2) return fail(SE_ERR_INVALD_ARGUMENT, "secret key field %zu is not ternary", i);
+            s[p * n + i] = t == 0 ? c->primes[p] - 1 : t - 1;          // sample.c:98-116
+        }
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, s.size() * sizeof(uint32_t)));
+    CU(cudaMemcpy(d, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    cudaError_t e = seb_launch_ntt(c->logn, d, c->d_roots, c->mods, (int)c->np, c->np, c->stream);
+    c->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(s.data(), d, s.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SE_ERR_CUDA, "ntt(s): %s", cudaGetErrorString(e));
+    int r = upload_shoup(c, s.data(), &c->d_ntt_s);
+    if (r) return r;
+    c->have_sk = true;
+    return 0;
+}
+
+extern "C" int seb_reserve(seb_ctx *c, size_t batch)
+{
+    if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
+    CU(cudaSetDevice(c->device));
+    return ensure_scratch(c, c->slot[0], batch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level entry points
+// ---------------------------------------------------------------------------------------------
+static int check_vlen(seb_ctx *c, size_t vlen)
+{
+    if (vlen > c->n / 2) return fail(SE_ERR_INVALD_ARGUMENT, "vlen %zu exceeds n/2 = %zu", vlen, c->n / 2);
+    return 0;
+}
+
+static int run_encode(seb_ctx *c, const float *d_values, size_t vlen, size_t batch, int64_t *d_pt, int *d_fail,
+                      cudaStream_t st)
+{
+    CU(cudaMemsetAsync(d_fail, 0, batch * sizeof(int), st));
+    CU(seb_launch_encode(c->logn, d_values, vlen, (int)vlen, c->d_src_map, c->d_tw, c->scale / (double)c->n, d_pt,
+                         d_fail, (int)batch, st));
+    c->launches++;
+    return 0;
+}
+
+extern "C" int seb_encode_device(seb_ctx *c, const float *d_values, size_t vlen, size_t batch, int64_t *d_pt)
+{
+    if (!c || !d_values || !d_pt) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    int r = check_vlen(c, vlen);
+    if (r) return r;
+    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    c->last_batch = batch;
+    return run_encode(c, d_values, vlen, batch, d_pt, c->slot[0].fail, c->stream);
+}
+
+extern "C" int seb_sample_asym_device(seb_ctx *c, const uint8_t *d_seeds, size_t batch, uint8_t *d_u, int8_t *d_e,
+                                      uint32_t *d_ctr)
+{
+    if (!c || !d_seeds || !d_u || !d_e || !d_ctr) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    seb_launch_sample_ternary(d_seeds, d_u, d_ctr, (int)c->n, (int)batch, c->stream);
+    seb_launch_sample_cbd(d_seeds, d_ctr, d_e, (int)c->n, 2, (int)batch, c->stream);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int seb_sample_cbd_device(seb_ctx *c, const uint8_t *d_seeds, const uint32_t *d_ctr, size_t npoly,
+                                     size_t batch, int8_t *d_e)
+{
+    if (!c || !d_seeds || !d_e) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    seb_launch_sample_cbd(d_seeds, d_ctr, d_e, (int)c->n, (int)npoly, (int)batch, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int seb_sample_uniform_device(seb_ctx *c, const uint8_t *d_seeds, uint32_t *d_ctr, size_t prime_idx,
+                                         size_t batch, uint32_t *d_out, size_t ct_stride)
+{
+    if (!c || !d_seeds || !d_ctr || !d_out || prime_idx >= c->np)
+        return fail(SE_ERR_INVALD_ARGUMENT, "bad argument");
+    seb_launch_uniform(d_seeds, d_ctr, d_out, ct_stride, (int)c->n, c->mods.m[prime_idx], (int)batch, c->stream);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int seb_ntt_device(seb_ctx *c, uint32_t *d_polys, size_t batch)
+{
+    if (!c || !d_polys) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(seb_launch_ntt(c->logn, d_polys, c->d_roots, c->mods, (int)c->np, batch * c->np, c->stream));
+    c->launches++;
+    return 0;
+}
+
+extern "C" int seb_prng_blocks_device(seb_ctx *c, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
+                                      uint64_t *d_out)
+{
+    if (!c || !d_seeds || !d_counters || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    seb_launch_prng_blocks(d_seeds, d_counters, d_out, (int)count, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// full path, device pointers
+// ---------------------------------------------------------------------------------------------
+// seal_embedded.c:98-215 (asymmetric branch) for a batch: encode, sample u/e0/e1, then one fused
+// kernel per (ciphertext, prime).
+static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t vlen, const uint8_t *d_seeds,
+                           size_t batch, uint32_t *d_out, cudaStream_t st)
+{
+    const int n = (int)c->n;
+    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
+    if (r) return r;
+    seb_launch_sample_ternary(d_seeds, s.u, s.ctr, n, (int)batch, st);
+    seb_launch_sample_cbd(d_seeds, s.ctr, s.e, n, 2, (int)batch, st);
+    CU(cudaGetLastError());
+    CU(seb_launch_encrypt_asym(c->logn, s.pt, s.e, s.u, c->d_roots, c->d_pk0, c->d_pk1, c->mods, (int)c->np, d_out,
+                               (int)batch, st));
+    c->launches += 3;
+    return 0;
+}
+
+// seal_embedded.c:98-215 (symmetric branch): encode, e, then per prime sample a (the shareable
+// PRNG's counter runs on across primes, ckks_sym.c:219), then the fused c0 kernel.
+static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
+                          const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk, cudaStream_t st)
+{
+    const int n = (int)c->n;
+    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
+    if (r) return r;
+    seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
+    CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
+    const size_t ct_stride = 2 * c->np * c->n;
+    for (size_t p = 0; p < c->np; p++)
+        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch, st);
+    CU(cudaGetLastError());
+    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,
+                              (int)batch, st));
+    c->launches += 2 + 2 * c->np;
+    return 0;
+}
+
+extern "C" int seb_encrypt_asym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_seeds,
+                                       size_t batch, uint32_t *d_out)
+{
+    if (!c || !d_values || !d_seeds || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (!c->have_pk) return fail(SE_ERR_NO_KEY, "no public key loaded");
+    int r = check_vlen(c, vlen);
+    if (r) return r;
+    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    c->last_batch = batch;
+    return encrypt_asym_on(c, c->slot[0], d_values, vlen, d_seeds, batch, d_out, c->stream);
+}
+
+extern "C" int seb_encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
+                                      const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk)
+{
+    if (!c || !d_values || !d_seeds || !d_sseeds || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (!c->have_sk) return fail(SE_ERR_NO_KEY, "no secret key loaded");
+    int r = check_vlen(c, vlen);
+    if (r) return r;
+    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    c->last_batch = batch;
+    return encrypt_sym_on(c, c->slot[0], d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, c->stream);
+}
+
+extern "C" int seb_encode_failures(seb_ctx *c)
+{
+    if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    if (!c->last_batch) return 0;
+    std::vector<int> f(c->last_batch);
+    CU(cudaMemcpy(f.data(), c->slot[0].fail, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int v : f) bad += v != 0;
+    return bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// full path, host pointers: two chunks in flight, each on its own stream, so the H2D of chunk
+// k+1 and the D2H of chunk k-1 overlap the kernels of chunk k.  Pinned caller buffers are used
+// in place; pageable ones are staged through pinned bounce buffers.
+// ---------------------------------------------------------------------------------------------
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static size_t host_chunk(const seb_ctx *c)
+{
+    // ~64 MiB of ciphertext per chunk keeps the copy engines busy without hoarding pinned memory
+    const size_t per_ct = 2 * c->np * c->n * sizeof(uint32_t);
+    size_t chunk        = (64u << 20) / per_ct;
+    return chunk < 16 ? 16 : chunk;
+}
+
+static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym)
+{
+    if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (chunk <= s.io_cap && (!sym || s.d_sseeds)) return 0;
+    cudaFree(s.d_values);
+    cudaFree(s.d_seeds);
+    cudaFree(s.d_sseeds);
+    cudaFree(s.d_out);
+    cudaFreeHost(s.h_values);
+    cudaFreeHost(s.h_seeds);
+    cudaFreeHost(s.h_sseeds);
+    cudaFreeHost(s.h_out);
+    cudaFreeHost(s.h_fail);
+    s.io_cap            = 0;
+    const size_t out_b  = chunk * 2 * c->np * c->n * sizeof(uint32_t);
+    CU(cudaMalloc(&s.d_values, chunk * (c->n / 2) * sizeof(float)));
+    CU(cudaMalloc(&s.d_seeds, chunk * SEB_SEED_BYTES));
+    CU(cudaMalloc(&s.d_sseeds, chunk * SEB_SEED_BYTES));
+    CU(cudaMalloc(&s.d_out, out_b));
+    CU(cudaMallocHost(&s.h_values, chunk * (c->n / 2) * sizeof(float)));
+    CU(cudaMallocHost(&s.h_seeds, chunk * SEB_SEED_BYTES));
+    CU(cudaMallocHost(&s.h_sseeds, chunk * SEB_SEED_BYTES));
+    CU(cudaMallocHost(&s.h_out, out_b));
+    CU(cudaMallocHost(&s.h_fail, chunk * sizeof(int)));
+    s.io_cap = chunk;
+    return 0;
+}
+
+static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, const uint8_t *sseeds,
+                        const uint8_t *seeds, size_t batch, uint32_t *out, int quirk)
+{
+    if (!c || !values || !seeds || !out || (sym && !sseeds)) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (sym ? !c->have_sk : !c->have_pk) return fail(SE_ERR_NO_KEY, "key material not loaded");
+    int r = check_vlen(c, vlen);
+    if (r) return r;
+    CU(cudaSetDevice(c->device));
+    const size_t chunk  = host_chunk(c) < batch ? host_chunk(c) : batch;
+    const size_t per_ct = 2 * c->np * c->n;
+    const bool pin_in   = is_pinned(values) && is_pinned(seeds) && (!sym || is_pinned(sseeds));
+    const bool pin_out  = is_pinned(out);
+    for (auto &s : c->slot)
+    {
+        if ((r = ensure_scratch(c, s, chunk))) return r;
+        if ((r = ensure_io(c, s, chunk, sym))) return r;
+    }
+    struct Pending
+    {
+        size_t first = 0, count = 0;
+        bool live = false;
+    } pend[2];
+    int failures = 0;
+
+    auto drain = [&](int k) -> int {
+        if (!pend[k].live) return 0;
+        Scratch &s = c->slot[k];
+        CU(cudaEventSynchronize(s.done));
+        if (!pin_out) memcpy(out + pend[k].first * per_ct, s.h_out, pend[k].count * per_ct * sizeof(uint32_t));
+        for (size_t i = 0; i < pend[k].count; i++) failures += s.h_fail[i] != 0;
+        pend[k].live = false;
+        return 0;
+    };
+
+    int k = 0;
+    for (size_t first = 0; first < batch; first += chunk, k ^= 1)
+    {
+        const size_t count = batch - first < chunk ? batch - first : chunk;
+        Scratch &s         = c->slot[k];
+        if ((r = drain(k))) return r;
+        const float *hv    = values + first * vlen;
+        const uint8_t *hs  = seeds + first * SEB_SEED_BYTES;
+        const uint8_t *hss = sym ? sseeds + first * SEB_SEED_BYTES : nullptr;
+        if (!pin_in)
+        {
+            memcpy(s.h_values, hv, count * vlen * sizeof(float));
+            memcpy(s.h_seeds, hs, count * SEB_SEED_BYTES);
+            if (sym) memcpy(s.h_sseeds, hss, count * SEB_SEED_BYTES);
+            hv  = s.h_values;
+            hs  = s.h_seeds;
+            hss = s.h_sseeds;
+        }
+        CU(cudaMemcpyAsync(s.d_values, hv, count * vlen * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_seeds, hs, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
+        if (sym) CU(cudaMemcpyAsync(s.d_sseeds, hss, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
+        r = sym ? encrypt_sym_on(c, s, s.d_values, vlen, s.d_sseeds, s.d_seeds, count, s.d_out, quirk, s.stream)
+                : encrypt_asym_on(c, s, s.d_values, vlen, s.d_seeds, count, s.d_out, s.stream);
+        if (r) return r;
+        uint32_t *ho = pin_out ? out + first * per_ct : s.h_out;
+        CU(cudaMemcpyAsync(ho, s.d_out, count * per_ct * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_fail, s.fail, count * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        pend[k].first = first;
+        pend[k].count = count;
+        pend[k].live  = true;
+    }
+    if ((r = drain(0))) return r;
+    if ((r = drain(1))) return r;
+    if (failures) return fail(SE_ERR_ENCODE_RANGE, "%d of %zu items exceed the int64 range when encoded", failures, batch);
+    return 0;
+}
+
+extern "C" int seb_encrypt_asym_host(seb_ctx *c, const float *values, size_t vlen, const uint8_t *seeds,
+                                     size_t batch, uint32_t *out)
+{
+    return encrypt_host(c, false, values, vlen, nullptr, seeds, batch, out, 0);
+}
+
+extern "C" int seb_encrypt_sym_host(seb_ctx *c, const float *values, size_t vlen, const uint8_t *sseeds,
+                                    const uint8_t *seeds, size_t batch, uint32_t *out, int quirk)
+{
+    return encrypt_host(c, true, values, vlen, sseeds, seeds, batch, out, quirk);
+}

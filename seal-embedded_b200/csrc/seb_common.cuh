@@ -1,0 +1,117 @@
+// seb_common.cuh — shared device helpers for the B200 CKKS encode+encrypt path.
+//
+// Limbs are 32-bit with 64-bit products, as in the reference (device/lib/defines.h:365-379);
+// primes are < 2^30 so lazy values in [0,4q) fit a word (device/lib/uintmodarith.h:293-331).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Host shims: the per-thread device functions in these headers are also compiled with plain g++
+// by tests/host_emul (a sequential emulation used by the CPU test-suite to check index math and
+// bit tricks without a GPU).  Under nvcc none of this is active.
+#ifndef __CUDACC__
+#include <algorithm>
+#include <cstring>
+#ifndef __forceinline__
+#define __forceinline__ inline
+#endif
+#define SEB_HOST_EMUL 1
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s)
+{
+    s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline uint32_t __vcmpgeu4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 0xFF) >= ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
+    return r;
+}
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+static inline void __syncthreads() {}
+using std::min;
+#define SEB_CONSTANT static const
+#else
+#define SEB_CONSTANT __constant__
+#endif
+
+#define SEB_MAX_PRIMES 13
+#define SEB_SEED_BYTES 64
+
+// one RNS prime with the constants the kernels need
+struct SebModulus
+{
+    uint32_t q;         // prime value (device/lib/modulus.h:22-30 `value`)
+    uint32_t two_q;     // 2q
+    uint32_t ratio_lo;  // floor(2^64/q) low word  (const_ratio[0], device/lib/modulus.c:30-47)
+    uint32_t ratio_hi;  // floor(2^64/q) high word (const_ratio[1])
+};
+
+// ---------------------------------------------------------------------------------------------
+// modular arithmetic
+// ---------------------------------------------------------------------------------------------
+// one conditional subtraction (device/lib/modulo.h:21-32 shift_result), branch-free
+__device__ __forceinline__ uint32_t seb_csub(uint32_t x, uint32_t q)
+{
+    return min(x, x - q);  // x - q wraps above x when x < q
+}
+
+// Shoup / "MUMO" lazy product (device/lib/uintmodarith.h:308-331): w < q, wq = floor(w*2^32/q);
+// result in [0,2q) for ANY 32-bit x.
+__device__ __forceinline__ uint32_t seb_mul_shoup_lazy(uint32_t x, uint32_t w, uint32_t wq, uint32_t q)
+{
+    return x * w - __umulhi(x, wq) * q;
+}
+
+// exact x mod q for a 64-bit x (device/lib/modulo.h:84-116): t = floor(x*floor(2^64/q)/2^64),
+// r = lo32(x) - lo32(t)*q, one correction.
+__device__ __forceinline__ uint32_t seb_barrett64(uint64_t x, const SebModulus &m)
+{
+    const uint64_t ratio = ((uint64_t)m.ratio_hi << 32) | m.ratio_lo;
+    const uint32_t t     = (uint32_t)__umul64hi(x, ratio);
+    return seb_csub((uint32_t)x - t * m.q, m.q);
+}
+
+// 32-bit input variant (device/lib/modulo.h:43-75)
+__device__ __forceinline__ uint32_t seb_barrett32(uint32_t x, const SebModulus &m)
+{
+    const uint32_t t = __umulhi(x, m.ratio_hi);
+    return seb_csub(x - t * m.q, m.q);
+}
+
+// [0,4q) -> [0,q) (device/lib/ntt.c:176-185)
+__device__ __forceinline__ uint32_t seb_final_reduce(uint32_t x, uint32_t q, uint32_t two_q)
+{
+    return seb_csub(seb_csub(x, two_q), q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cache-hinted global accesses for streamed (touched-once) data
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 seb_ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t seb_ldg_stream(const uint32_t *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void seb_stg_stream(uint4 *p, const uint4 &v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}

@@ -1,0 +1,154 @@
+// seb_encode.cu — CKKS encode: fp32 slots -> scatter -> FP64 inverse FFT -> scale -> round -> int64.
+//
+// Restates ckks_encode_base (device/lib/ckks_common.c:105-215) with ifft_inpl
+// (device/lib/fft.c:69-144) for a batch, one CTA (or, for n = 16384, one 2-CTA cluster) per
+// ciphertext with the whole complex vector in shared memory.
+//
+// Bit-exactness rules (SURVEY.md §7 "Bit-exact FP64 encode"):
+//   * every FP64 operation is individually rounded (__dadd_rn/__dsub_rn/__dmul_rn, never an FMA)
+//     and the complex product is re = a*c - b*d, im = a*d + b*c, the order GCC emits for C99
+//     complex multiplication on x86-64 without -ffast-math;
+//   * twiddles are the host libm's cos/sin (table built once in seb_api.cu with the reference's own
+//     expression, fft.c:27-45), not CUDA's;
+//   * radix-8 passes are three fused radix-2 stages, never a re-associated butterfly;
+//   * C round() (half away from zero) and the x86 cvttsd2si result for out-of-range values.
+#include <cooperative_groups.h>
+
+#include "seb_kernels.h"
+
+namespace cg = cooperative_groups;
+
+#include "seb_encode.cuh"
+
+template <int LOGN, int CL>
+__global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
+    k_encode(const float *__restrict__ values, size_t v_stride, int vlen, const uint16_t *__restrict__ src_map,
+             const double2 *__restrict__ tw, double n_inv, int64_t *__restrict__ pt, int *__restrict__ fail)
+{
+    constexpr int N     = 1 << LOGN;
+    constexpr int NL    = N / CL;
+    constexpr int LOGNL = (CL == 2) ? LOGN - 1 : LOGN;
+    constexpr int T     = NL / ENC_E;
+    constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
+    constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
+    extern __shared__ double esm[];
+    double *sre = esm;
+    double *sim = esm + NL;
+
+    const int t            = threadIdx.x;
+    const size_t b         = blockIdx.x / CL;
+    const uint32_t rank    = blockIdx.x % CL;
+    const uint32_t pos0    = rank * NL;
+    const float *vals      = values + b * v_stride;
+    int64_t *dst           = pt + b * N;
+    int bad                = 0;
+
+    double xr[ENC_E], xi[ENC_E];
+    EncRun<LOGN, LOGNL, 0>::run(xr, xi, sre, sim, t, pos0, vals, vlen, src_map, tw);
+
+    if (CL == 1)
+    {
+#pragma unroll
+        for (int i = 0; i < (ENC_E >> RL); i++)
+        {
+            const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
+            const uint32_t off  = g & ((1u << LSL) - 1u);
+            const uint32_t base = ((g >> LSL) << (LSL + RL)) | off;
+#pragma unroll
+            for (int j = 0; j < (1 << RL); j++)
+                dst[base | ((uint32_t)j << LSL)] = enc_finish(xr[i * (1 << RL) + j], n_inv, bad);
+        }
+    }
+    else
+    {
+        // n = 16384: each CTA of the pair holds one half after 13 local stages; the last stage
+        // (tt = n/2, twiddle index 1) pairs element k of rank 0 with element k of rank 1 through
+        // distributed shared memory.  Only real parts are needed afterwards.
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int i = 0; i < (ENC_E >> RL); i++)
+        {
+            const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
+            const uint32_t off  = g & ((1u << LSL) - 1u);
+            const uint32_t base = ((g >> LSL) << (LSL + RL)) | off;
+#pragma unroll
+            for (int j = 0; j < (1 << RL); j++)
+            {
+                const uint32_t pos = base | ((uint32_t)j << LSL);
+                sre[enc_swz(pos)]  = xr[i * (1 << RL) + j];
+                sim[enc_swz(pos)]  = xi[i * (1 << RL) + j];
+            }
+        }
+        cluster.sync();
+        const double *ore = cluster.map_shared_rank(sre, rank ^ 1u);
+        const double *oim = cluster.map_shared_rank(sim, rank ^ 1u);
+        const double2 s   = __ldg(tw + 1);
+        for (uint32_t k = t; k < (uint32_t)NL; k += T)
+        {
+            const uint32_t sk = enc_swz(k);
+            const double re = enc_cross_re(rank, sre[sk], sim[sk], ore[sk], rank ? oim[sk] : 0.0, s);
+            dst[pos0 + k] = enc_finish(re, n_inv, bad);
+        }
+        cluster.sync();  // partner may still be reading our shared memory
+    }
+    if (bad) fail[b] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int LOGN, int CL>
+static cudaError_t encode_cfg()
+{
+    return cudaFuncSetAttribute(k_encode<LOGN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(double) * 2 * ((1 << LOGN) / CL)));
+}
+
+cudaError_t seb_encode_configure(int logn)
+{
+    switch (logn)
+    {
+        case 10: return encode_cfg<10, 1>();
+        case 11: return encode_cfg<11, 1>();
+        case 12: return encode_cfg<12, 1>();
+        case 13: return encode_cfg<13, 1>();
+        case 14: return encode_cfg<14, 2>();
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int LOGN, int CL>
+static cudaError_t encode_launch(const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
+                                 const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                                 cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3((unsigned)batch * CL);
+    cfg.blockDim           = dim3((1 << LOGN) / CL / ENC_E);
+    cfg.dynamicSmemBytes   = sizeof(double) * 2 * ((1 << LOGN) / CL);
+    cfg.stream             = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs                = attr;
+    cfg.numAttrs             = 1;
+    return cudaLaunchKernelEx(&cfg, k_encode<LOGN, CL>, values, v_stride, vlen, src_map, tw, n_inv, pt, fail);
+}
+
+cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
+                              const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                              cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+    switch (logn)
+    {
+        case 10: return encode_launch<10, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        case 11: return encode_launch<11, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        case 12: return encode_launch<12, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        case 13: return encode_launch<13, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        case 14: return encode_launch<14, 2>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        default: return cudaErrorInvalidValue;
+    }
+}

@@ -1,0 +1,138 @@
+// seb_encode.cuh — per-thread pieces of the CKKS encode (FP64 inverse FFT), shared by the kernel
+// in seb_encode.cu and by the g++ host emulation in tests/host_emul.
+#pragma once
+
+#include "seb_common.cuh"
+
+#ifndef __CUDACC__
+#include <cmath>
+// host emulation: plain IEEE double ops (compiled with -ffp-contract=off)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+#endif
+
+#define ENC_E 8  // complex values per thread
+
+__host__ __device__ constexpr int enc_npass(int lognl) { return (lognl + 2) / 3; }
+__host__ __device__ constexpr int enc_r(int lognl, int p) { return (lognl - 3 * p) >= 3 ? 3 : (lognl - 3 * p); }
+
+// bank swizzle for the double-precision re[]/im[] arrays (index in elements)
+__device__ __forceinline__ uint32_t enc_swz(uint32_t i)
+{
+    return i ^ ((i >> 4) & 7u) ^ (((i >> 6) & 1u) << 3);
+}
+
+// one pass = R fused Gentleman-Sande stages starting at butterfly distance S = 2^LS
+// (fft.c:119-143: vec[k] = u + v; vec[k+tt] = (u - v) * s)
+template <int LOGN, int LOGNL, int P>
+__device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E], double *sre, double *sim,
+                                         const int t, const uint32_t cta_pos0, const float *__restrict__ vals,
+                                         const int vlen, const uint16_t *__restrict__ src_map,
+                                         const double2 *__restrict__ tw)
+{
+    constexpr int NL   = 1 << LOGNL;
+    constexpr int T    = NL / ENC_E;
+    constexpr int R    = enc_r(LOGNL, P);
+    constexpr int LS   = 3 * P;
+    constexpr int GP   = ENC_E >> R;
+    constexpr bool LAST = (P == enc_npass(LOGNL) - 1);
+
+#pragma unroll
+    for (int i = 0; i < GP; i++)
+    {
+        const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
+        const uint32_t off  = g & ((1u << LS) - 1u);
+        const uint32_t blk  = g >> LS;
+        const uint32_t base = (blk << (LS + R)) | off;  // local position of element j = 0
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++)
+        {
+            const uint32_t pos = base | ((uint32_t)j << LS);
+            if (P == 0)
+            {
+                // scatter (ckks_common.c:139-153) done as a gather: both conjugate slots get values[i]
+                const uint32_t slot      = __ldg(src_map + cta_pos0 + pos);
+                xr[i * (1 << R) + j] = (int)slot < vlen ? (double)__ldg(vals + slot) : 0.0;
+                xi[i * (1 << R) + j] = 0.0;
+            }
+            else
+            {
+                xr[i * (1 << R) + j] = sre[enc_swz(pos)];
+                xi[i * (1 << R) + j] = sim[enc_swz(pos)];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            // stage with tt = 2^(LS+r): group index of global position p is p >> (LS+r+1)
+            const uint32_t h     = 1u << (LOGN - LS - r - 1);
+            const uint32_t jbase = (cta_pos0 >> (LS + r + 1)) + (blk << (R - r - 1));
+#pragma unroll
+            for (int m = 0; m < (1 << (R - r - 1)); m++)
+            {
+                const double2 s = __ldg(tw + h + jbase + m);
+#pragma unroll
+                for (int k = 0; k < (1 << r); k++)
+                {
+                    const int ia    = i * (1 << R) + (m << (r + 1)) + k;
+                    const int ib    = ia + (1 << r);
+                    const double ur = xr[ia], ui = xi[ia], vr = xr[ib], vi = xi[ib];
+                    const double dr = __dsub_rn(ur, vr), di = __dsub_rn(ui, vi);
+                    xr[ia]          = __dadd_rn(ur, vr);
+                    xi[ia]          = __dadd_rn(ui, vi);
+                    xr[ib]          = __dsub_rn(__dmul_rn(dr, s.x), __dmul_rn(di, s.y));
+                    xi[ib]          = __dadd_rn(__dmul_rn(dr, s.y), __dmul_rn(di, s.x));
+                }
+            }
+        }
+        if (!LAST)
+        {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
+            {
+                const uint32_t pos = base | ((uint32_t)j << LS);
+                sre[enc_swz(pos)]  = xr[i * (1 << R) + j];
+                sim[enc_swz(pos)]  = xi[i * (1 << R) + j];
+            }
+        }
+    }
+}
+
+template <int LOGN, int LOGNL, int P>
+struct EncRun
+{
+    __device__ __forceinline__ static void run(double (&xr)[ENC_E], double (&xi)[ENC_E], double *sre, double *sim,
+                                               int t, uint32_t cta_pos0, const float *vals, int vlen,
+                                               const uint16_t *src_map, const double2 *tw)
+    {
+        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, cta_pos0, vals, vlen, src_map, tw);
+        if (P + 1 < enc_npass(LOGNL))
+        {
+            __syncthreads();
+            EncRun<LOGN, LOGNL, (P + 1 < enc_npass(LOGNL) ? P + 1 : P)>::run(xr, xi, sre, sim, t, cta_pos0, vals,
+                                                                             vlen, src_map, tw);
+        }
+    }
+};
+
+// coeff = round(Re * scale/n); |coeff| > 2^63 fails the encode; the int64 conversion follows x86
+// (ckks_common.c:183-206)
+__device__ __forceinline__ int64_t enc_finish(double re, double n_inv, int &bad)
+{
+    const double c = round(__dmul_rn(re, n_inv));
+    if (fabs(c) > 9223372036854775808.0) bad = 1;
+    if (!(c < 9223372036854775808.0)) return (int64_t)0x8000000000000000ULL;  // NaN / 2^63: "indefinite"
+    return (int64_t)c;
+}
+
+
+// Last stage of the n = 16384 transform (tt = n/2, one group, twiddle index 1), real part only:
+// rank 0 owns element k (u), rank 1 owns element k + n/2 (v).  fft.c:134-141.
+__device__ __forceinline__ double enc_cross_re(uint32_t rank, double own_re, double own_im, double oth_re,
+                                               double oth_im, const double2 s)
+{
+    if (rank == 0) return __dadd_rn(own_re, oth_re);  // Re(u + v)
+    const double dr = __dsub_rn(oth_re, own_re), di = __dsub_rn(oth_im, own_im);  // u - v
+    return __dsub_rn(__dmul_rn(dr, s.x), __dmul_rn(di, s.y));                      // Re((u - v) * s)
+}

@@ -1,0 +1,291 @@
+// seb_encrypt.cu — batched RNS NTT and the fused per-(ciphertext, prime) encrypt kernels.
+//
+//   k_ntt_forward   : ntt_inpl (device/lib/ntt.c:168-189) over a batch of [np][n] polynomials
+//   k_encrypt_asym  : one prime of ckks_encode_encrypt_asym (device/lib/ckks_asym.c:205-286):
+//                     expand u / reduce e1 / reduce (m+e0) on load, three NTTs through shared
+//                     memory sharing every twiddle fetch, then
+//                       c1 = pk1 (.) ntt(u) + ntt(e1),  c0 = pk0 (.) ntt(u) + ntt(m+e0)
+//                     straight from registers with 128-bit stores.
+//   k_encrypt_sym   : one prime of ckks_encode_encrypt_sym (device/lib/ckks_sym.c:199-301) with
+//                     ntt(s) precomputed at setup:  c0 = -(a (.) ntt(s)) + ntt(m+e)
+//
+// One CTA of n/16 threads per polynomial slot; blockIdx.x = ciphertext*np + prime so the CTAs that
+// re-read one ciphertext's m/e/u are scheduled together and hit L2.
+#include "seb_kernels.h"
+#include "seb_ntt.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// on-load conversions (all produce values the lazy butterflies accept, i.e. < 4q)
+// ---------------------------------------------------------------------------------------------
+// 2-bit field -> {q-1, 0, 1} (device/lib/sample.c:98-116)
+__device__ __forceinline__ uint32_t expand_ternary(const uint8_t *__restrict__ u, uint32_t pos, uint32_t q)
+{
+    const uint32_t byte = __ldg(u + (pos >> 2));
+    const uint32_t t    = (byte >> (6 - 2 * (pos & 3))) & 3u;
+    return t == 0 ? q - 1 : t - 1;
+}
+// small signed -> [0,q) (device/lib/ckks_common.c:259-265)
+__device__ __forceinline__ uint32_t reduce_small(const int8_t *__restrict__ e, uint32_t pos, uint32_t q)
+{
+    const int v = __ldg(e + pos);
+    return v < 0 ? q + (uint32_t)v : (uint32_t)v;
+}
+// (m + e) int64 -> |x| mod q, q - r for negatives (device/lib/ckks_common.c:224-245)
+__device__ __forceinline__ uint32_t reduce_pte(const int64_t *__restrict__ pt, const int8_t *__restrict__ e,
+                                               uint32_t pos, const SebModulus &m)
+{
+    const uint64_t x  = (uint64_t)__ldg(pt + pos) + (uint64_t)(int64_t)__ldg(e + pos);
+    const bool neg    = (int64_t)x < 0;
+    const uint64_t ax = neg ? (uint64_t)0 - x : x;
+    const uint32_t r  = seb_barrett64(ax, m);
+    return neg ? m.q - r : r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NTT only
+// ---------------------------------------------------------------------------------------------
+struct LoadPlain
+{
+    const uint32_t *src;
+    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return seb_ldg_stream(src + pos); }
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E) k_ntt_forward(uint32_t *__restrict__ polys,
+                                                                     const uint2 *__restrict__ roots,
+                                                                     const __grid_constant__ SebModuli mods,
+                                                                     int np)
+{
+    constexpr int N = 1 << LOGN;
+    extern __shared__ uint32_t smem[];
+    const int t         = threadIdx.x;
+    const size_t poly   = blockIdx.x;
+    const int p         = (int)(poly % (size_t)np);
+    const SebModulus &m = mods.m[p];
+    uint32_t *data      = polys + poly * N;
+
+    uint32_t x[1][SEB_E];
+    LoadPlain ld{data};
+    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+
+    using O = NttOut<LOGN>;
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(data + O::pos(t, i));
+#pragma unroll
+        for (int k = 0; k < O::RUN / 4; k++)
+        {
+            uint4 v;
+            v.x = seb_final_reduce(x[0][i * O::RUN + 4 * k + 0], m.q, m.two_q);
+            v.y = seb_final_reduce(x[0][i * O::RUN + 4 * k + 1], m.q, m.two_q);
+            v.z = seb_final_reduce(x[0][i * O::RUN + 4 * k + 2], m.q, m.two_q);
+            v.w = seb_final_reduce(x[0][i * O::RUN + 4 * k + 3], m.q, m.two_q);
+            seb_stg_stream(dst + k, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// asymmetric encrypt, one (ciphertext, prime)
+// ---------------------------------------------------------------------------------------------
+struct LoadAsym
+{
+    const uint8_t *u;
+    const int8_t *e0;
+    const int8_t *e1;
+    const int64_t *pt;
+    SebModulus m;
+    __device__ __forceinline__ uint32_t operator()(int p, uint32_t pos) const
+    {
+        if (p == 0) return expand_ternary(u, pos, m.q);
+        if (p == 1) return reduce_small(e1, pos, m.q);
+        return reduce_pte(pt, e0, pos, m);
+    }
+};
+
+// x*w mod q in [0,q) for a Shoup pair, then + y (y lazy in [0,4q)) mod q
+__device__ __forceinline__ uint32_t mul_add_final(uint32_t x, uint2 w, uint32_t y, uint32_t q, uint32_t two_q)
+{
+    const uint32_t prod = seb_csub(seb_mul_shoup_lazy(x, w.x, w.y, q), q);
+    return seb_csub(prod + seb_final_reduce(y, q, two_q), q);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E)
+    k_encrypt_asym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
+                   const uint2 *__restrict__ roots, const uint2 *__restrict__ pk0s,
+                   const uint2 *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
+                   uint32_t *__restrict__ out)
+{
+    constexpr int N = 1 << LOGN;
+    extern __shared__ uint32_t smem[];
+    const int t      = threadIdx.x;
+    const size_t b   = blockIdx.x / (unsigned)np;
+    const int p      = (int)(blockIdx.x % (unsigned)np);
+    const SebModulus m = mods.m[p];
+
+    LoadAsym ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
+    uint32_t x[3][SEB_E];
+    seb_ntt_forward<LOGN, 3>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+
+    using O          = NttOut<LOGN>;
+    uint32_t *c0     = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1     = c0 + N;
+    const uint2 *k0  = pk0s + (size_t)p * N;
+    const uint2 *k1  = pk1s + (size_t)p * N;
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+    {
+        const uint32_t pos0 = O::pos(t, i);
+#pragma unroll
+        for (int k = 0; k < O::RUN / 4; k++)
+        {
+            const uint32_t pos = pos0 + 4 * k;
+            const uint4 a0     = __ldg(reinterpret_cast<const uint4 *>(k0 + pos));
+            const uint4 a1     = __ldg(reinterpret_cast<const uint4 *>(k0 + pos + 2));
+            const uint4 b0     = __ldg(reinterpret_cast<const uint4 *>(k1 + pos));
+            const uint4 b1     = __ldg(reinterpret_cast<const uint4 *>(k1 + pos + 2));
+            const int r        = i * O::RUN + 4 * k;
+            uint4 v0, v1;
+            v0.x = mul_add_final(x[0][r + 0], make_uint2(a0.x, a0.y), x[2][r + 0], m.q, m.two_q);
+            v0.y = mul_add_final(x[0][r + 1], make_uint2(a0.z, a0.w), x[2][r + 1], m.q, m.two_q);
+            v0.z = mul_add_final(x[0][r + 2], make_uint2(a1.x, a1.y), x[2][r + 2], m.q, m.two_q);
+            v0.w = mul_add_final(x[0][r + 3], make_uint2(a1.z, a1.w), x[2][r + 3], m.q, m.two_q);
+            v1.x = mul_add_final(x[0][r + 0], make_uint2(b0.x, b0.y), x[1][r + 0], m.q, m.two_q);
+            v1.y = mul_add_final(x[0][r + 1], make_uint2(b0.z, b0.w), x[1][r + 1], m.q, m.two_q);
+            v1.z = mul_add_final(x[0][r + 2], make_uint2(b1.x, b1.y), x[1][r + 2], m.q, m.two_q);
+            v1.w = mul_add_final(x[0][r + 3], make_uint2(b1.z, b1.w), x[1][r + 3], m.q, m.two_q);
+            seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), v0);
+            seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), v1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// symmetric encrypt, one (ciphertext, prime)
+// ---------------------------------------------------------------------------------------------
+struct LoadSym
+{
+    const int8_t *e;
+    const int64_t *pt;
+    SebModulus m;
+    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return reduce_pte(pt, e, pos, m); }
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E)
+    k_encrypt_sym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint2 *__restrict__ roots,
+                  const uint2 *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
+                  uint32_t *__restrict__ out, int quirk)
+{
+    constexpr int N = 1 << LOGN;
+    extern __shared__ uint32_t smem[];
+    const int t        = threadIdx.x;
+    const size_t b     = blockIdx.x / (unsigned)np;
+    const int p        = (int)(blockIdx.x % (unsigned)np);
+    const SebModulus m = mods.m[p];
+
+    LoadSym ld{e + b * N, pt + b * N, m};
+    uint32_t x[1][SEB_E];
+    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+
+    using O         = NttOut<LOGN>;
+    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1    = c0 + N;
+    const uint2 *sk = ntt_s + (size_t)p * N;
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+    {
+        const uint32_t pos0 = O::pos(t, i);
+#pragma unroll
+        for (int k = 0; k < O::RUN / 4; k++)
+        {
+            const uint32_t pos = pos0 + 4 * k;
+            const uint4 a      = *reinterpret_cast<const uint4 *>(c1 + pos);
+            const uint4 s0     = __ldg(reinterpret_cast<const uint4 *>(sk + pos));
+            const uint4 s1     = __ldg(reinterpret_cast<const uint4 *>(sk + pos + 2));
+            const int r        = i * O::RUN + 4 * k;
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+            const uint2 sv[4]    = {make_uint2(s0.x, s0.y), make_uint2(s0.z, s0.w), make_uint2(s1.x, s1.y),
+                                    make_uint2(s1.z, s1.w)};
+            uint32_t cv[4], mv[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+            {
+                const uint32_t prod = seb_csub(seb_mul_shoup_lazy(av[c], sv[c].x, sv[c].y, m.q), m.q);
+                const uint32_t neg  = prod ? m.q - prod : 0u;  // poly_neg_mod (polymodarith.h:67-70)
+                mv[c]               = seb_final_reduce(x[0][r + c], m.q, m.two_q);
+                cv[c]               = seb_csub(neg + mv[c], m.q);
+            }
+            seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), make_uint4(cv[0], cv[1], cv[2], cv[3]));
+            if (quirk) seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), make_uint4(mv[0], mv[1], mv[2], mv[3]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+#define SEB_DISPATCH_LOGN(logn, CALL)      \
+    switch (logn)                          \
+    {                                      \
+        case 10: CALL(10); break;          \
+        case 11: CALL(11); break;          \
+        case 12: CALL(12); break;          \
+        case 13: CALL(13); break;          \
+        case 14: CALL(14); break;          \
+        default: return cudaErrorInvalidValue; \
+    }
+
+cudaError_t seb_encrypt_configure(int logn)
+{
+    cudaError_t err = cudaSuccess;
+#define CFG(L)                                                                                                    \
+    {                                                                                                             \
+        err = cudaFuncSetAttribute(k_ntt_forward<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << L);        \
+        if (err == cudaSuccess)                                                                                   \
+            err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 << L);  \
+        if (err == cudaSuccess)                                                                                   \
+            err = cudaFuncSetAttribute(k_encrypt_sym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << L);    \
+    }
+    SEB_DISPATCH_LOGN(logn, CFG)
+#undef CFG
+    return err;
+}
+
+cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const SebModuli &mods, int np,
+                           size_t npolys_total, cudaStream_t st)
+{
+    if (npolys_total == 0) return cudaSuccess;
+#define RUN(L) k_ntt_forward<L><<<(unsigned)npolys_total, (1 << L) / SEB_E, 4 << L, st>>>(polys, roots, mods, np)
+    SEB_DISPATCH_LOGN(logn, RUN)
+#undef RUN
+    return cudaGetLastError();
+}
+
+cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
+                                    const uint2 *roots, const uint2 *pk0s, const uint2 *pk1s,
+                                    const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+#define RUN(L)                                                                                            \
+    k_encrypt_asym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 << L, st>>>(pt, e, u, roots, pk0s, \
+                                                                                           pk1s, mods, np, out)
+    SEB_DISPATCH_LOGN(logn, RUN)
+#undef RUN
+    return cudaGetLastError();
+}
+
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const uint2 *roots,
+                                   const uint2 *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
+                                   int batch, cudaStream_t st)
+{
+    if (batch <= 0) return cudaSuccess;
+#define RUN(L)                                                                                              \
+    k_encrypt_sym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 4 << L, st>>>(pt, e, roots, ntt_s, mods, \
+                                                                                         np, out, quirk)
+    SEB_DISPATCH_LOGN(logn, RUN)
+#undef RUN
+    return cudaGetLastError();
+}

@@ -1,0 +1,47 @@
+// seb_kernels.h — launchers of the sm_100a kernels (internal; the public C ABI is
+// include/seal_embedded_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "seb_common.cuh"
+
+struct SebModuli
+{
+    SebModulus m[SEB_MAX_PRIMES];
+};
+
+// ---- samplers (seb_sample.cu) ----
+void seb_launch_prng_blocks(const uint8_t *seeds, const uint64_t *counters, uint64_t *out, int count,
+                            cudaStream_t st);
+void seb_launch_sample_ternary(const uint8_t *seeds, uint8_t *u_out, uint32_t *ctr_out, int n, int batch,
+                               cudaStream_t st);
+void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_t *e_out, int n, int npoly,
+                           int batch, cudaStream_t st);
+void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
+                        const SebModulus &mod, int batch, cudaStream_t st);
+
+// ---- encode (seb_encode.cu) ----
+// values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);
+// src_map[pos] = slot whose value lands on position pos; tw[i] = IFFT twiddle (re, im), i in [1,n)
+cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
+                              const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                              cudaStream_t st);
+cudaError_t seb_encode_configure(int logn);
+
+// ---- NTT + encrypt (seb_encrypt.cu) ----
+// roots: [np][n] {w, floor(w*2^32/q)} with w = psi^bitrev-order table (ntt.c:40-52)
+cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const SebModuli &mods, int np,
+                           size_t npolys_total, cudaStream_t st);
+// asym: out[b][p][0] = pk0 (.) ntt(u) + ntt(m+e0), out[b][p][1] = pk1 (.) ntt(u) + ntt(e1)
+cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
+                                    const uint2 *roots, const uint2 *pk0s, const uint2 *pk1s,
+                                    const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st);
+// sym: out[b][p][1] already holds a; out[b][p][0] = -(a (.) ntt(s)) + ntt(m+e);
+// quirk != 0 additionally overwrites out[b][p][1] with ntt(m+e) (reference byte stream)
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const uint2 *roots,
+                                   const uint2 *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
+                                   int batch, cudaStream_t st);
+cudaError_t seb_encrypt_configure(int logn);

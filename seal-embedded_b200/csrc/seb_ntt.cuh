@@ -1,0 +1,208 @@
+// seb_ntt.cuh — in-shared-memory negacyclic forward NTT over a 30-bit prime, register-blocked.
+//
+// Computes exactly what device/lib/ntt.c:124-189 (ntt_inpl) computes: Cooley-Tukey, natural
+// order in, bit-reversed order out, A[j] = a(psi^(2*bitrev(j)+1)), every output in [0,q).  Outputs
+// are canonical residues of an exact function, so the algorithm is free to differ: here stages are
+// fused 3 or 4 at a time in registers (radix-8/16), butterflies are Harvey lazy butterflies on
+// [0,4q) with Shoup twiddles {w, floor(w*2^32/q)} (the reference's own SE_NTT_FAST variant,
+// ntt.c:72-109, uintmodarith.h:308-331), and a final correction brings values to [0,q).
+//
+// Work decomposition for one polynomial of n = 2^LOGN coefficients:
+//   * T = n/16 threads, 16 coefficients per thread (SEB_E).
+//   * the log2(n) stages are split into passes of R in {3,4} stages (NttPlan<LOGN>); a pass of R
+//     stages with stride S = n >> (s0+R) works on groups {blk*(S<<R) + off + j*S, j < 2^R}; a thread
+//     owns 16 >> R such groups.  Between passes coefficients go through shared memory; the
+//     first pass takes its inputs from a loader functor (global memory / on-the-fly expansion)
+//     and the last pass, whose groups are 2^R contiguous coefficients, hands each thread its
+//     contiguous outputs so the caller can fuse its epilogue and issue 128-bit stores.
+//   * shared-memory words are XOR-swizzled (seb_swz) so every pass is bank-conflict free
+//     (checked exhaustively by tests/test_host_logic.py::test_swizzle_conflict_free).
+//   * NPOLY polynomials that share the modulus go through the passes together so each twiddle
+//     is fetched once for all of them.
+#pragma once
+
+#include "seb_common.cuh"
+
+#define SEB_E 16  // coefficients per thread
+
+template <int LOGN>
+struct NttPlan;
+template <>
+struct NttPlan<10>
+{
+    static constexpr int NPASS = 3;
+    static constexpr int R[4]  = {4, 3, 3, 0};
+};
+template <>
+struct NttPlan<11>
+{
+    static constexpr int NPASS = 3;
+    static constexpr int R[4]  = {4, 4, 3, 0};
+};
+template <>
+struct NttPlan<12>
+{
+    static constexpr int NPASS = 3;
+    static constexpr int R[4]  = {4, 4, 4, 0};
+};
+template <>
+struct NttPlan<13>
+{
+    static constexpr int NPASS = 4;
+    static constexpr int R[4]  = {4, 3, 3, 3};
+};
+template <>
+struct NttPlan<14>
+{
+    static constexpr int NPASS = 4;
+    static constexpr int R[4]  = {4, 4, 3, 3};
+};
+
+// stage offset of pass P
+template <int LOGN, int P>
+struct NttS0
+{
+    static constexpr int value = NttS0<LOGN, P - 1>::value + NttPlan<LOGN>::R[P - 1];
+};
+template <int LOGN>
+struct NttS0<LOGN, 0>
+{
+    static constexpr int value = 0;
+};
+
+// bank swizzle of a coefficient index (word address inside one polynomial's buffer)
+template <int LOGN>
+__host__ __device__ __forceinline__ uint32_t seb_swz(uint32_t a)
+{
+    if (LOGN == 12) return a ^ ((a >> 5) & 15u) ^ (((a >> 8) & 1u) << 4);
+    if (LOGN == 11) return a ^ ((a >> 5) & 7u) ^ (((a >> 7) & 3u) << 3);
+    return a ^ ((a >> 5) & 7u) ^ (((a >> 6) & 3u) << 3);
+}
+
+// Harvey lazy butterfly: X,Y in [0,4q) -> X+WY, X-WY in [0,4q) (ntt.c:94-105)
+__device__ __forceinline__ void seb_bfly(uint32_t &x, uint32_t &y, const uint2 w, const uint32_t q,
+                                         const uint32_t two_q)
+{
+    const uint32_t u = min(x, x - two_q);
+    const uint32_t t = seb_mul_shoup_lazy(y, w.x, w.y, q);
+    x                = u + t;
+    y                = u - t + two_q;
+}
+
+// R fused stages on NPOLY register groups of 2^R coefficients; tw points at the prime's table
+// roots[bitrev(i)] = psi^i (ntt.c:40-52) in Shoup form; twbase = (1 << s0) + blk for stage 0 of
+// the pass, each later stage doubles it.
+template <int R, int NPOLY>
+__device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], const int gofs,
+                                               const uint2 *__restrict__ tw, uint32_t twbase, const uint32_t q,
+                                               const uint32_t two_q)
+{
+#pragma unroll
+    for (int r = 0; r < R; r++)
+    {
+        const int half = 1 << (R - 1 - r);
+#pragma unroll
+        for (int m = 0; m < (1 << r); m++)
+        {
+            const uint2 w = __ldg(tw + ((twbase << r) + m));
+#pragma unroll
+            for (int t = 0; t < half; t++)
+            {
+                const int ia = gofs + m * 2 * half + t;
+                const int ib = ia + half;
+#pragma unroll
+                for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], w, q, two_q);
+            }
+        }
+    }
+}
+
+// One pass P of the plan.  FIRST: inputs come from load(p, pos); otherwise from smem.  LAST:
+// outputs stay in registers (x[p][i*2^R + j] = coefficient (g_i << R) + j, lazy [0,4q)) and the
+// caller finishes; otherwise they are written back to smem (same slots this thread read).
+template <int LOGN, int P, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+                                             const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                             Loader &load)
+{
+    constexpr int N     = 1 << LOGN;
+    constexpr int T     = N / SEB_E;
+    constexpr int R     = NttPlan<LOGN>::R[P];
+    constexpr int S0    = NttS0<LOGN, P>::value;
+    constexpr int LS    = LOGN - S0 - R;  // log2 stride
+    constexpr int GP    = SEB_E >> R;     // groups per thread
+    constexpr bool LAST = (P == NttPlan<LOGN>::NPASS - 1);
+
+#pragma unroll
+    for (int i = 0; i < GP; i++)
+    {
+        const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
+        const uint32_t off  = g & ((1u << LS) - 1u);
+        const uint32_t blk  = g >> LS;
+        const uint32_t base = (blk << (LS + R)) | off;
+#pragma unroll
+        for (int j = 0; j < (1 << R); j++)
+        {
+            const uint32_t pos = base | ((uint32_t)j << LS);
+#pragma unroll
+            for (int p = 0; p < NPOLY; p++)
+            {
+                if (P == 0)
+                    x[p][i * (1 << R) + j] = load(p, pos);
+                else
+                    x[p][i * (1 << R) + j] = smem[p * N + seb_swz<LOGN>(pos)];
+            }
+        }
+        seb_radix_regs<R, NPOLY>(x, i * (1 << R), tw, (1u << S0) + blk, q, two_q);
+        if (!LAST)
+        {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
+            {
+                const uint32_t pos = base | ((uint32_t)j << LS);
+#pragma unroll
+                for (int p = 0; p < NPOLY; p++) smem[p * N + seb_swz<LOGN>(pos)] = x[p][i * (1 << R) + j];
+            }
+        }
+    }
+}
+
+template <int LOGN, int P, int NPOLY, class Loader>
+struct SebNttRun
+{
+    __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+                                               const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                               Loader &load)
+    {
+        seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
+        if (P + 1 < NttPlan<LOGN>::NPASS)
+        {
+            __syncthreads();
+            SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
+                                                                                              load);
+        }
+    }
+};
+
+// Full forward NTT of NPOLY polynomials sharing one modulus, executed by the T = n/16 threads
+// t = 0..T-1 that share `smem` (NPOLY*n words).  On return thread t holds, for each of its
+// GPL = 16 >> R_last groups i, the 2^R_last contiguous coefficients starting at
+// seb_ntt_out_pos<LOGN>(t, i), still lazy in [0,4q).  All T threads must call (barriers inside).
+// The caller must __syncthreads() before smem is reused.
+template <int LOGN, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_forward(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+                                                const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                                Loader &load)
+{
+    SebNttRun<LOGN, 0, NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
+}
+
+template <int LOGN>
+struct NttOut
+{
+    static constexpr int RL  = NttPlan<LOGN>::R[NttPlan<LOGN>::NPASS - 1];
+    static constexpr int GPL = SEB_E >> RL;   // contiguous runs per thread
+    static constexpr int RUN = 1 << RL;       // coefficients per run
+    static constexpr int T   = (1 << LOGN) / SEB_E;
+    __device__ __forceinline__ static uint32_t pos(int t, int i) { return ((uint32_t)t + (uint32_t)i * T) << RL; }
+};

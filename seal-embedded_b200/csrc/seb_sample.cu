@@ -1,0 +1,283 @@
+// seb_sample.cu — SHAKE256-driven samplers, bit-exact with device/lib/sample.c.
+//
+//   k_prng_blocks      : raw PRNG output blocks (tests / KATs)
+//   k_sample_ternary   : sample_small_poly_ternary_prng_96 (sample.c:218-242), one warp per ciphertext
+//   k_sample_cbd       : sample_*_cbd_generic_prng_16 (sample.c:263-356), one thread per 96-byte call
+//   k_uniform_bulk/fix : sample_poly_uniform (sample.c:39-57), thread per ciphertext + warp per ciphertext
+//
+// PRNG consumption order is the reference's: every prng_fill_buffer call is
+// a fresh SHAKE256(seed || LE64(counter)) and bumps the counter, including the data-dependent
+// single-value redraws of the rejection samplers.
+#include "seb_kernels.h"
+#include "seb_sample.cuh"
+
+__device__ __forceinline__ void load_seed(const uint8_t *seeds, size_t b, uint64_t (&s)[8])
+{
+    const uint64_t *p = reinterpret_cast<const uint64_t *>(seeds + b * SEB_SEED_BYTES);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = __ldg(p + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw blocks: out[i][0..136) = first rate block of SHAKE256(seed[b_i] || LE64(ctr_i))
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prng_blocks(const uint8_t *__restrict__ seeds, const uint64_t *__restrict__ counters,
+                              uint64_t *__restrict__ out, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t s[8], a[25];
+    load_seed(seeds, (size_t)i, s);
+    seb_prng_init(a, s, counters[i]);
+    seb_keccak_f1600(a);
+#pragma unroll
+    for (int k = 0; k < 17; k++) out[(size_t)i * 17 + k] = a[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// ternary u (packed 2 bits/coefficient, MSB-first in each byte: sample.c:61-87)
+// ---------------------------------------------------------------------------------------------
+// One warp per ciphertext.  The sampler's PRNG counter walk is sequential (block j+1's counter
+// depends on how many redraws blocks <= j needed), but X(seed,c,96) and X(seed,c,1) are the same
+// SHAKE stream, so the warp computes 32 consecutive counters' streams per wave and then walks
+// them in order, deciding per counter whether it was a 96-byte block or a 1-byte redraw.
+__global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restrict__ seeds,
+                                                        uint8_t *__restrict__ u_out,
+                                                        uint32_t *__restrict__ ctr_out, int n, int batch)
+{
+    extern __shared__ uint32_t usm_all[];
+    const int lane      = threadIdx.x & 31;
+    const int warp      = threadIdx.x >> 5;
+    const int b         = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int words_per = n / 16;  // n/4 bytes
+    uint32_t *usm       = usm_all + warp * words_per;
+    if (b >= batch) return;
+    uint8_t *usm8 = reinterpret_cast<uint8_t *>(usm);
+
+    uint64_t seed[8];
+    load_seed(seeds, (size_t)b, seed);
+
+    const int nblocks = (n + 95) / 96;
+    int j             = 0;  // next block index
+    int need          = 0;  // redraws still owed to the current block
+    int cur           = 0;  // current block index
+    uint32_t cm0 = 0, cm1 = 0, cm2 = 0;  // unresolved rejected positions of the current block
+    uint32_t consumed = 0;
+    uint64_t cbase    = 0;
+
+    while (j < nblocks || need > 0)
+    {
+        uint64_t a[25];
+        seb_prng_init(a, seed, cbase + (uint64_t)lane);
+        seb_keccak_f1600(a);
+
+        uint32_t m0, m1, m2;
+        uint32_t packed[6];
+        seb_ternary_block(a, packed, m0, m1, m2);
+        const uint32_t b0 = (uint32_t)a[0] & 0xFFu;  // value if this counter was a 1-byte redraw
+
+        for (int i = 0; i < 32; i++)
+        {
+            if (need > 0)
+            {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, b0, i);
+                if (v < 0xFEu)
+                {
+                    int pos;
+                    if (cm0)
+                    {
+                        pos = __ffs(cm0) - 1;
+                        cm0 &= cm0 - 1;
+                    }
+                    else if (cm1)
+                    {
+                        pos = 32 + __ffs(cm1) - 1;
+                        cm1 &= cm1 - 1;
+                    }
+                    else
+                    {
+                        pos = 64 + __ffs(cm2) - 1;
+                        cm2 &= cm2 - 1;
+                    }
+                    if (lane == 0)
+                        usm8[cur * 24 + (pos >> 2)] |= (uint8_t)((v % 3u) << (6 - 2 * (pos & 3)));
+                    need--;
+                }
+            }
+            else if (j < nblocks)
+            {
+                const int valid = min(96, n - 96 * j);  // multiple of 32 for every legal n
+                if (lane == i)
+                {
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                        if (k * 16 < valid) usm[j * 6 + k] = packed[k];
+                }
+                cm0  = __shfl_sync(0xFFFFFFFFu, m0, i);
+                cm1  = valid > 32 ? __shfl_sync(0xFFFFFFFFu, m1, i) : 0u;
+                cm2  = valid > 64 ? __shfl_sync(0xFFFFFFFFu, m2, i) : 0u;
+                need = __popc(cm0) + __popc(cm1) + __popc(cm2);
+                cur  = j;
+                j++;
+                __syncwarp();
+            }
+            else
+                break;
+            consumed++;
+        }
+        cbase += 32;
+    }
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(u_out + (size_t)b * (n / 4));
+    for (int k = lane; k < words_per; k += 32) dst[k] = usm[k];
+    if (lane == 0) ctr_out[b] = consumed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// centered binomial (k=21): one thread per 96-byte PRNG call = 16 samples
+// ---------------------------------------------------------------------------------------------
+// e_out: [batch][npoly][n] int8; polynomial k of ciphertext b uses counters
+// ctr_base[b] + k*n/16 + (0 .. n/16)   (ckks_asym.c:199-200: e0 then e1 from the same PRNG)
+__global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ seeds,
+                                                    const uint32_t *__restrict__ ctr_base,
+                                                    int8_t *__restrict__ e_out, int n, int npoly, int batch)
+{
+    const size_t per_ct = (size_t)npoly * (n / 16);
+    const size_t idx    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_ct * (size_t)batch) return;
+    const size_t b = idx / per_ct;
+    const size_t r = idx % per_ct;
+
+    uint64_t s[8], a[25];
+    load_seed(seeds, b, s);
+    seb_prng_init(a, s, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
+    seb_keccak_f1600(a);
+
+    uint32_t o[4];
+    seb_cbd_block(a, o);
+    uint4 *dst = reinterpret_cast<uint4 *>(e_out + b * (size_t)npoly * n + r * 16);
+    *dst       = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// uniform mod q with rejection (symmetric `a`): bulk 4n-byte squeeze, then ordered redraws
+// ---------------------------------------------------------------------------------------------
+// Thread per ciphertext: the 4n-byte squeeze is one sequential sponge.  Accepted words are
+// stored already reduced mod q (< q <= max_multiple); rejected words are stored raw
+// (>= max_multiple), which is how k_uniform_fix finds them.
+__global__ void __launch_bounds__(128) k_uniform_bulk(const uint8_t *__restrict__ seeds,
+                                                      const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
+                                                      size_t ct_stride, int n, SebModulus mod,
+                                                      uint32_t max_multiple, int batch)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    uint64_t s[8], a[25];
+    load_seed(seeds, (size_t)b, s);
+    seb_prng_init(a, s, (uint64_t)ctr[b]);
+    uint2 *dst = reinterpret_cast<uint2 *>(out + (size_t)b * ct_stride);
+    int left   = n / 2;  // 64-bit lanes still to emit
+    while (left > 0)
+    {
+        seb_keccak_f1600(a);
+#pragma unroll
+        for (int k = 0; k < 17; k++)
+        {
+            if (k < left)
+            {
+                uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
+                if (lo < max_multiple) lo = seb_barrett32(lo, mod);
+                if (hi < max_multiple) hi = seb_barrett32(hi, mod);
+                dst[k] = make_uint2(lo, hi);
+            }
+        }
+        dst += 17;
+        left -= 17;
+    }
+}
+
+// Warp per ciphertext: the k-th rejected index (ascending) receives the k-th accepted
+// candidate LE32(X(seed, c0+1+t, 4)), t = 0,1,...; the counter ends one past the last candidate
+// consumed (sample.c:49-56).
+__global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
+                                                     uint32_t *__restrict__ out, size_t ct_stride, int n,
+                                                     SebModulus mod, uint32_t max_multiple, int batch)
+{
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    uint32_t *row = out + (size_t)b * ct_stride;
+    uint64_t s[8];
+    load_seed(seeds, (size_t)b, s);
+
+    const uint64_t c0  = (uint64_t)ctr[b];
+    uint64_t wave_base = c0 + 1;  // counter of lane 0's candidate in the next wave to generate
+    uint64_t last_used = c0;      // counter of the last candidate consumed
+    uint32_t avail     = 0;       // accepted, unused candidates of the current wave (bit = lane)
+    uint32_t cand      = 0;
+    uint64_t cur_base  = 0;
+
+    for (int base = 0; base < n; base += 32)
+    {
+        const uint32_t w = row[base + lane];
+        uint32_t rm      = __ballot_sync(0xFFFFFFFFu, w >= max_multiple);
+        while (rm)
+        {
+            while (avail == 0)
+            {
+                uint64_t a[25];
+                seb_prng_init(a, s, wave_base + (uint64_t)lane);
+                seb_keccak_f1600(a);
+                cand     = (uint32_t)a[0];
+                avail    = __ballot_sync(0xFFFFFFFFu, cand < max_multiple);
+                cur_base = wave_base;
+                wave_base += 32;
+            }
+            const int rp     = __ffs(rm) - 1;
+            const int cl     = __ffs(avail) - 1;
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, cand, cl);
+            if (lane == rp) row[base + rp] = seb_barrett32(v, mod);
+            rm &= rm - 1;
+            avail &= avail - 1;
+            last_used = cur_base + (uint64_t)cl;
+        }
+    }
+    if (lane == 0) ctr[b] = (uint32_t)(last_used + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void seb_launch_prng_blocks(const uint8_t *seeds, const uint64_t *counters, uint64_t *out, int count,
+                            cudaStream_t st)
+{
+    if (count <= 0) return;
+    k_prng_blocks<<<(count + 127) / 128, 128, 0, st>>>(seeds, counters, out, count);
+}
+
+void seb_launch_sample_ternary(const uint8_t *seeds, uint8_t *u_out, uint32_t *ctr_out, int n, int batch,
+                               cudaStream_t st)
+{
+    if (batch <= 0) return;
+    const int warps = 4;
+    const size_t sm = (size_t)warps * (n / 4);
+    k_sample_ternary<<<(batch + warps - 1) / warps, warps * 32, sm, st>>>(seeds, u_out, ctr_out, n, batch);
+}
+
+void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_t *e_out, int n, int npoly,
+                           int batch, cudaStream_t st)
+{
+    if (batch <= 0) return;
+    const size_t total = (size_t)batch * npoly * (n / 16);
+    k_sample_cbd<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(seeds, ctr_base, e_out, n, npoly, batch);
+}
+
+void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
+                        const SebModulus &mod, int batch, cudaStream_t st)
+{
+    if (batch <= 0) return;
+    // max_multiple = 0xFFFFFFFF - (0xFFFFFFFF mod q) - 1 (sample.c:45-46)
+    const uint32_t max_multiple = 0xFFFFFFFFu - (0xFFFFFFFFu % mod.q) - 1u;
+    k_uniform_bulk<<<(batch + 127) / 128, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch);
+    k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch);
+}

@@ -1,0 +1,323 @@
+/*
+ * seal_embedded.c — the reference's public API (device/lib/seal_embedded.{h,c}) implemented in C on
+ * top of the B200 kernels' C ABI (seb_* in include/seal_embedded_b200.h).
+ *
+ * Same symbols, argument meaning, key-file conventions, callback protocol and error behaviour as
+ * the reference, so an application written against SEAL-Embedded's device library links against
+ * this one unchanged:
+ *   - se_setup_custom / se_setup / se_setup_default      seal_embedded.c:24-96
+ *   - se_encrypt_seeded / se_encrypt                     seal_embedded.c:98-221
+ *   - se_cleanup                                         seal_embedded.c:223-235
+ * A single static context per process, like the reference (seal_embedded.c:18-22).
+ */
+#include <errno.h>
+#include <fcntl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/random.h>
+#include <unistd.h>
+
+#include "../../include/seal_embedded_b200.h"
+
+#ifndef SE_DATA_PATH
+#define SE_DATA_PATH "adapter_output_data" /* device/CMakeLists.txt:285 */
+#endif
+
+static Parms g_parms;
+static SE_PTRS g_ptrs;
+static SE_PARMS g_se_parms;
+static seb_ctx *g_ctx   = NULL;
+static uint32_t *g_ct   = NULL; /* [nprimes][2][n] host copy of the last ciphertext */
+static int g_ref_quirk  = 0;
+static int g_pk_loaded  = 0;
+
+/* fileops.c:60-138 read_from_image + check_ret: a missing or short key file is fatal */
+static void read_key_file(const char *fpath, size_t bytes_expected, void *vec)
+{
+    int fd = open(fpath, O_RDONLY);
+    if (fd < 0)
+    {
+        printf("Error: problem with opening or closing file\n");
+        printf("errno value: %d\n", errno);
+        printf("errno message: %s\n", strerror(errno));
+        printf("file path: %s\n", fpath);
+        exit(1);
+    }
+    size_t got = 0;
+    while (got < bytes_expected)
+    {
+        ssize_t r = read(fd, (char *)vec + got, bytes_expected - got);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    close(fd);
+    if (got != bytes_expected)
+    {
+        printf("Error: problem with reading from file\n");
+        printf("bytes read     : %zu bytes\n", got);
+        printf("bytes expected : %zu bytes\n", bytes_expected);
+        printf("file path: %s\n", fpath);
+        exit(1);
+    }
+}
+
+static void die_on(int rc, const char *what)
+{
+    if (rc == 0) return;
+    printf("Error! %s failed: %s\n", what, seb_last_error());
+    exit(1);
+}
+
+/* load_pki (fileops.c:172-204) for every prime, once, instead of on every encryption */
+static void load_public_key(void)
+{
+    size_t n = g_parms.coeff_count, np = g_parms.nprimes;
+    ZZ *pk0 = malloc(np * n * sizeof(ZZ)), *pk1 = malloc(np * n * sizeof(ZZ));
+    char fpath[512];
+    if (!pk0 || !pk1)
+    {
+        printf("Error! Allocation failed. Exiting...\n");
+        exit(1);
+    }
+    for (size_t p = 0; p < np; p++)
+    {
+        snprintf(fpath, sizeof fpath, "%s/pk0_ntt_%zu_%u.dat", SE_DATA_PATH, n, g_parms.moduli[p].value);
+        read_key_file(fpath, n * sizeof(ZZ), pk0 + p * n);
+        snprintf(fpath, sizeof fpath, "%s/pk1_ntt_%zu_%u.dat", SE_DATA_PATH, n, g_parms.moduli[p].value);
+        read_key_file(fpath, n * sizeof(ZZ), pk1 + p * n);
+    }
+    die_on(seb_set_public_key(g_ctx, pk0, pk1), "seb_set_public_key");
+    free(pk0);
+    free(pk1);
+    g_pk_loaded = 1;
+}
+
+static void release_all(void)
+{
+    if (g_ctx) seb_destroy(g_ctx);
+    g_ctx = NULL;
+    free(g_parms.moduli);
+    free(g_ptrs.values);
+    free(g_ptrs.index_map_ptr);
+    free(g_ptrs.ternary);
+    free(g_ct);
+    g_ct = NULL;
+    memset(&g_parms, 0, sizeof g_parms);
+    memset(&g_ptrs, 0, sizeof g_ptrs);
+    g_pk_loaded = 0;
+}
+
+SE_PARMS *se_setup_custom(size_t degree, size_t nprimes, const ZZ *modulus_vals, const ZZ *ratios,
+                          double scale, EncryptType encrypt_type)
+{
+    if (g_ctx) release_all();
+    int asym   = encrypt_type == SE_ASYM_ENCR;
+    int device = -1;
+    const char *dev_env = getenv("SE_B200_DEVICE");
+    if (dev_env && *dev_env) device = atoi(dev_env);
+
+    /* With default parameters the requested scale is overridden by the degree's default exactly
+     * as set_parms_ckks does (parameters.c:197-225).  Custom moduli keep the caller's
+     * scale (parameters.c:232-249); their 2n-th roots must be tabulated (ntt.c:199-291). */
+    int custom = modulus_vals && ratios;
+    g_ctx      = seb_create(degree, nprimes, custom ? modulus_vals : NULL, NULL, custom ? scale : 0.0, asym, device);
+    if (!g_ctx)
+    {
+        printf("Error! se_setup failed: %s\n", seb_last_error());
+        exit(1);
+    }
+
+    size_t n              = degree;
+    g_parms.coeff_count   = n;
+    g_parms.logn          = (size_t)log2((double)n);
+    g_parms.nprimes       = nprimes;
+    g_parms.scale         = seb_scale(g_ctx);
+    g_parms.is_asymmetric = asym;
+    g_parms.pk_from_file  = 1; /* seal_embedded.c:37-41 */
+    g_parms.sample_s      = 0;
+    g_parms.small_u       = 1;
+    g_parms.small_s       = 1;
+    g_parms.moduli        = calloc(nprimes, sizeof(Modulus));
+    g_ptrs.values         = calloc(n / 2, sizeof(flpt));
+    g_ptrs.index_map_ptr  = calloc(n, sizeof(uint16_t));
+    g_ptrs.ternary        = calloc(n / 4, 1);
+    g_ct                  = calloc(2 * nprimes * n, sizeof(ZZ));
+    if (!g_parms.moduli || !g_ptrs.values || !g_ptrs.index_map_ptr || !g_ptrs.ternary || !g_ct)
+    {
+        printf("Error! Allocation failed. Exiting...\n");
+        exit(1);
+    }
+    for (size_t i = 0; i < nprimes; i++)
+    {
+        uint32_t q = seb_prime(g_ctx, i);
+        /* floor(2^64/q), low then high word (modulus.c:23-56) */
+        unsigned __int128 one     = (unsigned __int128)1 << 64;
+        uint64_t ratio            = (uint64_t)(one / q);
+        g_parms.moduli[i].value          = q;
+        g_parms.moduli[i].const_ratio[0] = custom ? ratios[2 * i + 1] : (ZZ)ratio;
+        g_parms.moduli[i].const_ratio[1] = custom ? ratios[2 * i] : (ZZ)(ratio >> 32);
+    }
+    g_parms.curr_modulus_idx = 0;
+    g_parms.curr_modulus     = &g_parms.moduli[0];
+
+    /* ckks_calc_index_map (ckks_common.c:32-68), kept host-visible like SE_INDEX_MAP_PERSIST */
+    {
+        uint64_t m = 2 * (uint64_t)n, pos = 1;
+        size_t logn = g_parms.logn;
+        for (size_t i = 0; i < n / 2; i++)
+        {
+            size_t a = (size_t)((pos - 1) / 2), b = n - 1 - a, ra = 0, rb = 0;
+            for (size_t k = 0; k < logn; k++)
+            {
+                ra |= ((a >> k) & 1) << (logn - 1 - k);
+                rb |= ((b >> k) & 1) << (logn - 1 - k);
+            }
+            g_ptrs.index_map_ptr[i]         = (uint16_t)ra;
+            g_ptrs.index_map_ptr[i + n / 2] = (uint16_t)rb;
+            pos                             = (pos * 3) & (m - 1);
+        }
+    }
+
+    if (!asym)
+    {
+        /* ckks_setup_s -> load_sk (ckks_sym.c:162-179, fileops.c:140-170) */
+        char fpath[512];
+        snprintf(fpath, sizeof fpath, "%s/sk_%zu.dat", SE_DATA_PATH, n);
+        read_key_file(fpath, n / 4, g_ptrs.ternary);
+        die_on(seb_set_secret_key(g_ctx, (const uint8_t *)g_ptrs.ternary), "seb_set_secret_key");
+    }
+    g_ptrs.c0_ptr      = g_ct;
+    g_ptrs.c1_ptr      = g_ct + n;
+    g_se_parms.parms   = &g_parms;
+    g_se_parms.se_ptrs = &g_ptrs;
+    return &g_se_parms;
+}
+
+SE_PARMS *se_setup(size_t degree, size_t nprimes, double scale, EncryptType encrypt_type)
+{
+    return se_setup_custom(degree, nprimes, NULL, NULL, scale, encrypt_type);
+}
+
+SE_PARMS *se_setup_default(EncryptType encrypt_type)
+{
+    return se_setup(4096, 3, pow(2, 25), encrypt_type); /* seal_embedded.c:90-96 */
+}
+
+void se_b200_set_reference_quirk(int on) { g_ref_quirk = on != 0; }
+
+seb_ctx *se_b200_context(SE_PARMS *se_parms)
+{
+    return (se_parms == &g_se_parms) ? g_ctx : NULL;
+}
+
+/* rng.h:45-53: a NULL seed means a fresh random one */
+static void fill_seeds(uint8_t *dst, const uint8_t *src, size_t count)
+{
+    if (src)
+    {
+        memcpy(dst, src, count * SE_PRNG_SEED_BYTE_COUNT);
+        return;
+    }
+    size_t want = count * SE_PRNG_SEED_BYTE_COUNT, got = 0;
+    while (got < want)
+    {
+        ssize_t r = getrandom(dst + got, want - got, 0);
+        if (r < 0)
+        {
+            printf("Error: getrandom failed\n");
+            exit(1);
+        }
+        got += (size_t)r;
+    }
+}
+
+bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seeds, const flpt *v, size_t vlen,
+                             size_t batch, ZZ *out, SE_PARMS *se_parms)
+{
+    if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v || !out) return false;
+    if (batch == 0) return true;
+    if (vlen > g_parms.coeff_count / 2) vlen = g_parms.coeff_count / 2;
+    uint8_t *sd = malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
+    uint8_t *ss = g_parms.is_asymmetric ? NULL : malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
+    if (!sd || (!g_parms.is_asymmetric && !ss))
+    {
+        printf("Error! Allocation failed. Exiting...\n");
+        exit(1);
+    }
+    fill_seeds(sd, seeds, batch);
+    int rc;
+    if (g_parms.is_asymmetric)
+    {
+        if (!g_pk_loaded) load_public_key();
+        rc = seb_encrypt_asym_host(g_ctx, v, vlen, sd, batch, out);
+    }
+    else
+    {
+        fill_seeds(ss, shareable_seeds, batch);
+        rc = seb_encrypt_sym_host(g_ctx, v, vlen, ss, sd, batch, out, g_ref_quirk);
+    }
+    free(sd);
+    free(ss);
+    if (rc == SE_ERR_ENCODE_RANGE)
+    {
+        printf("Error! Value is possibly too large.\n"); /* ckks_common.c:197 */
+        return false;
+    }
+    die_on(rc, "se_encrypt");
+    return true;
+}
+
+bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR network_send_function, void *v,
+                       size_t vlen_bytes, bool print, SE_PARMS *se_parms)
+{
+    if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v) return false;
+    size_t n = g_parms.coeff_count, np = g_parms.nprimes;
+
+    /* seal_embedded.c:108-111: at most n/2 values are taken; slots past the input keep what the
+     * previous call staged there (zero after setup), as in the reference */
+    size_t copy_size_bytes = (n / 2) * sizeof(ZZ);
+    if (vlen_bytes < copy_size_bytes) copy_size_bytes = vlen_bytes;
+    memset(g_ptrs.values, 0, copy_size_bytes);
+    memcpy(g_ptrs.values, v, copy_size_bytes);
+
+    bool ok = se_encrypt_batch_seeded(shareable_seed, seed, g_ptrs.values, n / 2, 1, g_ct, se_parms);
+    if (!ok) return false;
+
+    /* seal_embedded.c:145-213: per prime, c0 then c1, n words each; the callback must consume
+     * exactly what it is given */
+    for (size_t i = 0; i < np; i++)
+    {
+        g_parms.curr_modulus_idx = i;
+        g_parms.curr_modulus     = &g_parms.moduli[i];
+        g_ptrs.c0_ptr            = g_ct + (2 * i) * n;
+        g_ptrs.c1_ptr            = g_ct + (2 * i + 1) * n;
+        if (print)
+        {
+            printf("c0: { %u, %u, ..., %u }\n", g_ptrs.c0_ptr[0], g_ptrs.c0_ptr[1], g_ptrs.c0_ptr[n - 1]);
+            printf("c1: { %u, %u, ..., %u }\n", g_ptrs.c1_ptr[0], g_ptrs.c1_ptr[1], g_ptrs.c1_ptr[n - 1]);
+        }
+        if (network_send_function)
+        {
+            size_t nbytes_send = n * sizeof(ZZ);
+            size_t nbytes_recv = network_send_function(g_ptrs.c0_ptr, nbytes_send);
+            if (nbytes_recv != nbytes_send) return false;
+            nbytes_recv = network_send_function(g_ptrs.c1_ptr, nbytes_send);
+            if (nbytes_recv != nbytes_send) return false;
+        }
+    }
+    return true;
+}
+
+bool se_encrypt(SEND_FNCT_PTR network_send_function, void *v, size_t vlen_bytes, bool print, SE_PARMS *se_parms)
+{
+    return se_encrypt_seeded(NULL, NULL, network_send_function, v, vlen_bytes, print, se_parms);
+}
+
+void se_cleanup(SE_PARMS *se_parms)
+{
+    if (!se_parms || se_parms != &g_se_parms) return;
+    release_all();
+    se_parms->parms = 0; /* seal_embedded.c:234 */
+}

@@ -1,0 +1,257 @@
+// emul.cpp — sequential g++ emulation of the per-thread device functions in
+// seal-embedded_b200/csrc/*.cuh (NTT passes, IFFT passes, Keccak, sampler bit tricks).
+//
+// TEST INFRASTRUCTURE: lets the CPU test-suite check the kernels' index math, swizzles and bit
+// manipulation against the oracle without a GPU.  "Threads" run one after another and a pass
+// boundary (__syncthreads in the kernel) is the end of the loop over threads.  Nothing here is
+// part of the product and nothing here computes a product result.
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "seb_encode.cuh"
+#include "seb_ntt.cuh"
+#include "seb_sample.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// NTT
+// ---------------------------------------------------------------------------------------------
+struct HostLoad
+{
+    const uint32_t *src;
+    int n;
+    uint32_t operator()(int p, uint32_t pos) const { return src[(size_t)p * n + pos]; }
+};
+
+template <int LOGN, int NPOLY, int P>
+static void ntt_passes(std::vector<std::array<uint32_t[SEB_E], NPOLY>> &regs, uint32_t *smem, const uint2 *tw,
+                       uint32_t q, HostLoad &ld)
+{
+    constexpr int T = (1 << LOGN) / SEB_E;
+    for (int t = 0; t < T; t++)
+    {
+        uint32_t(&x)[NPOLY][SEB_E] = *reinterpret_cast<uint32_t(*)[NPOLY][SEB_E]>(regs[t].data());
+        seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, 2 * q, ld);
+    }
+    if constexpr (P + 1 < NttPlan<LOGN>::NPASS) ntt_passes<LOGN, NPOLY, P + 1>(regs, smem, tw, q, ld);
+}
+
+template <int LOGN, int NPOLY>
+static void ntt_emul(const uint32_t *in, const uint2 *tw, uint32_t q, uint32_t *out)
+{
+    constexpr int N = 1 << LOGN;
+    constexpr int T = N / SEB_E;
+    std::vector<std::array<uint32_t[SEB_E], NPOLY>> regs(T);
+    std::vector<uint32_t> smem((size_t)NPOLY * N, 0xDEADBEEFu);
+    HostLoad ld{in, N};
+    ntt_passes<LOGN, NPOLY, 0>(regs, smem.data(), tw, q, ld);
+    using O = NttOut<LOGN>;
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < O::GPL; i++)
+            for (int j = 0; j < O::RUN; j++)
+                for (int p = 0; p < NPOLY; p++)
+                    out[(size_t)p * N + O::pos(t, i) + j] = seb_final_reduce(regs[t][p][i * O::RUN + j], q, 2 * q);
+}
+
+extern "C" int emul_ntt(int logn, int npoly, const uint32_t *in, const uint32_t *roots_w, const uint32_t *roots_wq,
+                        uint32_t q, uint32_t *out)
+{
+    const int n = 1 << logn;
+    std::vector<uint2> tw(n);
+    for (int i = 0; i < n; i++) tw[i] = make_uint2(roots_w[i], roots_wq[i]);
+#define CASE(L)                                                  \
+    case L:                                                      \
+        if (npoly == 1)                                          \
+            ntt_emul<L, 1>(in, tw.data(), q, out);               \
+        else if (npoly == 3)                                     \
+            ntt_emul<L, 3>(in, tw.data(), q, out);               \
+        else                                                     \
+            return -1;                                           \
+        return 0;
+    switch (logn)
+    {
+        CASE(10)
+        CASE(11)
+        CASE(12)
+        CASE(13)
+        CASE(14)
+    }
+#undef CASE
+    return -1;
+}
+
+extern "C" uint32_t emul_swz(int logn, uint32_t a)
+{
+    switch (logn)
+    {
+        case 10: return seb_swz<10>(a);
+        case 11: return seb_swz<11>(a);
+        case 12: return seb_swz<12>(a);
+        case 13: return seb_swz<13>(a);
+        case 14: return seb_swz<14>(a);
+    }
+    return a;
+}
+
+extern "C" int emul_plan(int logn, int *radices)
+{
+#define CASE(L)                                                                 \
+    case L:                                                                     \
+        for (int i = 0; i < NttPlan<L>::NPASS; i++) radices[i] = NttPlan<L>::R[i]; \
+        return NttPlan<L>::NPASS;
+    switch (logn)
+    {
+        CASE(10)
+        CASE(11)
+        CASE(12)
+        CASE(13)
+        CASE(14)
+    }
+#undef CASE
+    return 0;
+}
+
+extern "C" uint32_t emul_barrett64(uint64_t x, uint32_t q)
+{
+    const uint64_t ratio = (uint64_t)(((unsigned __int128)1 << 64) / q);
+    SebModulus m{q, 2 * q, (uint32_t)ratio, (uint32_t)(ratio >> 32)};
+    return seb_barrett64(x, m);
+}
+extern "C" uint32_t emul_barrett32(uint32_t x, uint32_t q)
+{
+    const uint64_t ratio = (uint64_t)(((unsigned __int128)1 << 64) / q);
+    SebModulus m{q, 2 * q, (uint32_t)ratio, (uint32_t)(ratio >> 32)};
+    return seb_barrett32(x, m);
+}
+extern "C" uint32_t emul_shoup_lazy(uint32_t x, uint32_t w, uint32_t q)
+{
+    return seb_mul_shoup_lazy(x, w, (uint32_t)(((uint64_t)w << 32) / q), q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------------------------
+template <int LOGN, int LOGNL, int P>
+static void enc_passes(std::vector<std::array<double, 2 * ENC_E>> &regs, double *sre, double *sim, uint32_t pos0,
+                       const float *vals, int vlen, const uint16_t *src_map, const double2 *tw)
+{
+    constexpr int T = (1 << LOGNL) / ENC_E;
+    for (int t = 0; t < T; t++)
+    {
+        double(&xr)[ENC_E] = *reinterpret_cast<double(*)[ENC_E]>(regs[t].data());
+        double(&xi)[ENC_E] = *reinterpret_cast<double(*)[ENC_E]>(regs[t].data() + ENC_E);
+        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, pos0, vals, vlen, src_map, tw);
+    }
+    if constexpr (P + 1 < enc_npass(LOGNL)) enc_passes<LOGN, LOGNL, P + 1>(regs, sre, sim, pos0, vals, vlen, src_map, tw);
+}
+
+template <int LOGN, int CL>
+static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const double2 *tw, double n_inv,
+                    int64_t *out)
+{
+    constexpr int N     = 1 << LOGN;
+    constexpr int NL    = N / CL;
+    constexpr int LOGNL = (CL == 2) ? LOGN - 1 : LOGN;
+    constexpr int T     = NL / ENC_E;
+    constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
+    constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
+    int bad             = 0;
+    std::vector<double> sre[2], sim[2];
+    for (int rank = 0; rank < CL; rank++)
+    {
+        sre[rank].assign(NL, 1e300);
+        sim[rank].assign(NL, 1e300);
+        std::vector<std::array<double, 2 * ENC_E>> regs(T);
+        enc_passes<LOGN, LOGNL, 0>(regs, sre[rank].data(), sim[rank].data(), rank * NL, vals, vlen, src_map, tw);
+        for (int t = 0; t < T; t++)
+            for (int i = 0; i < (ENC_E >> RL); i++)
+            {
+                const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
+                const uint32_t off  = g & ((1u << LSL) - 1u);
+                const uint32_t base = ((g >> LSL) << (LSL + RL)) | off;
+                for (int j = 0; j < (1 << RL); j++)
+                {
+                    const uint32_t pos = base | ((uint32_t)j << LSL);
+                    if (CL == 1)
+                        out[pos] = enc_finish(regs[t][i * (1 << RL) + j], n_inv, bad);
+                    else
+                    {
+                        sre[rank][enc_swz(pos)] = regs[t][i * (1 << RL) + j];
+                        sim[rank][enc_swz(pos)] = regs[t][ENC_E + i * (1 << RL) + j];
+                    }
+                }
+            }
+    }
+    if (CL == 2)
+        for (uint32_t rank = 0; rank < 2; rank++)
+            for (uint32_t k = 0; k < (uint32_t)NL; k++)
+            {
+                const uint32_t sk = enc_swz(k);
+                const double re   = enc_cross_re(rank, sre[rank][sk], sim[rank][sk], sre[rank ^ 1][sk],
+                                                 sim[rank ^ 1][sk], tw[1]);
+                out[rank * NL + k] = enc_finish(re, n_inv, bad);
+            }
+    return bad;
+}
+
+// tw: interleaved (re, im) pairs, n of them
+extern "C" int emul_encode(int logn, const float *vals, int vlen, const uint16_t *src_map, const double *tw,
+                           double n_inv, int64_t *out)
+{
+    const double2 *t2 = reinterpret_cast<const double2 *>(tw);
+    switch (logn)
+    {
+        case 10: return enc_emul<10, 1>(vals, vlen, src_map, t2, n_inv, out);
+        case 11: return enc_emul<11, 1>(vals, vlen, src_map, t2, n_inv, out);
+        case 12: return enc_emul<12, 1>(vals, vlen, src_map, t2, n_inv, out);
+        case 13: return enc_emul<13, 1>(vals, vlen, src_map, t2, n_inv, out);
+        case 14: return enc_emul<14, 2>(vals, vlen, src_map, t2, n_inv, out);
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keccak and sampler blocks
+// ---------------------------------------------------------------------------------------------
+extern "C" void emul_keccak(uint64_t *st)
+{
+    uint64_t a[25];
+    memcpy(a, st, sizeof a);
+    seb_keccak_f1600(a);
+    memcpy(st, a, sizeof a);
+}
+
+// first rate block of SHAKE256(seed || LE64(ctr)) as 17 words
+extern "C" void emul_prng_block(const uint8_t *seed, uint64_t ctr, uint64_t *out17)
+{
+    uint64_t s[8], a[25];
+    memcpy(s, seed, 64);
+    seb_prng_init(a, s, ctr);
+    seb_keccak_f1600(a);
+    memcpy(out17, a, 17 * 8);
+}
+
+extern "C" void emul_ternary_block(const uint8_t *seed, uint64_t ctr, uint32_t *packed6, uint32_t *mask3)
+{
+    uint64_t s[8], a[25];
+    memcpy(s, seed, 64);
+    seb_prng_init(a, s, ctr);
+    seb_keccak_f1600(a);
+    uint32_t p[6];
+    seb_ternary_block(a, p, mask3[0], mask3[1], mask3[2]);
+    memcpy(packed6, p, sizeof p);
+}
+
+extern "C" void emul_cbd_block(const uint8_t *seed, uint64_t ctr, uint32_t *out4)
+{
+    uint64_t s[8], a[25];
+    memcpy(s, seed, 64);
+    seb_prng_init(a, s, ctr);
+    seb_keccak_f1600(a);
+    uint32_t o[4];
+    seb_cbd_block(a, o);
+    memcpy(out4, o, sizeof o);
+}
+
+extern "C" uint32_t emul_mod3_bytes(uint32_t x) { return seb_mod3_bytes(x); }

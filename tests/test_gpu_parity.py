@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on identical seeded
+inputs — bit-exact (integer/byte work; the FP64 encode is required to be bit-exact too, so the
+tolerance is zero everywhere).  Reference behaviour being pinned is cited per test.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, keys_for
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [(1024, 1), (2048, 1), (4096, 3), (8192, 4), (16384, 6)]
+
+
+def dev(torch, a: np.ndarray):
+    a = np.ascontiguousarray(a)
+    view = {np.dtype(np.uint32): np.int32, np.dtype(np.uint16): np.int16, np.dtype(np.uint64): np.int64}.get(a.dtype)
+    return torch.from_numpy(a.view(view) if view else a).cuda()
+
+
+def host(t, dtype):
+    return t.cpu().numpy().view(dtype)
+
+
+@pytest.fixture(scope="module")
+def ctxs(seb, torch_cuda):
+    cache = {}
+
+    def get(n, np_, asym):
+        key = (n, np_, asym)
+        if key not in cache:
+            cache[key] = seb.Context(n, np_, asym, device=0)
+        return cache[key]
+
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+def test_prng_blocks(seb, torch_cuda, oracle_mod, ctxs):
+    """rng.h:78-91 / fips202.c:105-128 — SHAKE256(seed || LE64(ctr)), against hashlib."""
+    torch = torch_cuda
+    ctx = ctxs(1024, 1, True)
+    count = 300
+    seeds = oracle_mod.make_seeds(count)
+    ctrs = np.arange(count, dtype=np.uint64) * np.uint64(0x0101010101) + np.uint64(3)
+    d_out = torch.zeros(count * 17, dtype=torch.int64, device="cuda")
+    ctx.prng_blocks_device(dev(torch, seeds), dev(torch, ctrs), count, d_out)
+    torch.cuda.synchronize()
+    out = host(d_out, np.uint8).reshape(count, 136)
+    for i in range(count):
+        exp = hashlib.shake_256(seeds[i].tobytes() + struct.pack("<Q", int(ctrs[i]))).digest(136)
+        assert out[i].tobytes() == exp, i
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_encode(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """ckks_common.c:105-215 + fft.c:69-144, incl. short inputs (zero padded) and the 9 message
+    patterns of device/test/ckks_tests_common.c:25-57."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    vlen = n // 2
+    rows = [oracle_mod.make_values(1, vlen, seed=n + k)[0] for k in range(4)]
+    pat = np.zeros((7, vlen), np.float32)
+    pat[0, 0] = 1
+    pat[1, 0] = 2
+    pat[2, :] = 1
+    pat[3, :] = 2
+    pat[4, :] = 1.1
+    pat[5, :] = -2.1
+    pat[6, 1::2] = 1
+    big = (oracle_mod.make_values(1, vlen, seed=5)[0] * np.float32(1e6)).astype(np.float32)
+    vals = np.stack(rows + list(pat) + [big])
+    batch = vals.shape[0]
+    d_pt = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+    ctx.encode_device(dev(torch, vals), vlen, batch, d_pt)
+    assert ctx.encode_failures() == 0
+    got = d_pt.cpu().numpy().reshape(batch, n)
+    for b in range(batch):
+        ok, exp = orc.encode(n, vals[b])
+        assert ok and np.array_equal(got[b], exp), (n, b, np.nonzero(got[b] != exp)[0][:8])
+    # short rows: vlen < n/2 is zero padded
+    for short in (1, 7, n // 4):
+        sv = np.ascontiguousarray(vals[:3, :short])
+        ctx.encode_device(dev(torch, sv), short, 3, d_pt)
+        assert ctx.encode_failures() == 0
+        got = d_pt.cpu().numpy().reshape(batch, n)
+        for b in range(3):
+            ok, exp = orc.encode(n, sv[b])
+            assert ok and np.array_equal(got[b], exp), (n, short, b)
+
+
+def test_encode_overflow_flag(seb, torch_cuda, orc, ctxs):
+    """ckks_common.c:195-204: |coeff| > 2^63 makes the encode fail (returns false)."""
+    torch = torch_cuda
+    n = 4096
+    ctx = ctxs(n, 3, True)
+    vals = np.zeros((3, n // 2), np.float32)
+    vals[0, :] = 1.0
+    vals[1, :] = 3e37  # scale 2^25 * 3e37 >> 2^63
+    vals[2, 0] = 0.5
+    assert orc.encode(n, vals[1])[0] is False
+    d_pt = torch.zeros(3 * n, dtype=torch.int64, device="cuda")
+    ctx.encode_device(dev(torch, vals), n // 2, 3, d_pt)
+    assert ctx.encode_failures() == 1
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_samplers_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """sample.c:218-242 (ternary with interleaved single-byte redraws) and :311-356 (CBD), PRNG
+    counter order of ckks_asym.c:184-201."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    batch = 48
+    seeds = oracle_mod.make_seeds(batch, b"sampler-%d" % n)
+    d_u = torch.zeros(batch * n // 4, dtype=torch.uint8, device="cuda")
+    d_e = torch.zeros(batch * 2 * n, dtype=torch.int8, device="cuda")
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    ctx.sample_asym_device(dev(torch, seeds), batch, d_u, d_e, d_ctr)
+    torch.cuda.synchronize()
+    u = d_u.cpu().numpy().reshape(batch, n // 4)
+    e = d_e.cpu().numpy().reshape(batch, 2, n)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        eu, c = orc.sample_ternary_small(n, seeds[b])
+        assert ctr[b] == c, (b, ctr[b], c)
+        assert np.array_equal(u[b], eu), (n, b)
+        e0, c = orc.sample_cbd(n, seeds[b], c)
+        e1, c = orc.sample_cbd(n, seeds[b], c)
+        assert np.array_equal(e[b, 0], e0) and np.array_equal(e[b, 1], e1), (n, b)
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """sample.c:39-57: bulk draw, ordered redraws, counter running on across primes (ckks_sym.c:219)."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    batch = 9
+    seeds = oracle_mod.make_seeds(batch, b"uniform-%d" % n)
+    d_seeds = dev(torch, seeds)
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+    for p in range(np_):
+        ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+    torch.cuda.synchronize()
+    out = host(d_out, np.uint32).reshape(batch, np_, n)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        c = 0
+        for p, q in enumerate(ctx.primes):
+            exp, c = orc.sample_uniform(n, q, seeds[b], c)
+            assert np.array_equal(out[b, p], exp), (n, b, p)
+        assert ctr[b] == c
+
+
+@pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (8192, 6), (16384, 13)])
+def test_ntt(n, np_, seb, torch_cuda, orc, ctxs):
+    """ntt.c:168-189 for every tabulated (n, q): random residues plus the delta and all-(q-1) edge
+    polynomials (device/test/ntt_tests.c:130-317 cases)."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    rng = np.random.default_rng(n)
+    batch = 4
+    polys = np.zeros((batch, np_, n), np.uint32)
+    for p, q in enumerate(ctx.primes):
+        polys[0, p] = rng.integers(0, q, n)
+        polys[1, p, 0] = 1
+        polys[2, p, :] = q - 1
+        polys[3, p] = rng.integers(0, q, n)
+    d = dev(torch, polys)
+    ctx.ntt_device(d, batch)
+    torch.cuda.synchronize()
+    got = host(d, np.uint32).reshape(batch, np_, n)
+    for p, q in enumerate(ctx.primes):
+        for b in range(batch):
+            assert np.array_equal(got[b, p], orc.ntt(n, q, polys[b, p])), (n, q, b)
+        assert np.all(got[1, p] == 1)  # NTT(delta_0) = all ones
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_encrypt_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """seal_embedded.c:98-215 asymmetric branch == ckks_asym.c:173-286, full ciphertext bit-exact."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    ctx.set_public_key(pk0, pk1)
+    batch = 5
+    vlen = n // 2
+    vals = oracle_mod.make_values(batch, vlen, seed=n)
+    seeds = oracle_mod.make_seeds(batch, b"asym-%d" % n)
+    d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    ctx.encrypt_asym_device(dev(torch, vals), vlen, dev(torch, seeds), batch, d_out)
+    assert ctx.encode_failures() == 0
+    got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+    for b in range(batch):
+        ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        assert ok and np.array_equal(got[b], exp), (n, b)
+    # decrypt + decode round trip (device/test/ckks_tests_asym.c: within 0.1)
+    dec = orc.decrypt_decode(n, np_, got[0], sk, vlen)
+    assert np.abs(dec - vals[0]).max() < 0.1
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """ckks_sym.c:181-301: c1 = a, c0 = -a*s + m + e; and the reference's se_encrypt byte stream
+    where c1 holds ntt(m+e) when ref_quirk is on."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    sk = oracle_mod.make_sk(n)
+    ctx.set_secret_key(sk)
+    batch = 4
+    vlen = n // 2
+    vals = oracle_mod.make_values(batch, vlen, seed=n + 1)
+    seeds = oracle_mod.make_seeds(batch, b"sym-%d" % n)
+    sseeds = oracle_mod.make_seeds(batch, b"share-%d" % n)
+    d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    for quirk in (False, True):
+        ctx.encrypt_sym_device(dev(torch, vals), vlen, dev(torch, sseeds), dev(torch, seeds), batch, d_out, quirk)
+        assert ctx.encode_failures() == 0
+        got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+        for b in range(batch):
+            ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk, ref_quirk=quirk)
+            assert ok and np.array_equal(got[b], exp), (n, b, quirk)
+        if not quirk:
+            dec = orc.decrypt_decode(n, np_, got[0], sk, vlen)
+            assert np.abs(dec - vals[0]).max() < 0.1
+
+
+def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs):
+    """Host-pointer batch API: pageable and pinned buffers, more items than one chunk, ragged vlen."""
+    torch = torch_cuda
+    n, np_ = 4096, 3
+    ctx = ctxs(n, np_, True)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    ctx.set_public_key(pk0, pk1)
+    batch = 1500  # chunk is ~682 items at 96 KiB per ciphertext
+    vlen = 100
+    vals = oracle_mod.make_values(batch, vlen, seed=99)
+    seeds = oracle_mod.make_seeds(batch, b"host")
+    out = ctx.encrypt_asym_host(vals, seeds)
+    pv = torch.from_numpy(vals).pin_memory()
+    ps = torch.from_numpy(seeds).pin_memory()
+    po = torch.empty((batch, np_, 2, n), dtype=torch.int32).pin_memory()
+    ctx.lib.seb_encrypt_asym_host(ctx.h, pv.data_ptr(), vlen, ps.data_ptr(), batch, po.data_ptr())
+    assert np.array_equal(out, po.numpy().view(np.uint32))
+    for b in (0, 1, 681, 682, 683, 1364, 1499):
+        ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        assert ok and np.array_equal(out[b], exp), b
+
+
+def _send_collector(chunks):
+    def send(data: bytes) -> int:
+        chunks.append(data)
+        return len(data)
+
+    return send
+
+
+@pytest.mark.parametrize("asym", [False, True])
+def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeypatch):
+    """The reference's own API surface: se_setup reads adapter_output_data/, se_encrypt_seeded calls
+    send(c0), send(c1) per prime with n*4 bytes each (seal_embedded.c:180-204); compared with the
+    oracle and, when its .so is present, with the compiled reference run on the same files."""
+    n, np_ = 4096, 3
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    primes = orc.primes(n, np_)
+    oracle_mod.write_key_files(str(tmp_path), n, primes, sk, pk0, pk1)
+    monkeypatch.chdir(tmp_path)
+    se = seb.SealEmbedded()
+    se.se_setup(n, np_, 12345.0, seb.api.SE_ASYM_ENCR if asym else seb.api.SE_SYM_ENCR)
+    try:
+        p = se.parms
+        assert p.coeff_count == n and p.nprimes == np_ and p.logn == 12
+        assert p.scale == 2.0 ** 25  # user scale overridden like set_parms_ckks (parameters.c:214)
+        assert [p.moduli[i].value for i in range(np_)] == primes
+        assert [(p.moduli[i].const_ratio[0], p.moduli[i].const_ratio[1]) for i in range(np_)] == \
+            [orc.const_ratio(q) for q in primes]
+        vals = oracle_mod.make_values(1, n // 2, seed=3)[0]
+        seed = oracle_mod.make_seeds(1, b"api")[0]
+        sseed = oracle_mod.make_seeds(1, b"api-share")[0]
+        se.set_reference_quirk(True)
+        chunks = []
+        assert se.se_encrypt_seeded(sseed, seed, _send_collector(chunks), vals)
+        assert len(chunks) == 2 * np_ and all(len(c) == 4 * n for c in chunks)
+        got = np.frombuffer(b"".join(chunks), np.uint32).reshape(np_, 2, n)
+        if asym:
+            ok, exp = orc.encrypt_asym(n, np_, vals, seed, pk0, pk1)
+        else:
+            ok, exp = orc.encrypt_sym(n, np_, vals, sseed, seed, sk, ref_quirk=True)
+        assert ok and np.array_equal(got, exp)
+        if oracle_mod.have_reference():
+            ref = oracle_mod.ReferenceLib()
+            ref.setup(n, np_, asym, sk=sk, pk0=pk0, pk1=pk1, primes=primes)
+            try:
+                okr, ctr = ref.encrypt_seeded(sseed, seed, vals)
+            finally:
+                ref.close()
+                os.chdir(tmp_path)
+            assert okr and np.array_equal(got, ctr)
+        # short input keeps earlier slots only (seal_embedded.c:108-111); NULL seeds draw randomness
+        chunks2 = []
+        assert se.se_encrypt(_send_collector(chunks2), vals[:16])
+        assert len(chunks2) == 2 * np_
+        assert b"".join(chunks2) != b"".join(chunks)
+        # batch extension
+        se.set_reference_quirk(False)
+        bvals = oracle_mod.make_values(3, n // 2, seed=4)
+        bseeds = oracle_mod.make_seeds(3, b"batch")
+        bshare = oracle_mod.make_seeds(3, b"batch-share")
+        ok, out = se.se_encrypt_batch_seeded(None if asym else bshare, bseeds, bvals)
+        assert ok
+        for b in range(3):
+            if asym:
+                _, exp = orc.encrypt_asym(n, np_, bvals[b], bseeds[b], pk0, pk1)
+            else:
+                _, exp = orc.encrypt_sym(n, np_, bvals[b], bshare[b], bseeds[b], sk)
+            assert np.array_equal(out[b], exp)
+    finally:
+        se.se_cleanup()
+
+
+def test_golden_fixtures(seb, torch_cuda, oracle_mod, ctxs):
+    """Committed vectors generated from the compiled reference (tests/golden/make_golden.py)."""
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLDEN, "encrypt_golden.npz"))
+    for key in [k[:-len("_digest")] for k in g.files if k.endswith("_digest")]:
+        n, np_, asym = (int(x) for x in g[key + "_cfg"])
+        vals, seeds, sseeds = g[key + "_values"], g[key + "_seeds"], g[key + "_sseeds"]
+        sk = oracle_mod.make_sk(n)
+        ctx = ctxs(n, np_, bool(asym))
+        batch = vals.shape[0]
+        d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+        if asym:
+            pk0, pk1 = oracle_mod.Oracle().gen_pk(n, np_, sk)
+            assert hashlib.sha256(pk0.tobytes() + pk1.tobytes()).digest() == g[key + "_pkdigest"].tobytes()
+            ctx.set_public_key(pk0, pk1)
+            ctx.encrypt_asym_device(dev(torch, vals), vals.shape[1], dev(torch, seeds), batch, d_out)
+        else:
+            ctx.set_secret_key(sk)
+            ctx.encrypt_sym_device(dev(torch, vals), vals.shape[1], dev(torch, sseeds), dev(torch, seeds), batch,
+                                   d_out, True)
+        assert ctx.encode_failures() == 0
+        got = host(d_out, np.uint32).reshape(batch, -1)
+        for b in range(batch):
+            assert hashlib.sha256(got[b].tobytes()).digest() == g[key + "_digest"][b].tobytes(), (key, b)
+        if key + "_ct0" in g.files:
+            assert np.array_equal(got[0], g[key + "_ct0"].reshape(-1))
+
+
+def test_full_size_properties(seb, torch_cuda, oracle_mod, orc, ctxs):
+    """Config B at full size (n=4096, 3 primes, batch 65536): size-independent properties —
+    (1) items are independent of batch position and grid shape (re-encrypting slices reproduces the
+    same per-item checksums), (2) first/last items equal the oracle bit for bit, (3) every residue
+    is < q, (4) decrypt+decode of sampled items returns the message within 0.1."""
+    torch = torch_cuda
+    n, np_ = 4096, 3
+    batch = 65536
+    ctx = ctxs(n, np_, True)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    ctx.set_public_key(pk0, pk1)
+    vlen = n // 2
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    d_vals = torch.rand((batch, vlen), generator=gen, device="cuda", dtype=torch.float32) * 32 - 16
+    d_seeds = torch.randint(0, 256, (batch, 64), generator=gen, device="cuda", dtype=torch.uint8)
+    d_out = torch.empty((batch, np_, 2, n), dtype=torch.int32, device="cuda")
+    ctx.encrypt_asym_device(d_vals, vlen, d_seeds, batch, d_out)
+    assert ctx.encode_failures() == 0
+    sums = d_out.view(batch, -1).to(torch.int64).sum(dim=1)
+    xors = d_out.view(batch, -1)[:, ::97].to(torch.int64).sum(dim=1)
+    for p, q in enumerate(ctx.primes):
+        assert int(d_out[:, p].max()) < q and int(d_out[:, p].min()) >= 0
+    # (1) slices with other batch sizes / offsets
+    for lo, hi in ((0, 1), (5, 777), (batch - 4099, batch)):
+        d_o2 = torch.empty((hi - lo, np_, 2, n), dtype=torch.int32, device="cuda")
+        ctx.encrypt_asym_device(d_vals[lo:hi].contiguous(), vlen, d_seeds[lo:hi].contiguous(), hi - lo, d_o2)
+        assert ctx.encode_failures() == 0
+        assert torch.equal(d_o2.view(hi - lo, -1).to(torch.int64).sum(dim=1), sums[lo:hi])
+        assert torch.equal(d_o2.view(hi - lo, -1)[:, ::97].to(torch.int64).sum(dim=1), xors[lo:hi])
+    # (2),(4) oracle on the ends
+    vals = d_vals.cpu().numpy()
+    seeds = d_seeds.cpu().numpy()
+    for b in (0, 1, batch // 2, batch - 1):
+        got = host(d_out[b], np.uint32).reshape(np_, 2, n)
+        ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        assert ok and np.array_equal(got, exp), b
+        dec = orc.decrypt_decode(n, np_, got, sk, vlen)
+        assert np.abs(dec - vals[b]).max() < 0.1
