@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — CKKS encryptions/s at n=4096, 3-prime RNS (BASELINE.json configs[1]) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path (N>1: under torchrun)
+  python bench.py --impl reference [--gpus N] --steps K --warmup W the reference's CPU path on this host
+
+One step = one pass of the hot path (encode -> sample u,e0,e1 -> 3 primes x [3 NTT + pointwise]) over
+one batch of 65536 synthetic fp32 messages per GPU, inputs resident in HBM.  Ciphertexts are
+independent, so N GPUs shard the batch with no data-path collective ("weak" scaling: the per-GPU
+batch is fixed).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DEG, N_PRIMES, BATCH = 4096, 3, 65536
+WORKLOAD = f"n={N_DEG}, {N_PRIMES}-prime RNS, batch={BATCH}/GPU, asymmetric encrypt (BASELINE.json configs[1])"
+METRIC = "ckks_encryptions_per_sec"
+UNIT = "ciphertexts/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ----------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref = the unmodified reference compiled here; else the oracle port)
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(conn, idx: int, n: int, np_: int, items: int):
+    """One process per core: the reference keeps static state (seal_embedded.c:18-22)."""
+    from oracle import oracle as O
+
+    orc = O.Oracle()
+    sk = O.make_sk(n)
+    pk0, pk1 = orc.gen_pk(n, np_, sk)
+    vals = O.make_values(items, n // 2, seed=1000 + idx)
+    seeds = O.make_seeds(items, b"cpu-%d" % idx)
+    ref = None
+    if O.have_reference():
+        ref = O.ReferenceLib()
+        ref.setup(n, np_, True, sk=sk, pk0=pk0, pk1=pk1, primes=orc.primes(n, np_))
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg == "stop":
+            break
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.encrypt_loop(None, seeds, vals)
+        else:
+            orc.encrypt_asym_batch(n, np_, vals, seeds, pk0, pk1)
+        conn.send(time.perf_counter() - t0)
+    if ref is not None:
+        ref.close()
+    conn.close()
+
+
+class CpuArm:
+    def __init__(self, items_per_worker: int, cores: int | None = None):
+        from oracle import oracle as O
+
+        O.build()
+        self.kind = "reference" if O.have_reference() else "port"
+        self.cores = cores or (os.cpu_count() or 1)
+        self.items = items_per_worker
+        ctx = mp.get_context("spawn")
+        self.procs, self.conns = [], []
+        for i in range(self.cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(b, i, N_DEG, N_PRIMES, items_per_worker), daemon=True)
+            p.start()
+            self.procs.append(p)
+            self.conns.append(a)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def step(self) -> float:
+        """All workers encrypt their `items` once; returns the slowest worker's seconds."""
+        for c in self.conns:
+            c.send("go")
+        return max(c.recv() for c in self.conns)
+
+    def close(self):
+        for c in self.conns:
+            c.send("stop")
+        for p in self.procs:
+            p.join(timeout=10)
+
+    def describe(self, value: float) -> dict:
+        return {"value": value, "unit": UNIT, "cores": self.cores, "kind": self.kind,
+                "sample": f"{self.items} items/process x {self.cores} processes per step, se_encrypt_seeded "
+                          f"n={N_DEG} {N_PRIMES} primes asym (one process per core: the reference is non-reentrant)"}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm(items_per_worker=96)
+    for _ in range(args.warmup):
+        arm.step()
+    times = [arm.step() for _ in range(args.steps)]
+    arm.close()
+    total = sum(times)
+    value = arm.cores * arm.items * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": N_DEG, "nprimes": N_PRIMES,
+                       "batch_per_step": arm.cores * arm.items, "host_threads": arm.cores},
+            "cpu_baseline": arm.describe(value),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gbps", "hbm_gb_s"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """dram read+write bytes per launch from the committed ncu summary, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_b200_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    seb = importlib.import_module("seal-embedded_b200")
+
+    n, np_, batch, vlen = N_DEG, N_PRIMES, args.batch, N_DEG // 2
+    ctx = seb.Context(n, np_, asym=True, device=local)
+    rng = np.random.default_rng(7)
+    pk0 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes])
+    pk1 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes])
+    ctx.set_public_key(pk0, pk1)
+    ctx.reserve(batch)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    d_vals = torch.rand((batch, vlen), generator=gen, device="cuda", dtype=torch.float32) * 32 - 16
+    d_seeds = torch.randint(0, 256, (batch, 64), generator=gen, device="cuda", dtype=torch.uint8)
+    d_out = torch.empty((batch, np_, 2, n), dtype=torch.int32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.encrypt_asym_device(d_vals, vlen, d_seeds, batch, d_out)
+
+    for _ in range(args.warmup):
+        step()
+    assert ctx.encode_failures() == 0
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launch_count
+    ctx.profile_begin(args.steps)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    kern_ms = ctx.profile_end()
+    launches = ctx.launch_count - launches0
+    clock_info = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * batch * args.steps / (ms_max * 1e-3)
+
+    # ---- NTT-only micro-benchmark (config E shape: same n, primes; polys >> L2), rank-local
+    polys = torch.randint(0, 1 << 30, (batch, np_, n), generator=gen, device="cuda", dtype=torch.int32)
+    for _ in range(2):
+        ctx.ntt_device(polys, batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ntt_iters = 5
+    for _ in range(ntt_iters):
+        ctx.ntt_device(polys, batch)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ntt_ms = e0.elapsed_time(e1) / ntt_iters
+    del polys
+
+    # ---- e2e: host buffers (pinned) through the host-pointer C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        eb = args.e2e_batch or batch
+        h_vals = torch.empty((eb, vlen), dtype=torch.float32).pin_memory()
+        h_vals.copy_(d_vals[:eb])
+        h_seeds = torch.empty((eb, 64), dtype=torch.uint8).pin_memory()
+        h_seeds.copy_(d_seeds[:eb])
+        h_out = torch.empty((eb, np_, 2, n), dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            rc = ctx.lib.seb_encrypt_asym_host(ctx.h, h_vals.data_ptr(), vlen, h_seeds.data_ptr(), eb,
+                                               h_out.data_ptr())
+            assert rc == 0, ctx.lib.seb_last_error()
+
+        e2e_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(1, min(args.steps, 5))
+        s0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        t2 = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item()) / e2e_steps
+        same = bool(torch.equal(h_out[:64].cuda(), d_out[:64]))
+        e2e = {"value": world * eb / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "batch_per_gpu": eb, "h2d_bytes_per_step": eb * (vlen * 4 + 64),
+               "d2h_bytes_per_step": eb * (np_ * 2 * n * 4 + 4), "matches_device_path": same,
+               "api": "seb_encrypt_asym_host (pinned host buffers, 2 chunks in flight)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (by measured share of the step)
+    names = ctx.PROFILE_SEGMENTS[True]
+    avg = kern_ms.mean(axis=0) if len(kern_ms) else np.zeros(4)
+    alg_bytes = {  # algorithmic bytes per ciphertext for each kernel (DESIGN.md "Kernels")
+        "encode": vlen * 4 + 8 * n,
+        "sample_ternary": 64 + n // 4 + 4,
+        "sample_cbd": 64 + 4 + 2 * n,
+        "encrypt": 8 * n + 2 * n + n // 4 + 8 * n * np_,
+    }
+    top = int(np.argmax(avg))
+    peak, peak_src = hbm_peak()
+    top_name = names[top]
+    achieved = alg_bytes[top_name] * batch / (avg[top] * 1e-3) / 1e9 if avg[top] > 0 else 0.0
+    kernel_sym = {"encode": "k_encode", "sample_ternary": "k_sample_ternary", "sample_cbd": "k_sample_cbd",
+                  "encrypt": "k_encrypt_asym"}[top_name]
+    roofline = {"kernel": kernel_sym, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(kernel_sym), "peak_source": peak_src,
+                "avg_launch_ms": float(avg[top]), "share_of_step": float(avg[top] / max(avg.sum(), 1e-9)),
+                "algorithmic_bytes_per_launch": alg_bytes[top_name] * batch,
+                "note": "integer-issue bound kernel (Keccak / modular butterflies), not an HBM-bound one: "
+                        "see ntt_microbench for the HBM-rooflined NTT-only kernel"}
+    ntt_gbs = 8 * n * np_ * batch / (ntt_ms * 1e-3) / 1e9
+    ntt_micro = {"kernel": "k_ntt_forward", "bound": "hbm", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
+                 "frac": ntt_gbs / peak, "traffic": ncu_traffic("k_ntt_forward"), "ms_per_launch": ntt_ms,
+                 "polys_per_launch": batch * np_, "algorithmic_bytes_per_launch": 8 * n * np_ * batch,
+                 "ntt_per_sec": batch * np_ / (ntt_ms * 1e-3)}
+
+    # ---- CPU baseline: the reference's own path on this host's cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        arm = CpuArm(items_per_worker=256)
+        arm.step()
+        secs = [arm.step() for _ in range(3)]
+        arm.close()
+        cpu = arm.describe(arm.cores * arm.items * len(secs) / sum(secs))
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": n, "nprimes": np_, "batch_per_gpu": batch,
+                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": f"inputs+outputs per step ({(d_vals.numel() * 4 + d_out.numel() * 4) >> 20} MiB) "
+                             "exceed the 126 MB L2"},
+            "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+            "kernels_ms": {nm: float(v) for nm, v in zip(names, avg)},
+            "roofline": roofline, "ntt_microbench": ntt_micro, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="ciphertexts per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="ciphertexts per GPU per e2e step (default: --batch)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,13 @@ int seb_encrypt_sym_device(seb_ctx *ctx, const float *d_values, size_t vlen,
  * (>= 0) or a negative error */
 int seb_encode_failures(seb_ctx *ctx);
 
+/* Per-kernel CUDA-event timing of the next max_steps *_device full-path calls (events recorded on
+ * the context's stream around each kernel).  seb_profile_end synchronises, writes ms[step][4]
+ * (asym: encode, sample_ternary, sample_cbd, encrypt; sym: encode, sample_cbd, sample_uniform,
+ * encrypt) and returns the number of steps recorded. */
+int seb_profile_begin(seb_ctx *ctx, int max_steps);
+int seb_profile_end(seb_ctx *ctx, float *ms);
+
 /* ---- full path, host pointers: pinned staging, chunked, H2D/compute/D2H overlapped ---- */
 int seb_encrypt_asym_host(seb_ctx *ctx, const float *values, size_t vlen, const uint8_t *seeds,
                           size_t batch, uint32_t *out);

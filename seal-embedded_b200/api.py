@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "seb_reserve", "seb_degree", "seb_nprimes", "seb_scale", "seb_prime", "seb_launch_count",
     "seb_encrypt_asym_device", "seb_encrypt_sym_device", "seb_encode_failures", "seb_encrypt_asym_host",
     "seb_encrypt_sym_host", "seb_encode_device", "seb_sample_asym_device", "seb_sample_cbd_device",
-    "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device",
+    "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
 ]
 
 
@@ -131,6 +131,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_sample_uniform_device.argtypes = [vp, vp, vp, sz, sz, vp, sz]
     L.seb_ntt_device.argtypes = [vp, vp, sz]
     L.seb_prng_blocks_device.argtypes = [vp, vp, vp, sz, vp]
+    L.seb_profile_begin.argtypes = [vp, i32]
+    L.seb_profile_end.argtypes = [vp, vp]
     L.se_setup_custom.argtypes = [sz, sz, vp, vp, C.c_double, i32]
     L.se_setup_custom.restype = C.POINTER(_SeParms)
     L.se_setup.argtypes = [sz, sz, C.c_double, i32]
@@ -253,6 +255,19 @@ class Context:
         self._check(self.lib.seb_encrypt_sym_host(self.h, _addr(values), vlen, _addr(share_seeds), _addr(seeds),
                                                   batch, _addr(out), int(ref_quirk)))
         return out
+
+    PROFILE_SEGMENTS = {True: ("encode", "sample_ternary", "sample_cbd", "encrypt"),
+                        False: ("encode", "sample_cbd", "sample_uniform", "encrypt")}
+
+    def profile_begin(self, max_steps: int) -> None:
+        self._prof_max = max_steps
+        self._check(self.lib.seb_profile_begin(self.h, max_steps))
+
+    def profile_end(self) -> np.ndarray:
+        """ms[step][4] per-kernel durations (CUDA events on the launching stream)."""
+        ms = np.zeros((max(self._prof_max, 1), 4), np.float32)
+        steps = self._check(self.lib.seb_profile_end(self.h, _addr(ms)))
+        return ms[:steps]
 
     # -- stage level
     def encode_device(self, d_values, vlen: int, batch: int, d_pt) -> None:

@@ -162,7 +162,22 @@ struct seb_ctx
     Scratch slot[2];
     size_t last_batch = 0;
     uint64_t launches = 0;
+    // per-kernel CUDA-event timing of the *_device full-path calls (seb_profile_begin/end)
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_max = 0, prof_step = 0;
+    bool prof_on = false;
 };
+
+#define SEB_PROF_SEGMENTS 4
+static inline void prof_mark(seb_ctx *c, cudaStream_t st, int k)
+{
+    if (c->prof_on && st == c->stream && c->prof_step < c->prof_max)
+        cudaEventRecord(c->prof_ev[(size_t)c->prof_step * (SEB_PROF_SEGMENTS + 1) + k], st);
+}
+static inline void prof_next(seb_ctx *c, cudaStream_t st)
+{
+    if (c->prof_on && st == c->stream && c->prof_step < c->prof_max) c->prof_step++;
+}
 
 static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
 {
@@ -335,6 +350,7 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaFree(c->d_pk0);
     cudaFree(c->d_pk1);
     cudaFree(c->d_ntt_s);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -504,13 +520,19 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
                            size_t batch, uint32_t *d_out, cudaStream_t st)
 {
     const int n = (int)c->n;
+    prof_mark(c, st, 0);
     int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
     if (r) return r;
+    prof_mark(c, st, 1);
     seb_launch_sample_ternary(d_seeds, s.u, s.ctr, n, (int)batch, st);
+    prof_mark(c, st, 2);
     seb_launch_sample_cbd(d_seeds, s.ctr, s.e, n, 2, (int)batch, st);
     CU(cudaGetLastError());
+    prof_mark(c, st, 3);
     CU(seb_launch_encrypt_asym(c->logn, s.pt, s.e, s.u, c->d_roots, c->d_pk0, c->d_pk1, c->mods, (int)c->np, d_out,
                                (int)batch, st));
+    prof_mark(c, st, 4);
+    prof_next(c, st);
     c->launches += 3;
     return 0;
 }
@@ -521,16 +543,22 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
                           const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk, cudaStream_t st)
 {
     const int n = (int)c->n;
+    prof_mark(c, st, 0);
     int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
     if (r) return r;
+    prof_mark(c, st, 1);
     seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
+    prof_mark(c, st, 2);
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
     const size_t ct_stride = 2 * c->np * c->n;
     for (size_t p = 0; p < c->np; p++)
         seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch, st);
     CU(cudaGetLastError());
+    prof_mark(c, st, 3);
     CU(seb_launch_encrypt_sym(c->logn, s.pt, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,
                               (int)batch, st));
+    prof_mark(c, st, 4);
+    prof_next(c, st);
     c->launches += 2 + 2 * c->np;
     return 0;
 }
@@ -557,6 +585,38 @@ extern "C" int seb_encrypt_sym_device(seb_ctx *c, const float *d_values, size_t 
     if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
     c->last_batch = batch;
     return encrypt_sym_on(c, c->slot[0], d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, c->stream);
+}
+
+// Per-kernel timing of the next `max_steps` full-path *_device calls: CUDA events are recorded on
+// the context's stream around each kernel (asym: encode, sample_ternary, sample_cbd, encrypt;
+// sym: encode, sample_cbd, sample_uniform (all primes), encrypt).
+extern "C" int seb_profile_begin(seb_ctx *c, int max_steps)
+{
+    if (!c || max_steps < 0) return fail(SE_ERR_INVALD_ARGUMENT, "bad argument");
+    const size_t need = (size_t)max_steps * (SEB_PROF_SEGMENTS + 1);
+    while (c->prof_ev.size() < need)
+    {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+    }
+    c->prof_max  = max_steps;
+    c->prof_step = 0;
+    c->prof_on   = max_steps > 0;
+    return 0;
+}
+
+// Synchronises the stream, stops profiling and writes ms[step][4]; returns the number of steps.
+extern "C" int seb_profile_end(seb_ctx *c, float *ms)
+{
+    if (!c || !ms) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(cudaStreamSynchronize(c->stream));
+    c->prof_on = false;
+    for (int s = 0; s < c->prof_step; s++)
+        for (int k = 0; k < SEB_PROF_SEGMENTS; k++)
+            CU(cudaEventElapsedTime(ms + s * SEB_PROF_SEGMENTS + k, c->prof_ev[(size_t)s * (SEB_PROF_SEGMENTS + 1) + k],
+                                    c->prof_ev[(size_t)s * (SEB_PROF_SEGMENTS + 1) + k + 1]));
+    return c->prof_step;
 }
 
 extern "C" int seb_encode_failures(seb_ctx *c)
