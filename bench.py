@@ -123,7 +123,7 @@ def run_reference_arm(args) -> None:
             "cpu_baseline": arm.describe(value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=float), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -357,7 +357,7 @@ def run_b200_arm(args) -> None:
             "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
             "kernels_ms": {nm: float(v) for nm, v in zip(names, avg)},
             "roofline": roofline, "ntt_microbench": ntt_micro, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=float), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

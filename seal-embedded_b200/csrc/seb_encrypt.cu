@@ -14,6 +14,7 @@
 #include "seb_kernels.h"
 #include "seb_ntt.cuh"
 
+
 // ---------------------------------------------------------------------------------------------
 // on-load conversions (all produce values the lazy butterflies accept, i.e. < 4q)
 // ---------------------------------------------------------------------------------------------
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E) k_ntt_forward(uint32_t *_
                                                                      int np)
 {
     constexpr int N = 1 << LOGN;
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     const int t         = threadIdx.x;
     const size_t poly   = blockIdx.x;
     const int p         = (int)(poly % (size_t)np);
@@ -111,55 +112,132 @@ __device__ __forceinline__ uint32_t mul_add_final(uint32_t x, uint2 w, uint32_t 
     return seb_csub(prod + seb_final_reduce(y, q, two_q), q);
 }
 
+// c0/c1 for one run of 4 coefficients starting at pos; ue/up = ntt(e1)/ntt(m+e0) values (lazy)
+__device__ __forceinline__ void asym_store4(const uint32_t (&xu)[4], const uint32_t (&xe)[4], const uint32_t (&xp)[4],
+                                            const uint2 *__restrict__ k0, const uint2 *__restrict__ k1,
+                                            uint32_t *__restrict__ c0, uint32_t *__restrict__ c1, uint32_t pos,
+                                            uint32_t q, uint32_t two_q)
+{
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(k0 + pos));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(k0 + pos + 2));
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(k1 + pos));
+    const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(k1 + pos + 2));
+    uint4 v0, v1;
+    v0.x = mul_add_final(xu[0], make_uint2(a0.x, a0.y), xp[0], q, two_q);
+    v0.y = mul_add_final(xu[1], make_uint2(a0.z, a0.w), xp[1], q, two_q);
+    v0.z = mul_add_final(xu[2], make_uint2(a1.x, a1.y), xp[2], q, two_q);
+    v0.w = mul_add_final(xu[3], make_uint2(a1.z, a1.w), xp[3], q, two_q);
+    v1.x = mul_add_final(xu[0], make_uint2(b0.x, b0.y), xe[0], q, two_q);
+    v1.y = mul_add_final(xu[1], make_uint2(b0.z, b0.w), xe[1], q, two_q);
+    v1.z = mul_add_final(xu[2], make_uint2(b1.x, b1.y), xe[2], q, two_q);
+    v1.w = mul_add_final(xu[3], make_uint2(b1.z, b1.w), xe[3], q, two_q);
+    seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), v0);
+    seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), v1);
+}
+
+// Three polynomials at once (registers permitting): every twiddle fetched once for all three.
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E)
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
     k_encrypt_asym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
                    const uint2 *__restrict__ roots, const uint2 *__restrict__ pk0s,
                    const uint2 *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
                    uint32_t *__restrict__ out)
 {
     constexpr int N = 1 << LOGN;
-    extern __shared__ uint32_t smem[];
-    const int t      = threadIdx.x;
-    const size_t b   = blockIdx.x / (unsigned)np;
-    const int p      = (int)(blockIdx.x % (unsigned)np);
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t        = threadIdx.x;
+    const size_t b     = blockIdx.x / (unsigned)np;
+    const int p        = (int)(blockIdx.x % (unsigned)np);
     const SebModulus m = mods.m[p];
 
     LoadAsym ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
     uint32_t x[3][SEB_E];
     seb_ntt_forward<LOGN, 3>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
 
-    using O          = NttOut<LOGN>;
-    uint32_t *c0     = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1     = c0 + N;
-    const uint2 *k0  = pk0s + (size_t)p * N;
-    const uint2 *k1  = pk1s + (size_t)p * N;
+    using O         = NttOut<LOGN>;
+    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1    = c0 + N;
+    const uint2 *k0 = pk0s + (size_t)p * N;
+    const uint2 *k1 = pk1s + (size_t)p * N;
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
-    {
-        const uint32_t pos0 = O::pos(t, i);
 #pragma unroll
         for (int k = 0; k < O::RUN / 4; k++)
         {
-            const uint32_t pos = pos0 + 4 * k;
-            const uint4 a0     = __ldg(reinterpret_cast<const uint4 *>(k0 + pos));
-            const uint4 a1     = __ldg(reinterpret_cast<const uint4 *>(k0 + pos + 2));
-            const uint4 b0     = __ldg(reinterpret_cast<const uint4 *>(k1 + pos));
-            const uint4 b1     = __ldg(reinterpret_cast<const uint4 *>(k1 + pos + 2));
-            const int r        = i * O::RUN + 4 * k;
-            uint4 v0, v1;
-            v0.x = mul_add_final(x[0][r + 0], make_uint2(a0.x, a0.y), x[2][r + 0], m.q, m.two_q);
-            v0.y = mul_add_final(x[0][r + 1], make_uint2(a0.z, a0.w), x[2][r + 1], m.q, m.two_q);
-            v0.z = mul_add_final(x[0][r + 2], make_uint2(a1.x, a1.y), x[2][r + 2], m.q, m.two_q);
-            v0.w = mul_add_final(x[0][r + 3], make_uint2(a1.z, a1.w), x[2][r + 3], m.q, m.two_q);
-            v1.x = mul_add_final(x[0][r + 0], make_uint2(b0.x, b0.y), x[1][r + 0], m.q, m.two_q);
-            v1.y = mul_add_final(x[0][r + 1], make_uint2(b0.z, b0.w), x[1][r + 1], m.q, m.two_q);
-            v1.z = mul_add_final(x[0][r + 2], make_uint2(b1.x, b1.y), x[1][r + 2], m.q, m.two_q);
-            v1.w = mul_add_final(x[0][r + 3], make_uint2(b1.z, b1.w), x[1][r + 3], m.q, m.two_q);
-            seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), v0);
-            seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), v1);
+            const int r = i * O::RUN + 4 * k;
+            const uint32_t xu[4] = {x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]};
+            const uint32_t xe[4] = {x[1][r], x[1][r + 1], x[1][r + 2], x[1][r + 3]};
+            const uint32_t xp[4] = {x[2][r], x[2][r + 1], x[2][r + 2], x[2][r + 3]};
+            asym_store4(xu, xe, xp, k0, k1, c0, c1, O::pos(t, i) + 4 * k, m.q, m.two_q);
         }
+}
+
+// Large degrees (n >= 8192): the three transforms run one after another through one working
+// buffer so the register footprint stays that of a single NTT; ntt(e1) and ntt(m+e0) wait in
+// shared memory (in the slots of the thread that will consume them) for ntt(u)'s epilogue.
+struct LoadOne
+{
+    LoadAsym a;
+    int which;
+    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return a(which, pos); }
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
+    k_encrypt_asym_seq(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
+                       const uint2 *__restrict__ roots, const uint2 *__restrict__ pk0s,
+                       const uint2 *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
+                       uint32_t *__restrict__ out)
+{
+    constexpr int N          = 1 << LOGN;
+    constexpr uint32_t WORDS = NttSmem<LOGN>::WORDS;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t        = threadIdx.x;
+    const size_t b     = blockIdx.x / (unsigned)np;
+    const int p        = (int)(blockIdx.x % (unsigned)np);
+    const SebModulus m = mods.m[p];
+    const uint2 *tw    = roots + (size_t)p * N;
+    using O            = NttOut<LOGN>;
+
+    uint32_t x[1][SEB_E];
+    LoadOne ld{LoadAsym{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
+#pragma unroll 1
+    for (int which = 1; which <= 2; which++)  // 1: e1 -> buffer 1, 2: m+e0 -> buffer 2
+    {
+        ld.which = which;
+        seb_ntt_forward<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+#pragma unroll
+        for (int i = 0; i < O::GPL; i++)
+#pragma unroll
+            for (int k = 0; k < O::RUN / 4; k++)
+            {
+                const int r = i * O::RUN + 4 * k;
+                *reinterpret_cast<uint4 *>(smem + which * WORDS + seb_pad<LOGN>(O::pos(t, i)) + 4 * k) =
+                    make_uint4(x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]);
+            }
+        __syncthreads();  // the working buffer is about to be overwritten by the next transform
     }
+    ld.which = 0;
+    seb_ntt_forward<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+
+    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1    = c0 + N;
+    const uint2 *k0 = pk0s + (size_t)p * N;
+    const uint2 *k1 = pk1s + (size_t)p * N;
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+#pragma unroll
+        for (int k = 0; k < O::RUN / 4; k++)
+        {
+            const int r       = i * O::RUN + 4 * k;
+            const uint32_t sp = seb_pad<LOGN>(O::pos(t, i)) + 4 * k;
+            const uint4 ve    = *reinterpret_cast<const uint4 *>(smem + WORDS + sp);
+            const uint4 vp    = *reinterpret_cast<const uint4 *>(smem + 2 * WORDS + sp);
+            const uint32_t xu[4] = {x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]};
+            const uint32_t xe[4] = {ve.x, ve.y, ve.z, ve.w};
+            const uint32_t xp[4] = {vp.x, vp.y, vp.z, vp.w};
+            asym_store4(xu, xe, xp, k0, k1, c0, c1, O::pos(t, i) + 4 * k, m.q, m.two_q);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,7 +258,7 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
                   uint32_t *__restrict__ out, int quirk)
 {
     constexpr int N = 1 << LOGN;
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     const int t        = threadIdx.x;
     const size_t b     = blockIdx.x / (unsigned)np;
     const int p        = (int)(blockIdx.x % (unsigned)np);
@@ -243,11 +321,13 @@ cudaError_t seb_encrypt_configure(int logn)
     cudaError_t err = cudaSuccess;
 #define CFG(L)                                                                                                    \
     {                                                                                                             \
-        err = cudaFuncSetAttribute(k_ntt_forward<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << L);        \
+        err = cudaFuncSetAttribute(k_ntt_forward<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<L>::WORDS);        \
         if (err == cudaSuccess)                                                                                   \
-            err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 << L);  \
+            err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
         if (err == cudaSuccess)                                                                                   \
-            err = cudaFuncSetAttribute(k_encrypt_sym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << L);    \
+            err = cudaFuncSetAttribute(k_encrypt_asym_seq<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
+        if (err == cudaSuccess)                                                                                   \
+            err = cudaFuncSetAttribute(k_encrypt_sym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<L>::WORDS);    \
     }
     SEB_DISPATCH_LOGN(logn, CFG)
 #undef CFG
@@ -258,7 +338,7 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const 
                            size_t npolys_total, cudaStream_t st)
 {
     if (npolys_total == 0) return cudaSuccess;
-#define RUN(L) k_ntt_forward<L><<<(unsigned)npolys_total, (1 << L) / SEB_E, 4 << L, st>>>(polys, roots, mods, np)
+#define RUN(L) k_ntt_forward<L><<<(unsigned)npolys_total, (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(polys, roots, mods, np)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
@@ -269,9 +349,13 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
-#define RUN(L)                                                                                            \
-    k_encrypt_asym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 << L, st>>>(pt, e, u, roots, pk0s, \
-                                                                                           pk1s, mods, np, out)
+#define RUN(L)                                                                                                 \
+    if (L >= 13)                                                                                               \
+        k_encrypt_asym_seq<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(  \
+            pt, e, u, roots, pk0s, pk1s, mods, np, out);                                                       \
+    else                                                                                                       \
+        k_encrypt_asym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(      \
+            pt, e, u, roots, pk0s, pk1s, mods, np, out)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
@@ -283,7 +367,7 @@ cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e,
 {
     if (batch <= 0) return cudaSuccess;
 #define RUN(L)                                                                                              \
-    k_encrypt_sym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 4 << L, st>>>(pt, e, roots, ntt_s, mods, \
+    k_encrypt_sym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, e, roots, ntt_s, mods, \
                                                                                          np, out, quirk)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN

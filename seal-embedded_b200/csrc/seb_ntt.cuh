@@ -15,8 +15,12 @@
 //     first pass takes its inputs from a loader functor (global memory / on-the-fly expansion)
 //     and the last pass, whose groups are 2^R contiguous coefficients, hands each thread its
 //     contiguous outputs so the caller can fuse its epilogue and issue 128-bit stores.
-//   * shared-memory words are XOR-swizzled (seb_swz) so every pass is bank-conflict free
-//     (checked exhaustively by tests/test_host_logic.py::test_swizzle_conflict_free).
+//   * shared-memory words are laid out with padding (seb_pad: a few words inserted every 32/64/128
+//     coefficients, per plan) so that every pass is bank-conflict free AND the address of element
+//     j of a group is phys(base) + a compile-time constant, i.e. an immediate offset: no
+//     per-access address arithmetic (checked exhaustively by
+//     tests/test_host_logic.py::test_smem_layout_conflict_free).  The last pass reads its 2^R
+//     contiguous coefficients with 128-bit loads.
 //   * NPOLY polynomials that share the modulus go through the passes together so each twiddle
 //     is fetched once for all of them.
 #pragma once
@@ -70,14 +74,19 @@ struct NttS0<LOGN, 0>
     static constexpr int value = 0;
 };
 
-// bank swizzle of a coefficient index (word address inside one polynomial's buffer)
+// Padded shared-memory layout: physical word of coefficient index a.  Additive over bit-disjoint
+// fields: seb_pad(x | y) = seb_pad(x) + seb_pad(y) whenever x & y == 0.
 template <int LOGN>
-__host__ __device__ __forceinline__ uint32_t seb_swz(uint32_t a)
+__host__ __device__ __forceinline__ constexpr uint32_t seb_pad(uint32_t a)
 {
-    if (LOGN == 12) return a ^ ((a >> 5) & 15u) ^ (((a >> 8) & 1u) << 4);
-    if (LOGN == 11) return a ^ ((a >> 5) & 7u) ^ (((a >> 7) & 3u) << 3);
-    return a ^ ((a >> 5) & 7u) ^ (((a >> 6) & 3u) << 3);
+    return a + 4u * (a >> 5) + (LOGN == 11 ? 4u * (a >> 6) : 0u) + (LOGN == 12 ? 8u * (a >> 7) : 0u);
 }
+// words of shared memory one polynomial occupies
+template <int LOGN>
+struct NttSmem
+{
+    static constexpr uint32_t WORDS = (seb_pad<LOGN>((1u << LOGN) - 1u) + 4u) & ~3u;
+};
 
 // Harvey lazy butterfly: X,Y in [0,4q) -> X+WY, X-WY in [0,4q) (ntt.c:94-105)
 __device__ __forceinline__ void seb_bfly(uint32_t &x, uint32_t &y, const uint2 w, const uint32_t q,
@@ -101,17 +110,31 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
     for (int r = 0; r < R; r++)
     {
         const int half = 1 << (R - 1 - r);
+        // the 2^r twiddles of this stage are contiguous and 2^r-aligned: fetch them two at a time
+        uint2 w[1 << (R - 1)];
+        if (r == 0)
+            w[0] = __ldg(tw + twbase);
+        else
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(tw + (twbase << r));
+#pragma unroll
+            for (int m = 0; m < (1 << r) / 2; m++)
+            {
+                const uint4 v = __ldg(src + m);
+                w[2 * m]      = make_uint2(v.x, v.y);
+                w[2 * m + 1]  = make_uint2(v.z, v.w);
+            }
+        }
 #pragma unroll
         for (int m = 0; m < (1 << r); m++)
         {
-            const uint2 w = __ldg(tw + ((twbase << r) + m));
 #pragma unroll
             for (int t = 0; t < half; t++)
             {
                 const int ia = gofs + m * 2 * half + t;
                 const int ib = ia + half;
 #pragma unroll
-                for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], w, q, two_q);
+                for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], w[m], q, two_q);
             }
         }
     }
@@ -133,6 +156,7 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
     constexpr int GP    = SEB_E >> R;     // groups per thread
     constexpr bool LAST = (P == NttPlan<LOGN>::NPASS - 1);
 
+    constexpr uint32_t WORDS = NttSmem<LOGN>::WORDS;
 #pragma unroll
     for (int i = 0; i < GP; i++)
     {
@@ -140,29 +164,45 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
         const uint32_t off  = g & ((1u << LS) - 1u);
         const uint32_t blk  = g >> LS;
         const uint32_t base = (blk << (LS + R)) | off;
-#pragma unroll
-        for (int j = 0; j < (1 << R); j++)
+        uint32_t *sp        = smem + seb_pad<LOGN>(base);  // element j lives at sp[seb_pad(j << LS)]
+        if (P == 0)
         {
-            const uint32_t pos = base | ((uint32_t)j << LS);
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
+#pragma unroll
+                for (int p = 0; p < NPOLY; p++) x[p][i * (1 << R) + j] = load(p, base | ((uint32_t)j << LS));
+        }
+        else if (LAST)
+        {
+            // 2^R contiguous coefficients: 128-bit shared loads (LS == 0, base = g << R)
 #pragma unroll
             for (int p = 0; p < NPOLY; p++)
-            {
-                if (P == 0)
-                    x[p][i * (1 << R) + j] = load(p, pos);
-                else
-                    x[p][i * (1 << R) + j] = smem[p * N + seb_swz<LOGN>(pos)];
-            }
+#pragma unroll
+                for (int k = 0; k < (1 << R) / 4; k++)
+                {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sp + p * WORDS + 4 * k);
+                    x[p][i * (1 << R) + 4 * k + 0] = v.x;
+                    x[p][i * (1 << R) + 4 * k + 1] = v.y;
+                    x[p][i * (1 << R) + 4 * k + 2] = v.z;
+                    x[p][i * (1 << R) + 4 * k + 3] = v.w;
+                }
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
+#pragma unroll
+                for (int p = 0; p < NPOLY; p++)
+                    x[p][i * (1 << R) + j] = sp[p * WORDS + seb_pad<LOGN>((uint32_t)j << LS)];
         }
         seb_radix_regs<R, NPOLY>(x, i * (1 << R), tw, (1u << S0) + blk, q, two_q);
         if (!LAST)
         {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++)
-            {
-                const uint32_t pos = base | ((uint32_t)j << LS);
 #pragma unroll
-                for (int p = 0; p < NPOLY; p++) smem[p * N + seb_swz<LOGN>(pos)] = x[p][i * (1 << R) + j];
-            }
+                for (int p = 0; p < NPOLY; p++)
+                    sp[p * WORDS + seb_pad<LOGN>((uint32_t)j << LS)] = x[p][i * (1 << R) + j];
         }
     }
 }
@@ -185,7 +225,7 @@ struct SebNttRun
 };
 
 // Full forward NTT of NPOLY polynomials sharing one modulus, executed by the T = n/16 threads
-// t = 0..T-1 that share `smem` (NPOLY*n words).  On return thread t holds, for each of its
+// t = 0..T-1 that share `smem` (NPOLY * NttSmem<LOGN>::WORDS words, 16-byte aligned).  On return thread t holds, for each of its
 // GPL = 16 >> R_last groups i, the 2^R_last contiguous coefficients starting at
 // seb_ntt_out_pos<LOGN>(t, i), still lazy in [0,4q).  All T threads must call (barriers inside).
 // The caller must __syncthreads() before smem is reused.

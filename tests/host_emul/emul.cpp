@@ -43,9 +43,10 @@ static void ntt_emul(const uint32_t *in, const uint2 *tw, uint32_t q, uint32_t *
     constexpr int N = 1 << LOGN;
     constexpr int T = N / SEB_E;
     std::vector<std::array<uint32_t[SEB_E], NPOLY>> regs(T);
-    std::vector<uint32_t> smem((size_t)NPOLY * N, 0xDEADBEEFu);
+    std::vector<uint32_t> smem_store((size_t)NPOLY * NttSmem<LOGN>::WORDS + 4, 0xDEADBEEFu);
+    uint32_t *smem_al = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(smem_store.data()) + 15) & ~uintptr_t(15));
     HostLoad ld{in, N};
-    ntt_passes<LOGN, NPOLY, 0>(regs, smem.data(), tw, q, ld);
+    ntt_passes<LOGN, NPOLY, 0>(regs, smem_al, tw, q, ld);
     using O = NttOut<LOGN>;
     for (int t = 0; t < T; t++)
         for (int i = 0; i < O::GPL; i++)
@@ -81,17 +82,30 @@ extern "C" int emul_ntt(int logn, int npoly, const uint32_t *in, const uint32_t 
     return -1;
 }
 
-extern "C" uint32_t emul_swz(int logn, uint32_t a)
+extern "C" uint32_t emul_pad(int logn, uint32_t a)
 {
     switch (logn)
     {
-        case 10: return seb_swz<10>(a);
-        case 11: return seb_swz<11>(a);
-        case 12: return seb_swz<12>(a);
-        case 13: return seb_swz<13>(a);
-        case 14: return seb_swz<14>(a);
+        case 10: return seb_pad<10>(a);
+        case 11: return seb_pad<11>(a);
+        case 12: return seb_pad<12>(a);
+        case 13: return seb_pad<13>(a);
+        case 14: return seb_pad<14>(a);
     }
     return a;
+}
+
+extern "C" uint32_t emul_smem_words(int logn)
+{
+    switch (logn)
+    {
+        case 10: return NttSmem<10>::WORDS;
+        case 11: return NttSmem<11>::WORDS;
+        case 12: return NttSmem<12>::WORDS;
+        case 13: return NttSmem<13>::WORDS;
+        case 14: return NttSmem<14>::WORDS;
+    }
+    return 0;
 }
 
 extern "C" int emul_plan(int logn, int *radices)
