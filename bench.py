@@ -216,7 +216,9 @@ def run_b200_arm(args) -> None:
     pk1 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes])
     ctx.set_public_key(pk0, pk1)
     ctx.reserve(batch)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared with torch, so torch.cuda.Event times the kernels' own stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)

@@ -153,11 +153,11 @@ struct seb_ctx
     SebModuli mods;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // resident tables
-    uint2 *d_roots      = nullptr;  // [np][n]
+    seb_oct *d_roots    = nullptr;  // [np][seb_table_octs]: per-pass twiddle tables
     double2 *d_tw       = nullptr;  // [n]
     uint16_t *d_src_map = nullptr;  // [n]
-    uint2 *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n] Shoup pairs
-    uint2 *d_ntt_s = nullptr;                  // [np][n] Shoup pairs
+    seb_oct *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n/4] Shoup pairs, epilogue order
+    seb_oct *d_ntt_s = nullptr;                  // [np][n/4] Shoup pairs, epilogue order
     bool have_pk = false, have_sk = false;
     Scratch slot[2];
     size_t last_batch = 0;
@@ -224,20 +224,25 @@ static void free_scratch(Scratch &s)
 static int build_tables(seb_ctx *c)
 {
     const size_t n = c->n;
-    // NTT roots, bit-reversed powers of psi in Shoup form (ntt.c:40-52, uintmodarith.h:293-297)
-    std::vector<uint2> roots(c->np * n);
+    // NTT roots: bit-reversed powers of psi in Shoup form (ntt.c:40-52, uintmodarith.h:293-297),
+    // re-ordered per pass into the layout the kernels read with coalesced 256-bit loads
+    const size_t octs = seb_table_octs(c->logn);
+    std::vector<seb_oct> tabs(c->np * octs);
+    memset(tabs.data(), 0, tabs.size() * sizeof(seb_oct));
+    std::vector<uint2> roots(n);
     for (size_t p = 0; p < c->np; p++)
     {
         const uint32_t q = c->primes[p], psi = c->psis[p];
         uint32_t pw      = 1;
         for (size_t i = 0; i < n; i++)
         {
-            roots[p * n + bitrev(i, c->logn)] = make_uint2(pw, shoup(pw, q));
-            pw                                = mulmod(pw, psi, q);
+            roots[bitrev(i, c->logn)] = make_uint2(pw, shoup(pw, q));
+            pw                        = mulmod(pw, psi, q);
         }
+        seb_host_build_tw(c->logn, roots.data(), tabs.data() + p * octs);
     }
-    CU(cudaMalloc(&c->d_roots, roots.size() * sizeof(uint2)));
-    CU(cudaMemcpy(c->d_roots, roots.data(), roots.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_roots, tabs.size() * sizeof(seb_oct)));
+    CU(cudaMemcpy(c->d_roots, tabs.data(), tabs.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
 
     // IFFT twiddles from the host libm, same expression as fft.c:27-45 (+ conj at fft.c:129)
     std::vector<double2> tw(n);
@@ -368,18 +373,22 @@ extern "C" double seb_scale(const seb_ctx *c) { return c ? c->scale : 0; }
 extern "C" uint32_t seb_prime(const seb_ctx *c, size_t i) { return (c && i < c->np) ? c->primes[i] : 0; }
 extern "C" uint64_t seb_launch_count(const seb_ctx *c) { return c ? c->launches : 0; }
 
-static int upload_shoup(seb_ctx *c, const uint32_t *host, uint2 **dst)
+static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst)
 {
-    std::vector<uint2> tab(c->np * c->n);
+    std::vector<uint2> nat(c->n);
+    std::vector<seb_oct> tab(c->np * (c->n / 4));
     for (size_t p = 0; p < c->np; p++)
+    {
         for (size_t i = 0; i < c->n; i++)
         {
             const uint32_t w = host[p * c->n + i];
             if (w >= c->primes[p]) return fail(SE_ERR_INVALD_ARGUMENT, "key coefficient %u >= modulus", w);
-            tab[p * c->n + i] = make_uint2(w, shoup(w, c->primes[p]));
+            nat[i] = make_uint2(w, shoup(w, c->primes[p]));
         }
-    if (!*dst) CU(cudaMalloc(dst, tab.size() * sizeof(uint2)));
-    CU(cudaMemcpy(*dst, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        seb_host_build_epi(c->logn, nat.data(), tab.data() + p * (c->n / 4));
+    }
+    if (!*dst) CU(cudaMalloc(dst, tab.size() * sizeof(seb_oct)));
+    CU(cudaMemcpy(*dst, tab.data(), tab.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
     return 0;
 }
 

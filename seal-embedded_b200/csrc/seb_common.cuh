@@ -92,13 +92,44 @@ __device__ __forceinline__ uint32_t seb_final_reduce(uint32_t x, uint32_t q, uin
     return seb_csub(seb_csub(x, two_q), q);
 }
 
+// 256-bit accesses (sm_100: LDG.E.256 / STG.E.256): one full 32-byte sector per lane
+struct __align__(32) seb_oct
+{
+    uint32_t v[8];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ seb_oct seb_ldg256(const seb_oct *p)
+{
+    seb_oct r;  // read-only tables: plain (non-volatile) asm so the compiler may schedule it freely
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                   "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void seb_stg256_stream(seb_oct *p, const seb_oct &r)
+{
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]),
+                 "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+                 : "memory");
+}
+#else
+static inline seb_oct seb_ldg256(const seb_oct *p) { return *p; }
+static inline void seb_stg256_stream(seb_oct *p, const seb_oct &r) { *p = r; }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // cache-hinted global accesses for streamed (touched-once) data
 // ---------------------------------------------------------------------------------------------
+#ifndef __CUDACC__
+static inline uint4 seb_ldg_stream(const uint4 *p) { return *p; }
+static inline uint32_t seb_ldg_stream(const uint32_t *p) { return *p; }
+static inline void seb_stg_stream(uint4 *p, const uint4 &v) { *p = v; }
+#else
 __device__ __forceinline__ uint4 seb_ldg_stream(const uint4 *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
@@ -106,7 +137,7 @@ __device__ __forceinline__ uint4 seb_ldg_stream(const uint4 *p)
 __device__ __forceinline__ uint32_t seb_ldg_stream(const uint32_t *p)
 {
     uint32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void seb_stg_stream(uint4 *p, const uint4 &v)
@@ -115,3 +146,4 @@ __device__ __forceinline__ void seb_stg_stream(uint4 *p, const uint4 &v)
                  "r"(v.w)
                  : "memory");
 }
+#endif

@@ -53,7 +53,7 @@ struct LoadPlain
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E) k_ntt_forward(uint32_t *__restrict__ polys,
-                                                                     const uint2 *__restrict__ roots,
+                                                                     const seb_oct *__restrict__ roots,
                                                                      const __grid_constant__ SebModuli mods,
                                                                      int np)
 {
@@ -67,22 +67,20 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E) k_ntt_forward(uint32_t *_
 
     uint32_t x[1][SEB_E];
     LoadPlain ld{data};
-    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
 
     using O = NttOut<LOGN>;
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
     {
-        uint4 *dst = reinterpret_cast<uint4 *>(data + O::pos(t, i));
+        seb_oct *dst = reinterpret_cast<seb_oct *>(data + O::pos(t, i));
 #pragma unroll
-        for (int k = 0; k < O::RUN / 4; k++)
+        for (int k = 0; k < O::RUN / 8; k++)
         {
-            uint4 v;
-            v.x = seb_final_reduce(x[0][i * O::RUN + 4 * k + 0], m.q, m.two_q);
-            v.y = seb_final_reduce(x[0][i * O::RUN + 4 * k + 1], m.q, m.two_q);
-            v.z = seb_final_reduce(x[0][i * O::RUN + 4 * k + 2], m.q, m.two_q);
-            v.w = seb_final_reduce(x[0][i * O::RUN + 4 * k + 3], m.q, m.two_q);
-            seb_stg_stream(dst + k, v);
+            seb_oct v;
+#pragma unroll
+            for (int c = 0; c < 8; c++) v.v[c] = seb_final_reduce(x[0][i * O::RUN + 8 * k + c], m.q, m.two_q);
+            seb_stg256_stream(dst + k, v);
         }
     }
 }
@@ -112,35 +110,36 @@ __device__ __forceinline__ uint32_t mul_add_final(uint32_t x, uint2 w, uint32_t 
     return seb_csub(prod + seb_final_reduce(y, q, two_q), q);
 }
 
-// c0/c1 for one run of 4 coefficients starting at pos; ue/up = ntt(e1)/ntt(m+e0) values (lazy)
-__device__ __forceinline__ void asym_store4(const uint32_t (&xu)[4], const uint32_t (&xe)[4], const uint32_t (&xp)[4],
-                                            const uint2 *__restrict__ k0, const uint2 *__restrict__ k1,
-                                            uint32_t *__restrict__ c0, uint32_t *__restrict__ c1, uint32_t pos,
-                                            uint32_t q, uint32_t two_q)
+// c0/c1 for 8 consecutive coefficients starting at pos; xe/xp = ntt(e1)/ntt(m+e0) values (lazy);
+// k0/k1 point at the two key octs (4 Shoup pairs each) covering these coefficients, `ks` apart.
+__device__ __forceinline__ void asym_store8(const uint32_t (&xu)[8], const uint32_t (&xe)[8], const uint32_t (&xp)[8],
+                                            const seb_oct *__restrict__ k0, const seb_oct *__restrict__ k1,
+                                            const int ks, uint32_t *__restrict__ c0, uint32_t *__restrict__ c1,
+                                            uint32_t pos, uint32_t q, uint32_t two_q)
 {
-    const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(k0 + pos));
-    const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(k0 + pos + 2));
-    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(k1 + pos));
-    const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(k1 + pos + 2));
-    uint4 v0, v1;
-    v0.x = mul_add_final(xu[0], make_uint2(a0.x, a0.y), xp[0], q, two_q);
-    v0.y = mul_add_final(xu[1], make_uint2(a0.z, a0.w), xp[1], q, two_q);
-    v0.z = mul_add_final(xu[2], make_uint2(a1.x, a1.y), xp[2], q, two_q);
-    v0.w = mul_add_final(xu[3], make_uint2(a1.z, a1.w), xp[3], q, two_q);
-    v1.x = mul_add_final(xu[0], make_uint2(b0.x, b0.y), xe[0], q, two_q);
-    v1.y = mul_add_final(xu[1], make_uint2(b0.z, b0.w), xe[1], q, two_q);
-    v1.z = mul_add_final(xu[2], make_uint2(b1.x, b1.y), xe[2], q, two_q);
-    v1.w = mul_add_final(xu[3], make_uint2(b1.z, b1.w), xe[3], q, two_q);
-    seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), v0);
-    seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), v1);
+    seb_oct v0, v1;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        const seb_oct a = seb_ldg256(k0 + (size_t)h * ks);
+        const seb_oct b = seb_ldg256(k1 + (size_t)h * ks);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+        {
+            v0.v[4 * h + c] = mul_add_final(xu[4 * h + c], make_uint2(a.v[2 * c], a.v[2 * c + 1]), xp[4 * h + c], q, two_q);
+            v1.v[4 * h + c] = mul_add_final(xu[4 * h + c], make_uint2(b.v[2 * c], b.v[2 * c + 1]), xe[4 * h + c], q, two_q);
+        }
+    }
+    seb_stg256_stream(reinterpret_cast<seb_oct *>(c0 + pos), v0);
+    seb_stg256_stream(reinterpret_cast<seb_oct *>(c1 + pos), v1);
 }
 
 // Three polynomials at once (registers permitting): every twiddle fetched once for all three.
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
     k_encrypt_asym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
-                   const uint2 *__restrict__ roots, const uint2 *__restrict__ pk0s,
-                   const uint2 *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
+                   const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
+                   const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
                    uint32_t *__restrict__ out)
 {
     constexpr int N = 1 << LOGN;
@@ -152,23 +151,29 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
 
     LoadAsym ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
     uint32_t x[3][SEB_E];
-    seb_ntt_forward<LOGN, 3>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+    seb_ntt_forward<LOGN, 3>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
 
-    using O         = NttOut<LOGN>;
-    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1    = c0 + N;
-    const uint2 *k0 = pk0s + (size_t)p * N;
-    const uint2 *k1 = pk1s + (size_t)p * N;
+    using O           = NttOut<LOGN>;
+    uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1      = c0 + N;
+    const seb_oct *k0 = pk0s + (size_t)p * (N / 4);
+    const seb_oct *k1 = pk1s + (size_t)p * (N / 4);
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
 #pragma unroll
-        for (int k = 0; k < O::RUN / 4; k++)
+        for (int k = 0; k < O::RUN / 8; k++)
         {
-            const int r = i * O::RUN + 4 * k;
-            const uint32_t xu[4] = {x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]};
-            const uint32_t xe[4] = {x[1][r], x[1][r + 1], x[1][r + 2], x[1][r + 3]};
-            const uint32_t xp[4] = {x[2][r], x[2][r + 1], x[2][r + 2], x[2][r + 3]};
-            asym_store4(xu, xe, xp, k0, k1, c0, c1, O::pos(t, i) + 4 * k, m.q, m.two_q);
+            const int r = i * O::RUN + 8 * k;
+            uint32_t xu[8], xe[8], xp[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+            {
+                xu[c] = x[0][r + c];
+                xe[c] = x[1][r + c];
+                xp[c] = x[2][r + c];
+            }
+            const uint32_t ei = seb_epi_index<LOGN>(t, i, 2 * k);
+            asym_store8(xu, xe, xp, k0 + ei, k1 + ei, O::T, c0, c1, O::pos(t, i) + 8 * k, m.q, m.two_q);
         }
 }
 
@@ -185,8 +190,8 @@ struct LoadOne
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
     k_encrypt_asym_seq(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
-                       const uint2 *__restrict__ roots, const uint2 *__restrict__ pk0s,
-                       const uint2 *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
+                       const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
+                       const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
                        uint32_t *__restrict__ out)
 {
     constexpr int N          = 1 << LOGN;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
     const size_t b     = blockIdx.x / (unsigned)np;
     const int p        = (int)(blockIdx.x % (unsigned)np);
     const SebModulus m = mods.m[p];
-    const uint2 *tw    = roots + (size_t)p * N;
+    const seb_oct *tw  = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
     using O            = NttOut<LOGN>;
 
     uint32_t x[1][SEB_E];
@@ -220,23 +225,30 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
     ld.which = 0;
     seb_ntt_forward<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
 
-    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1    = c0 + N;
-    const uint2 *k0 = pk0s + (size_t)p * N;
-    const uint2 *k1 = pk1s + (size_t)p * N;
+    uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1      = c0 + N;
+    const seb_oct *k0 = pk0s + (size_t)p * (N / 4);
+    const seb_oct *k1 = pk1s + (size_t)p * (N / 4);
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
 #pragma unroll
-        for (int k = 0; k < O::RUN / 4; k++)
+        for (int k = 0; k < O::RUN / 8; k++)
         {
-            const int r       = i * O::RUN + 4 * k;
-            const uint32_t sp = seb_pad<LOGN>(O::pos(t, i)) + 4 * k;
-            const uint4 ve    = *reinterpret_cast<const uint4 *>(smem + WORDS + sp);
-            const uint4 vp    = *reinterpret_cast<const uint4 *>(smem + 2 * WORDS + sp);
-            const uint32_t xu[4] = {x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]};
-            const uint32_t xe[4] = {ve.x, ve.y, ve.z, ve.w};
-            const uint32_t xp[4] = {vp.x, vp.y, vp.z, vp.w};
-            asym_store4(xu, xe, xp, k0, k1, c0, c1, O::pos(t, i) + 4 * k, m.q, m.two_q);
+            const int r       = i * O::RUN + 8 * k;
+            const uint32_t sp = seb_pad<LOGN>(O::pos(t, i)) + 8 * k;
+            uint32_t xu[8], xe[8], xp[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                const uint4 ve = *reinterpret_cast<const uint4 *>(smem + WORDS + sp + 4 * h);
+                const uint4 vp = *reinterpret_cast<const uint4 *>(smem + 2 * WORDS + sp + 4 * h);
+                xe[4 * h + 0] = ve.x, xe[4 * h + 1] = ve.y, xe[4 * h + 2] = ve.z, xe[4 * h + 3] = ve.w;
+                xp[4 * h + 0] = vp.x, xp[4 * h + 1] = vp.y, xp[4 * h + 2] = vp.z, xp[4 * h + 3] = vp.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) xu[c] = x[0][r + c];
+            const uint32_t ei = seb_epi_index<LOGN>(t, i, 2 * k);
+            asym_store8(xu, xe, xp, k0 + ei, k1 + ei, O::T, c0, c1, O::pos(t, i) + 8 * k, m.q, m.two_q);
         }
 }
 
@@ -253,8 +265,8 @@ struct LoadSym
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
-    k_encrypt_sym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint2 *__restrict__ roots,
-                  const uint2 *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
+    k_encrypt_sym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const seb_oct *__restrict__ roots,
+                  const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
                   uint32_t *__restrict__ out, int quirk)
 {
     constexpr int N = 1 << LOGN;
@@ -266,40 +278,40 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
 
     LoadSym ld{e + b * N, pt + b * N, m};
     uint32_t x[1][SEB_E];
-    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * N, m.q, m.two_q, ld);
+    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
 
-    using O         = NttOut<LOGN>;
-    uint32_t *c0    = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1    = c0 + N;
-    const uint2 *sk = ntt_s + (size_t)p * N;
+    using O           = NttOut<LOGN>;
+    uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
+    uint32_t *c1      = c0 + N;
+    const seb_oct *sk = ntt_s + (size_t)p * (N / 4);
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
-    {
-        const uint32_t pos0 = O::pos(t, i);
 #pragma unroll
-        for (int k = 0; k < O::RUN / 4; k++)
+        for (int k = 0; k < O::RUN / 8; k++)
         {
-            const uint32_t pos = pos0 + 4 * k;
-            const uint4 a      = *reinterpret_cast<const uint4 *>(c1 + pos);
-            const uint4 s0     = __ldg(reinterpret_cast<const uint4 *>(sk + pos));
-            const uint4 s1     = __ldg(reinterpret_cast<const uint4 *>(sk + pos + 2));
-            const int r        = i * O::RUN + 4 * k;
-            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
-            const uint2 sv[4]    = {make_uint2(s0.x, s0.y), make_uint2(s0.z, s0.w), make_uint2(s1.x, s1.y),
-                                    make_uint2(s1.z, s1.w)};
-            uint32_t cv[4], mv[4];
+            const uint32_t pos = O::pos(t, i) + 8 * k;
+            const int r        = i * O::RUN + 8 * k;
+            const uint4 a0     = *reinterpret_cast<const uint4 *>(c1 + pos);
+            const uint4 a1     = *reinterpret_cast<const uint4 *>(c1 + pos + 4);
+            const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            seb_oct cv, mv;
 #pragma unroll
-            for (int c = 0; c < 4; c++)
+            for (int h = 0; h < 2; h++)
             {
-                const uint32_t prod = seb_csub(seb_mul_shoup_lazy(av[c], sv[c].x, sv[c].y, m.q), m.q);
-                const uint32_t neg  = prod ? m.q - prod : 0u;  // poly_neg_mod (polymodarith.h:67-70)
-                mv[c]               = seb_final_reduce(x[0][r + c], m.q, m.two_q);
-                cv[c]               = seb_csub(neg + mv[c], m.q);
+                const seb_oct s = seb_ldg256(sk + seb_epi_index<LOGN>(t, i, 2 * k + h));
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                {
+                    const uint32_t prod =
+                        seb_csub(seb_mul_shoup_lazy(av[4 * h + c], s.v[2 * c], s.v[2 * c + 1], m.q), m.q);
+                    const uint32_t neg = prod ? m.q - prod : 0u;  // poly_neg_mod (polymodarith.h:67-70)
+                    mv.v[4 * h + c]    = seb_final_reduce(x[0][r + 4 * h + c], m.q, m.two_q);
+                    cv.v[4 * h + c]    = seb_csub(neg + mv.v[4 * h + c], m.q);
+                }
             }
-            seb_stg_stream(reinterpret_cast<uint4 *>(c0 + pos), make_uint4(cv[0], cv[1], cv[2], cv[3]));
-            if (quirk) seb_stg_stream(reinterpret_cast<uint4 *>(c1 + pos), make_uint4(mv[0], mv[1], mv[2], mv[3]));
+            seb_stg256_stream(reinterpret_cast<seb_oct *>(c0 + pos), cv);
+            if (quirk) seb_stg256_stream(reinterpret_cast<seb_oct *>(c1 + pos), mv);
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,6 +327,43 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
         case 14: CALL(14); break;          \
         default: return cudaErrorInvalidValue; \
     }
+
+size_t seb_table_octs(int logn)
+{
+    switch (logn)
+    {
+        case 10: return NttTwSize<10>::OCTS;
+        case 11: return NttTwSize<11>::OCTS;
+        case 12: return NttTwSize<12>::OCTS;
+        case 13: return NttTwSize<13>::OCTS;
+        case 14: return NttTwSize<14>::OCTS;
+    }
+    return 0;
+}
+
+void seb_host_build_tw(int logn, const uint2 *roots_bitrev, seb_oct *out)
+{
+    switch (logn)
+    {
+        case 10: seb_build_tw<10>(roots_bitrev, out); break;
+        case 11: seb_build_tw<11>(roots_bitrev, out); break;
+        case 12: seb_build_tw<12>(roots_bitrev, out); break;
+        case 13: seb_build_tw<13>(roots_bitrev, out); break;
+        case 14: seb_build_tw<14>(roots_bitrev, out); break;
+    }
+}
+
+void seb_host_build_epi(int logn, const uint2 *natural, seb_oct *out)
+{
+    switch (logn)
+    {
+        case 10: seb_build_epi<10>(natural, out); break;
+        case 11: seb_build_epi<11>(natural, out); break;
+        case 12: seb_build_epi<12>(natural, out); break;
+        case 13: seb_build_epi<13>(natural, out); break;
+        case 14: seb_build_epi<14>(natural, out); break;
+    }
+}
 
 cudaError_t seb_encrypt_configure(int logn)
 {
@@ -334,7 +383,7 @@ cudaError_t seb_encrypt_configure(int logn)
     return err;
 }
 
-cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const SebModuli &mods, int np,
+cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, const SebModuli &mods, int np,
                            size_t npolys_total, cudaStream_t st)
 {
     if (npolys_total == 0) return cudaSuccess;
@@ -345,7 +394,7 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const 
 }
 
 cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
-                                    const uint2 *roots, const uint2 *pk0s, const uint2 *pk1s,
+                                    const seb_oct *roots, const seb_oct *pk0s, const seb_oct *pk1s,
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
@@ -361,8 +410,8 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e
     return cudaGetLastError();
 }
 
-cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const uint2 *roots,
-                                   const uint2 *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const seb_oct *roots,
+                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
                                    int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;

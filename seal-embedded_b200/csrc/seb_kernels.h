@@ -32,16 +32,20 @@ cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, in
 cudaError_t seb_encode_configure(int logn);
 
 // ---- NTT + encrypt (seb_encrypt.cu) ----
-// roots: [np][n] {w, floor(w*2^32/q)} with w = psi^bitrev-order table (ntt.c:40-52)
-cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const uint2 *roots, const SebModuli &mods, int np,
+// roots: per prime, the per-pass twiddle tables of seb_build_tw (seb_table_octs(logn) octs each);
+// pk0s/pk1s/ntt_s: per prime, n/4 octs in the epilogue order of seb_build_epi
+size_t seb_table_octs(int logn);
+void seb_host_build_tw(int logn, const uint2 *roots_bitrev, seb_oct *out);
+void seb_host_build_epi(int logn, const uint2 *natural, seb_oct *out);
+cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, const SebModuli &mods, int np,
                            size_t npolys_total, cudaStream_t st);
 // asym: out[b][p][0] = pk0 (.) ntt(u) + ntt(m+e0), out[b][p][1] = pk1 (.) ntt(u) + ntt(e1)
 cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
-                                    const uint2 *roots, const uint2 *pk0s, const uint2 *pk1s,
+                                    const seb_oct *roots, const seb_oct *pk0s, const seb_oct *pk1s,
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st);
 // sym: out[b][p][1] already holds a; out[b][p][0] = -(a (.) ntt(s)) + ntt(m+e);
 // quirk != 0 additionally overwrites out[b][p][1] with ntt(m+e) (reference byte stream)
-cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const uint2 *roots,
-                                   const uint2 *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const seb_oct *roots,
+                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
                                    int batch, cudaStream_t st);
 cudaError_t seb_encrypt_configure(int logn);

@@ -23,6 +23,9 @@
 //     contiguous coefficients with 128-bit loads.
 //   * NPOLY polynomials that share the modulus go through the passes together so each twiddle
 //     is fetched once for all of them.
+//   * twiddles are stored per pass in the order the threads consume them (seb_build_tw): the
+//     2^R - 1 roots a group needs sit in heap order in 2^R slots, split in 32-byte "octs" and
+//     interleaved across groups, so a warp's 256-bit loads are fully coalesced.
 #pragma once
 
 #include "seb_common.cuh"
@@ -98,43 +101,87 @@ __device__ __forceinline__ void seb_bfly(uint32_t &x, uint32_t &y, const uint2 w
     y                = u - t + two_q;
 }
 
-// R fused stages on NPOLY register groups of 2^R coefficients; tw points at the prime's table
-// roots[bitrev(i)] = psi^i (ntt.c:40-52) in Shoup form; twbase = (1 << s0) + blk for stage 0 of
-// the pass, each later stage doubles it.
+// Per-pass twiddle layout.  Pass P (stage offset S0, radix R) has NB = 2^S0 distinct groups
+// ("blk"); group blk needs, for stage r of the pass, the 2^r roots  roots[((2^S0 + blk) << r) + m].
+// They are stored in heap order: slot 2^r + m (slot 0 unused), 4 slots (32 bytes) per oct, and the
+// table of the pass is [oct][blk].  OFF = offset of the pass' table in octs.
+template <int LOGN, int P>
+struct NttTw
+{
+    static constexpr int R    = NttPlan<LOGN>::R[P];
+    static constexpr int S0   = NttS0<LOGN, P>::value;
+    static constexpr int OCTS = (1 << R) / 4;  // octs per group
+    static constexpr int NB   = 1 << S0;
+    static constexpr int OFF  = NttTw<LOGN, P - 1>::OFF + NttTw<LOGN, P - 1>::OCTS * NttTw<LOGN, P - 1>::NB;
+};
+template <int LOGN>
+struct NttTw<LOGN, 0>
+{
+    static constexpr int R    = NttPlan<LOGN>::R[0];
+    static constexpr int S0   = 0;
+    static constexpr int OCTS = (1 << R) / 4;
+    static constexpr int NB   = 1;
+    static constexpr int OFF  = 0;
+};
+// octs per prime (<= n/4: the table is the same size as the plain root table)
+template <int LOGN>
+struct NttTwSize
+{
+    static constexpr int LASTP = NttPlan<LOGN>::NPASS - 1;
+    static constexpr int OCTS  = NttTw<LOGN, LASTP>::OFF + NttTw<LOGN, LASTP>::OCTS * NttTw<LOGN, LASTP>::NB;
+};
+
+template <int LOGN, int P>
+inline void seb_build_tw_pass(const uint2 *roots, seb_oct *out)
+{
+    using TW = NttTw<LOGN, P>;
+    for (int blk = 0; blk < TW::NB; blk++)
+        for (int slot = 1; slot < (1 << TW::R); slot++)
+        {
+            int r = 0;
+            while ((2 << r) <= slot) r++;
+            const int m      = slot - (1 << r);
+            const uint2 w    = roots[(((size_t)TW::NB + blk) << r) + m];
+            seb_oct &o       = out[TW::OFF + (slot / 4) * TW::NB + blk];
+            o.v[2 * (slot % 4)]     = w.x;
+            o.v[2 * (slot % 4) + 1] = w.y;
+        }
+    if constexpr (P + 1 < NttPlan<LOGN>::NPASS) seb_build_tw_pass<LOGN, P + 1>(roots, out);
+}
+// roots: the reference's table roots[bitrev(i)] = psi^i (ntt.c:40-52) as Shoup pairs {w, floor(w*2^32/q)};
+// out: NttTwSize<LOGN>::OCTS octs, zero-initialised by the caller
+template <int LOGN>
+inline void seb_build_tw(const uint2 *roots, seb_oct *out)
+{
+    seb_build_tw_pass<LOGN, 0>(roots, out);
+}
+
+// R fused stages on NPOLY register groups of 2^R coefficients; tp points at oct 0 of this group's
+// twiddles, consecutive octs are NB apart.
 template <int R, int NPOLY>
 __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], const int gofs,
-                                               const uint2 *__restrict__ tw, uint32_t twbase, const uint32_t q,
+                                               const seb_oct *__restrict__ tp, const int nb, const uint32_t q,
                                                const uint32_t two_q)
 {
+    seb_oct w[(1 << R) / 4];
+#pragma unroll
+    for (int k = 0; k < (1 << R) / 4; k++) w[k] = seb_ldg256(tp + (size_t)k * nb);
 #pragma unroll
     for (int r = 0; r < R; r++)
     {
         const int half = 1 << (R - 1 - r);
-        // the 2^r twiddles of this stage are contiguous and 2^r-aligned: fetch them two at a time
-        uint2 w[1 << (R - 1)];
-        if (r == 0)
-            w[0] = __ldg(tw + twbase);
-        else
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(tw + (twbase << r));
-#pragma unroll
-            for (int m = 0; m < (1 << r) / 2; m++)
-            {
-                const uint4 v = __ldg(src + m);
-                w[2 * m]      = make_uint2(v.x, v.y);
-                w[2 * m + 1]  = make_uint2(v.z, v.w);
-            }
-        }
 #pragma unroll
         for (int m = 0; m < (1 << r); m++)
         {
+            const int slot = (1 << r) + m;
+            const uint2 tw = make_uint2(w[slot / 4].v[2 * (slot % 4)], w[slot / 4].v[2 * (slot % 4) + 1]);
 #pragma unroll
             for (int t = 0; t < half; t++)
             {
                 const int ia = gofs + m * 2 * half + t;
                 const int ib = ia + half;
 #pragma unroll
-                for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], w[m], q, two_q);
+                for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], tw, q, two_q);
             }
         }
     }
@@ -145,7 +192,7 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
 // caller finishes; otherwise they are written back to smem (same slots this thread read).
 template <int LOGN, int P, int NPOLY, class Loader>
 __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
-                                             const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                             const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                              Loader &load)
 {
     constexpr int N     = 1 << LOGN;
@@ -195,7 +242,7 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
                 for (int p = 0; p < NPOLY; p++)
                     x[p][i * (1 << R) + j] = sp[p * WORDS + seb_pad<LOGN>((uint32_t)j << LS)];
         }
-        seb_radix_regs<R, NPOLY>(x, i * (1 << R), tw, (1u << S0) + blk, q, two_q);
+        seb_radix_regs<R, NPOLY>(x, i * (1 << R), tw + NttTw<LOGN, P>::OFF + blk, NttTw<LOGN, P>::NB, q, two_q);
         if (!LAST)
         {
 #pragma unroll
@@ -211,7 +258,7 @@ template <int LOGN, int P, int NPOLY, class Loader>
 struct SebNttRun
 {
     __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
-                                               const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                               const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                                Loader &load)
     {
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
@@ -231,7 +278,7 @@ struct SebNttRun
 // The caller must __syncthreads() before smem is reused.
 template <int LOGN, int NPOLY, class Loader>
 __device__ __forceinline__ void seb_ntt_forward(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
-                                                const uint2 *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                                const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                                 Loader &load)
 {
     SebNttRun<LOGN, 0, NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
@@ -244,5 +291,32 @@ struct NttOut
     static constexpr int GPL = SEB_E >> RL;   // contiguous runs per thread
     static constexpr int RUN = 1 << RL;       // coefficients per run
     static constexpr int T   = (1 << LOGN) / SEB_E;
-    __device__ __forceinline__ static uint32_t pos(int t, int i) { return ((uint32_t)t + (uint32_t)i * T) << RL; }
+    __host__ __device__ __forceinline__ static constexpr uint32_t pos(int t, int i)
+    {
+        return ((uint32_t)t + (uint32_t)i * T) << RL;
+    }
 };
+
+// Key tables (pk0, pk1, ntt(s)) in the order the last pass hands coefficients to threads:
+// oct (i, k, t) holds the Shoup pairs of the 4 coefficients NttOut::pos(t, i) + 4k .. + 3, and octs
+// are interleaved across threads so a warp's 256-bit loads are contiguous.
+template <int LOGN>
+__host__ __device__ __forceinline__ constexpr uint32_t seb_epi_index(int t, int i, int k)
+{
+    return (uint32_t)((i * (NttOut<LOGN>::RUN / 4) + k) * NttOut<LOGN>::T + t);
+}
+template <int LOGN>
+inline void seb_build_epi(const uint2 *natural, seb_oct *out)
+{
+    using O = NttOut<LOGN>;
+    for (int t = 0; t < O::T; t++)
+        for (int i = 0; i < O::GPL; i++)
+            for (int k = 0; k < O::RUN / 4; k++)
+                for (int c = 0; c < 4; c++)
+                {
+                    const uint2 w = natural[(((uint32_t)t + (uint32_t)i * O::T) << O::RL) + 4 * k + c];
+                    seb_oct &o    = out[seb_epi_index<LOGN>(t, i, k)];
+                    o.v[2 * c]     = w.x;
+                    o.v[2 * c + 1] = w.y;
+                }
+}

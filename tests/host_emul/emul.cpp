@@ -25,7 +25,7 @@ struct HostLoad
 };
 
 template <int LOGN, int NPOLY, int P>
-static void ntt_passes(std::vector<std::array<uint32_t[SEB_E], NPOLY>> &regs, uint32_t *smem, const uint2 *tw,
+static void ntt_passes(std::vector<std::array<uint32_t[SEB_E], NPOLY>> &regs, uint32_t *smem, const seb_oct *tw,
                        uint32_t q, HostLoad &ld)
 {
     constexpr int T = (1 << LOGN) / SEB_E;
@@ -46,13 +46,27 @@ static void ntt_emul(const uint32_t *in, const uint2 *tw, uint32_t q, uint32_t *
     std::vector<uint32_t> smem_store((size_t)NPOLY * NttSmem<LOGN>::WORDS + 4, 0xDEADBEEFu);
     uint32_t *smem_al = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(smem_store.data()) + 15) & ~uintptr_t(15));
     HostLoad ld{in, N};
-    ntt_passes<LOGN, NPOLY, 0>(regs, smem_al, tw, q, ld);
+    std::vector<seb_oct> tabs(NttTwSize<LOGN>::OCTS + 1);
+    memset(tabs.data(), 0, tabs.size() * sizeof(seb_oct));
+    seb_build_tw<LOGN>(tw, tabs.data());
+    ntt_passes<LOGN, NPOLY, 0>(regs, smem_al, tabs.data(), q, ld);
+    // outputs are handed over through an epilogue-ordered identity table, the way the kernels
+    // read their key tables: out[pos] must come back as pos
     using O = NttOut<LOGN>;
+    std::vector<uint2> ident(N);
+    for (int i = 0; i < N; i++) ident[i] = make_uint2((uint32_t)i, ~(uint32_t)i);
+    std::vector<seb_oct> epi(N / 4);
+    seb_build_epi<LOGN>(ident.data(), epi.data());
     for (int t = 0; t < T; t++)
         for (int i = 0; i < O::GPL; i++)
             for (int j = 0; j < O::RUN; j++)
+            {
+                const seb_oct &o   = epi[seb_epi_index<LOGN>(t, i, j / 4)];
+                const uint32_t pos = o.v[2 * (j % 4)];
+                if (pos != O::pos(t, i) + j || o.v[2 * (j % 4) + 1] != ~pos) throw 1;
                 for (int p = 0; p < NPOLY; p++)
-                    out[(size_t)p * N + O::pos(t, i) + j] = seb_final_reduce(regs[t][p][i * O::RUN + j], q, 2 * q);
+                    out[(size_t)p * N + pos] = seb_final_reduce(regs[t][p][i * O::RUN + j], q, 2 * q);
+            }
 }
 
 extern "C" int emul_ntt(int logn, int npoly, const uint32_t *in, const uint32_t *roots_w, const uint32_t *roots_wq,
