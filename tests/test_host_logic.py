@@ -1,0 +1,239 @@
+"""CPU tests of the kernels' per-thread logic through tests/host_emul (the .cuh device functions
+compiled with g++ and run one "thread" after another): index math, shared-memory layout, twiddle and
+key-table orderings, Keccak and the samplers' bit tricks — all against the oracle or hashlib.
+No product result is computed on the CPU here; the product path stays CUDA-only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+LOGNS = [10, 11, 12, 13, 14]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+@pytest.fixture(scope="module")
+def E(emul):
+    emul.emul_ntt.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                              C.c_uint32, C.POINTER(C.c_uint32)]
+    emul.emul_pad.argtypes = [C.c_int, C.c_uint32]
+    emul.emul_pad.restype = C.c_uint32
+    emul.emul_smem_words.argtypes = [C.c_int]
+    emul.emul_smem_words.restype = C.c_uint32
+    emul.emul_plan.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    emul.emul_barrett64.argtypes = [C.c_uint64, C.c_uint32]
+    emul.emul_barrett64.restype = C.c_uint32
+    emul.emul_barrett32.argtypes = [C.c_uint32, C.c_uint32]
+    emul.emul_barrett32.restype = C.c_uint32
+    emul.emul_shoup_lazy.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    emul.emul_shoup_lazy.restype = C.c_uint32
+    emul.emul_encode.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_double),
+                                 C.c_double, C.POINTER(C.c_int64)]
+    emul.emul_keccak.argtypes = [C.POINTER(C.c_uint64)]
+    emul.emul_prng_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64)]
+    emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint32)]
+    emul.emul_cbd_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
+    emul.emul_mod3_bytes.argtypes = [C.c_uint32]
+    emul.emul_mod3_bytes.restype = C.c_uint32
+    return emul
+
+
+def _plan(E, logn):
+    r = (C.c_int * 4)()
+    k = E.emul_plan(logn, r)
+    return [r[i] for i in range(k)]
+
+
+# ------------------------------------------------------------------------------------------------
+# modular arithmetic helpers
+# ------------------------------------------------------------------------------------------------
+def test_barrett_and_shoup(E):
+    rng = np.random.default_rng(1)
+    for q in (134012929, 1053818881, 1062535169):
+        xs = [0, 1, q - 1, q, q + 1, 2 * q, 0xFFFFFFFF, (1 << 63) - 1, (1 << 64) - 1] + \
+             [int(x) for x in rng.integers(0, 1 << 63, 200, dtype=np.uint64)]
+        for x in xs:
+            assert E.emul_barrett64(x, q) == x % q
+            assert E.emul_barrett32(x & 0xFFFFFFFF, q) == (x & 0xFFFFFFFF) % q
+        for x, w in rng.integers(0, 1 << 32, (300, 2), dtype=np.uint64):
+            x, w = int(x), int(w) % q
+            r = E.emul_shoup_lazy(x, w, q)  # uintmodarith.h:308-331: [0, 2q), congruent to x*w
+            assert r < 2 * q and r % q == (x * w) % q
+
+
+# ------------------------------------------------------------------------------------------------
+# NTT: plan, layout, transform
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logn", LOGNS)
+def test_ntt_plan(logn, E):
+    plan = _plan(E, logn)
+    assert sum(plan) == logn and all(r in (3, 4) for r in plan)
+    assert plan[0] == 4  # the first pass reads 16 strided coefficients per thread
+
+
+@pytest.mark.parametrize("logn", LOGNS)
+def test_smem_layout_conflict_free(logn, E):
+    """seb_pad: (1) injective and inside NttSmem::WORDS; (2) additive over bit-disjoint fields, which is
+    what turns every per-element address into base + immediate; (3) for every pass, the 32 lanes of
+    every warp hit 32 distinct banks on each scalar access, and the last pass' 128-bit reads are
+    conflict free per quarter-warp phase."""
+    n = 1 << logn
+    T = n // 16
+    pad = np.array([E.emul_pad(logn, a) for a in range(n)], dtype=np.int64)
+    words = E.emul_smem_words(logn)
+    assert len(set(pad.tolist())) == n and pad.max() < words and words % 4 == 0
+    rng = np.random.default_rng(logn)
+    for _ in range(2000):
+        x = int(rng.integers(0, n))
+        y = int(rng.integers(0, n)) & ~x
+        assert E.emul_pad(logn, x | y) == E.emul_pad(logn, x) + E.emul_pad(logn, y)
+    plan = _plan(E, logn)
+    s0 = 0
+    for pi, R in enumerate(plan):
+        LS = logn - s0 - R
+        GP = 16 >> R
+        last = pi == len(plan) - 1
+        if pi > 0 or not last:
+            for i in range(GP):
+                for w0 in range(0, T, 32):
+                    g = np.arange(w0, w0 + 32) + i * T
+                    off, blk = g & ((1 << LS) - 1), g >> LS
+                    base = (blk << (LS + R)) | off
+                    if last and pi > 0:
+                        # 128-bit reads: 8 lanes per phase, each 4 consecutive words
+                        for k in range((1 << R) // 4):
+                            addr = pad[base] + 4 * k
+                            assert (addr % 4 == 0).all()
+                            for ph in range(4):
+                                banks = (addr[8 * ph: 8 * ph + 8] // 4) % 8
+                                assert len(set(banks.tolist())) == 8, (logn, pi, i, w0, k)
+                    else:
+                        for j in range(1 << R):
+                            banks = pad[base | (j << LS)] % 32
+                            assert len(set(banks.tolist())) == 32, (logn, pi, i, j, w0)
+        s0 += R
+
+
+@pytest.mark.parametrize("logn", LOGNS)
+@pytest.mark.parametrize("npoly", [1, 3])
+def test_ntt_emulation_matches_oracle(logn, npoly, E, orc):
+    """The register-blocked multi-pass transform (seb_ntt_pass + per-pass twiddle tables + the
+    epilogue-order key-table indexing) equals ntt_inpl (ntt.c:124-189) bit for bit."""
+    n = 1 << logn
+    nprimes = {10: 1, 11: 1, 12: 3, 13: 6, 14: 13}[logn]
+    rng = np.random.default_rng(100 + logn)
+    for q in (orc.primes(n, nprimes)[0], orc.primes(n, nprimes)[-1]):
+        roots = orc.ntt_roots(n, q)
+        wq = ((roots.astype(np.uint64) << np.uint64(32)) // np.uint64(q)).astype(np.uint32)
+        x = rng.integers(0, q, (npoly, n), dtype=np.uint32)
+        x[0, :4] = (0, 1, q - 1, q - 2)
+        out = np.zeros_like(x)
+        rc = E.emul_ntt(logn, npoly, _p(x, C.c_uint32), _p(roots, C.c_uint32), _p(wq, C.c_uint32), q,
+                        _p(out, C.c_uint32))
+        assert rc == 0
+        for p in range(npoly):
+            assert np.array_equal(out[p], orc.ntt(n, q, x[p])), (logn, q, p)
+
+
+def test_ntt_emulation_lazy_inputs(E, orc):
+    """The fused encrypt feeds on-load values anywhere below 4q (e.g. q - 1 + small): inputs in [0,4q)
+    must still give the canonical transform of their residues."""
+    logn, n, q = 12, 4096, 1053818881
+    rng = np.random.default_rng(9)
+    x = rng.integers(0, 4 * q, (1, n), dtype=np.uint64).astype(np.uint32)
+    roots = orc.ntt_roots(n, q)
+    wq = ((roots.astype(np.uint64) << np.uint64(32)) // np.uint64(q)).astype(np.uint32)
+    out = np.zeros_like(x)
+    assert E.emul_ntt(logn, 1, _p(x, C.c_uint32), _p(roots, C.c_uint32), _p(wq, C.c_uint32), q, _p(out, C.c_uint32)) == 0
+    assert np.array_equal(out[0], orc.ntt(n, q, (x[0] % np.uint32(q))))
+
+
+# ------------------------------------------------------------------------------------------------
+# encode
+# ------------------------------------------------------------------------------------------------
+def _src_map(orc, n):
+    im = orc.index_map(n)
+    src = np.zeros(n, np.uint16)
+    src[im[: n // 2]] = np.arange(n // 2, dtype=np.uint16)
+    src[im[n // 2:]] = np.arange(n // 2, dtype=np.uint16)
+    return src
+
+
+@pytest.mark.parametrize("logn", LOGNS)
+def test_encode_emulation_matches_oracle(logn, E, orc, oracle_mod):
+    """Radix-8 passes of fused radix-2 stages, swizzled shared memory, the 2-CTA split for
+    n = 16384: same int64 coefficients as ckks_encode_base (ckks_common.c:105-215), bit for bit."""
+    n = 1 << logn
+    tw = orc.ifft_twiddles(n)
+    src = _src_map(orc, n)
+    n_inv = orc.scale(n) / n
+    for vlen, seed in ((n // 2, 1), (n // 2, 2), (5, 3), (0, 4)):
+        v = oracle_mod.make_values(1, n // 2, seed=seed * 100 + logn)[0]
+        out = np.zeros(n, np.int64)
+        bad = E.emul_encode(logn, _p(v, C.c_float), vlen, _p(src, C.c_uint16), _p(tw, C.c_double), n_inv,
+                            _p(out, C.c_int64))
+        ok, exp = orc.encode(n, v[:vlen])
+        assert bad == 0 and ok and np.array_equal(out, exp), (logn, vlen)
+    # overflow flag (ckks_common.c:195-204)
+    v = np.full(n // 2, 3.0e38, np.float32)
+    out = np.zeros(n, np.int64)
+    assert E.emul_encode(logn, _p(v, C.c_float), n // 2, _p(src, C.c_uint16), _p(tw, C.c_double), n_inv,
+                         _p(out, C.c_int64)) == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Keccak / samplers
+# ------------------------------------------------------------------------------------------------
+def test_keccak_permutation_and_prng_block(E, oracle_mod):
+    st = (C.c_uint64 * 25)()
+    E.emul_keccak(st)  # Keccak-f[1600] of the zero state: first lane is the well-known 0xF1258F7940E1DDE7
+    assert st[0] == 0xF1258F7940E1DDE7 and st[24] == 0xEAF1FF7B5CECA249
+    seeds = oracle_mod.make_seeds(4, b"kk")
+    for i, ctr in enumerate((0, 1, 0xFFFFFFFF, 1 << 50)):
+        out = np.zeros(17, np.uint64)
+        E.emul_prng_block(_p(seeds[i], C.c_uint8), ctr, _p(out, C.c_uint64))
+        assert out.tobytes() == hashlib.shake_256(seeds[i].tobytes() + struct.pack("<Q", ctr)).digest(136)
+
+
+def test_mod3_bytes_exhaustive(E):
+    for b in range(256):
+        x = b | ((255 - b) << 8) | (((b * 7) & 0xFF) << 16) | (((b * 13 + 5) & 0xFF) << 24)
+        r = E.emul_mod3_bytes(x)
+        for k in range(4):
+            assert (r >> (8 * k)) & 0xFF == ((x >> (8 * k)) & 0xFF) % 3
+
+
+def test_ternary_and_cbd_blocks(E, oracle_mod):
+    """One 96-byte PRNG call as a ternary block (packed fields + rejection masks, sample.c:223-241) and as
+    16 CBD samples (sample.c:263-321)."""
+    seeds = oracle_mod.make_seeds(64, b"blk")
+    seen_reject = 0
+    for i in range(64):
+        ctr = i * 3
+        buf = hashlib.shake_256(seeds[i].tobytes() + struct.pack("<Q", ctr)).digest(96)
+        packed = np.zeros(6, np.uint32)
+        mask = np.zeros(3, np.uint32)
+        E.emul_ternary_block(_p(seeds[i], C.c_uint8), ctr, _p(packed, C.c_uint32), _p(mask, C.c_uint32))
+        pb = packed.tobytes()
+        for pos in range(96):
+            rej = buf[pos] >= 0xFE
+            assert ((int(mask[pos // 32]) >> (pos % 32)) & 1) == int(rej)
+            field = (pb[pos // 4] >> (6 - 2 * (pos % 4))) & 3
+            assert field == (0 if rej else buf[pos] % 3)
+            seen_reject += rej
+        o = np.zeros(4, np.uint32)
+        E.emul_cbd_block(_p(seeds[i], C.c_uint8), ctr, _p(o, C.c_uint32))
+        got = np.frombuffer(o.tobytes(), np.int8)
+        hw = lambda v: bin(v).count("1")  # noqa: E731
+        for s in range(16):
+            x = buf[6 * s: 6 * s + 6]
+            assert got[s] == hw(x[0]) + hw(x[1]) + hw(x[2] & 0x1F) - hw(x[3]) - hw(x[4]) - hw(x[5] & 0x1F)
+    assert seen_reject > 0
