@@ -30,6 +30,11 @@ if ROOT not in sys.path:
 
 N_DEG, N_PRIMES, BATCH = 4096, 3, 65536
 WORKLOAD = f"n={N_DEG}, {N_PRIMES}-prime RNS, batch={BATCH}/GPU, asymmetric encrypt (BASELINE.json configs[1])"
+# integer-issue ceilings measured on this pool's B200 with tools/ubench (profiles/r01_ubench_int_pipes.txt,
+# profiles/r01_ubench_bfly.txt): Keccak-f[1600] is ALU-pipe bound (LOP3/SHF at 64 lanes/clk/SM), the lazy
+# butterfly FMA-pipe bound (IMAD.HI + 2 IMAD)
+KECCAK_PEAK_PER_S = 4.26e9
+BUTTERFLY_PEAK_PER_S = 3.77e12
 METRIC = "ckks_encryptions_per_sec"
 UNIT = "ciphertexts/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
@@ -119,7 +124,8 @@ def run_reference_arm(args) -> None:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": N_DEG, "nprimes": N_PRIMES,
-                       "batch_per_step": arm.cores * arm.items, "host_threads": arm.cores},
+                       "batch_per_step": arm.cores * arm.items, "host_threads": arm.cores,
+                       "sample": f"{arm.items} of the workload's items per process per step"},
             "cpu_baseline": arm.describe(value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -138,7 +144,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(gpu_index), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -182,12 +188,14 @@ def hbm_peak() -> tuple[float, str]:
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel: str):
-    """dram read+write bytes per launch from the committed ncu summary, if one exists."""
+def ncu_traffic(kernel: str, batch: int):
+    """dram read+write bytes per launch from the committed `ncu --set full` summary (profiles/traffic.json,
+    written by tools/summarize_profile.py), scaled from the batch it was captured at to this run's."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            t = json.load(open(p)).get(kernel)
+            return float(t["dram_bytes_per_launch"]) * batch / float(t["batch"]) if t else None
         except Exception:
             return None
     return None
@@ -329,16 +337,31 @@ def run_b200_arm(args) -> None:
     kernel_sym = {"encode": "k_encode", "sample_ternary": "k_sample_ternary", "sample_cbd": "k_sample_cbd",
                   "encrypt": "k_encrypt_asym"}[top_name]
     roofline = {"kernel": kernel_sym, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(kernel_sym), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(kernel_sym, batch), "peak_source": peak_src,
                 "avg_launch_ms": float(avg[top]), "share_of_step": float(avg[top] / max(avg.sum(), 1e-9)),
                 "algorithmic_bytes_per_launch": alg_bytes[top_name] * batch,
                 "note": "integer-issue bound kernel (Keccak / modular butterflies), not an HBM-bound one: "
-                        "see ntt_microbench for the HBM-rooflined NTT-only kernel"}
+                        "see issue_bound here and ntt_microbench for the HBM-rooflined NTT-only kernel"}
+    # what actually bounds the Keccak / butterfly kernels: integer issue, against the measured pipe ceilings
+    keccak_per_ct = {"sample_cbd": 2 * (n // 16), "sample_ternary": 96}  # permutations launched per ciphertext
+    if top_name in keccak_per_ct and avg[top] > 0:
+        rate = keccak_per_ct[top_name] * batch / (avg[top] * 1e-3)
+        roofline["issue_bound"] = {"pipe": "alu", "achieved": rate, "peak": KECCAK_PEAK_PER_S, "unit": "Keccak-f/s",
+                                   "frac": rate / KECCAK_PEAK_PER_S,
+                                   "peak_source": "tools/ubench best Keccak-f variant on this pool (profiles/)"}
+    elif top_name == "encrypt" and avg[top] > 0:
+        rate = 3 * np_ * (n // 2) * (n.bit_length() - 1) * batch / (avg[top] * 1e-3)
+        roofline["issue_bound"] = {"pipe": "fma", "achieved": rate, "peak": BUTTERFLY_PEAK_PER_S, "unit": "butterflies/s",
+                                   "frac": rate / BUTTERFLY_PEAK_PER_S,
+                                   "peak_source": "tools/ubench_bfly register-only butterflies (profiles/)"}
     ntt_gbs = 8 * n * np_ * batch / (ntt_ms * 1e-3) / 1e9
     ntt_micro = {"kernel": "k_ntt_forward", "bound": "hbm", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
-                 "frac": ntt_gbs / peak, "traffic": ncu_traffic("k_ntt_forward"), "ms_per_launch": ntt_ms,
+                 "frac": ntt_gbs / peak, "traffic": ncu_traffic("k_ntt_forward", batch), "ms_per_launch": ntt_ms,
                  "polys_per_launch": batch * np_, "algorithmic_bytes_per_launch": 8 * n * np_ * batch,
-                 "ntt_per_sec": batch * np_ / (ntt_ms * 1e-3)}
+                 "ntt_per_sec": batch * np_ / (ntt_ms * 1e-3),
+                 "issue_bound": {"pipe": "fma", "achieved": batch * np_ * (n // 2) * (n.bit_length() - 1) / (ntt_ms * 1e-3),
+                                 "peak": BUTTERFLY_PEAK_PER_S, "unit": "butterflies/s",
+                                 "frac": batch * np_ * (n // 2) * (n.bit_length() - 1) / (ntt_ms * 1e-3) / BUTTERFLY_PEAK_PER_S}}
 
     # ---- CPU baseline: the reference's own path on this host's cores, bounded sample
     cpu = None
@@ -352,7 +375,8 @@ def run_b200_arm(args) -> None:
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n": n, "nprimes": np_, "batch_per_gpu": batch,
+            "config": {"workload": WORKLOAD.replace(f"batch={BATCH}/GPU", f"batch={batch}/GPU"), "n": n, "nprimes": np_,
+                       "batch_per_gpu": batch,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"inputs+outputs per step ({(d_vals.numel() * 4 + d_out.numel() * 4) >> 20} MiB) "
                              "exceed the 126 MB L2"},
@@ -367,7 +391,7 @@ def run_b200_arm(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="ciphertexts per GPU per step")
