@@ -9,8 +9,8 @@
 //   k_encrypt_sym   : one prime of ckks_encode_encrypt_sym (device/lib/ckks_sym.c:199-301) with
 //                     ntt(s) precomputed at setup:  c0 = -(a (.) ntt(s)) + ntt(m+e)
 //
-// One CTA of n/16 threads per polynomial slot; blockIdx.x = ciphertext*np + prime so the CTAs that
-// re-read one ciphertext's m/e/u are scheduled together and hit L2.
+// One CTA of n/16 threads per polynomial slot; grid = (prime, item low, item high) so the CTAs that
+// re-read one ciphertext's m/e/u are scheduled together and hit L2, and no thread divides by np.
 #include "seb_kernels.h"
 #include "seb_ntt.cuh"
 
@@ -31,14 +31,25 @@ __device__ __forceinline__ uint32_t reduce_small(const int8_t *__restrict__ e, u
     const int v = __ldg(e + pos);
     return v < 0 ? q + (uint32_t)v : (uint32_t)v;
 }
-// (m + e) int64 -> |x| mod q, q - r for negatives (device/lib/ckks_common.c:224-245)
+// (m + e) int64 -> |x| mod q, q - r for negatives (device/lib/ckks_common.c:224-245).
+// The result feeds a lazy butterfly, so any representative below 4q is as good as the canonical one.
+// |x| < 2^32 for every message the default scales can encode without overflow in practice
+// (|coefficient| <= max|v| * scale), so that case takes a 32-bit lazy Barrett step (one IMAD.HI);
+// anything larger falls back to the exact 64-bit reduction.  Both are exact residues.
 __device__ __forceinline__ uint32_t reduce_pte(const int64_t *__restrict__ pt, const int8_t *__restrict__ e,
                                                uint32_t pos, const SebModulus &m)
 {
     const uint64_t x  = (uint64_t)__ldg(pt + pos) + (uint64_t)(int64_t)__ldg(e + pos);
     const bool neg    = (int64_t)x < 0;
     const uint64_t ax = neg ? (uint64_t)0 - x : x;
-    const uint32_t r  = seb_barrett64(ax, m);
+    uint32_t r;
+    if ((uint32_t)(ax >> 32) == 0)
+    {
+        const uint32_t lo = (uint32_t)ax;
+        r                 = lo - __umulhi(lo, m.ratio_hi) * m.q;  // [0, 2q): floor(2^32/q) underestimates by < 1
+        return neg ? m.two_q - r : r;                             // (0, 2q]
+    }
+    r = seb_barrett64(ax, m);
     return neg ? m.q - r : r;
 }
 
@@ -51,19 +62,30 @@ struct LoadPlain
     __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return seb_ldg_stream(src + pos); }
 };
 
+// item index of this CTA for a grid built by seb_grid()
+__device__ __forceinline__ size_t seb_item() { return (size_t)blockIdx.z * gridDim.y + blockIdx.y; }
+
+// resident CTAs per SM the NTT-only kernel is compiled for (tools/ubench/ubench_ntt: 5 x 256 threads at
+// 48 registers beats 4 x 64 registers for n = 4096)
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E) k_ntt_forward(uint32_t *__restrict__ polys,
-                                                                     const seb_oct *__restrict__ roots,
-                                                                     const __grid_constant__ SebModuli mods,
-                                                                     int np)
+struct NttOcc
+{
+    static constexpr int MINB = LOGN == 12 ? 5 : 1;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E, NttOcc<LOGN>::MINB)
+    k_ntt_forward(uint32_t *__restrict__ polys, const seb_oct *__restrict__ roots,
+                  const __grid_constant__ SebModuli mods, int np, size_t items)
 {
     constexpr int N = 1 << LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t         = threadIdx.x;
-    const size_t poly   = blockIdx.x;
-    const int p         = (int)(poly % (size_t)np);
+    const size_t b      = seb_item();
+    if (b >= items) return;
+    const int p         = (int)blockIdx.x;
     const SebModulus &m = mods.m[p];
-    uint32_t *data      = polys + poly * N;
+    uint32_t *data      = polys + (b * np + p) * N;
 
     uint32_t x[1][SEB_E];
     LoadPlain ld{data};
@@ -140,13 +162,14 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
     k_encrypt_asym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
                    const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
                    const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
-                   uint32_t *__restrict__ out)
+                   uint32_t *__restrict__ out, size_t batch)
 {
     constexpr int N = 1 << LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t        = threadIdx.x;
-    const size_t b     = blockIdx.x / (unsigned)np;
-    const int p        = (int)(blockIdx.x % (unsigned)np);
+    const size_t b     = seb_item();
+    if (b >= batch) return;
+    const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
 
     LoadAsym ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
@@ -192,14 +215,15 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
     k_encrypt_asym_seq(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
                        const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
                        const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
-                       uint32_t *__restrict__ out)
+                       uint32_t *__restrict__ out, size_t batch)
 {
     constexpr int N          = 1 << LOGN;
     constexpr uint32_t WORDS = NttSmem<LOGN>::WORDS;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t        = threadIdx.x;
-    const size_t b     = blockIdx.x / (unsigned)np;
-    const int p        = (int)(blockIdx.x % (unsigned)np);
+    const size_t b     = seb_item();
+    if (b >= batch) return;
+    const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
     const seb_oct *tw  = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
     using O            = NttOut<LOGN>;
@@ -267,13 +291,14 @@ template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
     k_encrypt_sym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const seb_oct *__restrict__ roots,
                   const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
-                  uint32_t *__restrict__ out, int quirk)
+                  uint32_t *__restrict__ out, int quirk, size_t batch)
 {
     constexpr int N = 1 << LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t        = threadIdx.x;
-    const size_t b     = blockIdx.x / (unsigned)np;
-    const int p        = (int)(blockIdx.x % (unsigned)np);
+    const size_t b     = seb_item();
+    if (b >= batch) return;
+    const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
 
     LoadSym ld{e + b * N, pt + b * N, m};
@@ -317,6 +342,14 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// grid (np, items) folded into three dimensions: x = prime (fastest, so one item's primes are
+// neighbours), y/z = item
+static inline dim3 seb_grid(int np, size_t items)
+{
+    const size_t gy = items < 32768 ? items : 32768;
+    return dim3((unsigned)np, (unsigned)gy, (unsigned)((items + gy - 1) / gy));
+}
+
 #define SEB_DISPATCH_LOGN(logn, CALL)      \
     switch (logn)                          \
     {                                      \
@@ -387,7 +420,8 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, cons
                            size_t npolys_total, cudaStream_t st)
 {
     if (npolys_total == 0) return cudaSuccess;
-#define RUN(L) k_ntt_forward<L><<<(unsigned)npolys_total, (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(polys, roots, mods, np)
+    const size_t items = npolys_total / (size_t)np;
+#define RUN(L) k_ntt_forward<L><<<seb_grid(np, items), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(polys, roots, mods, np, items)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
@@ -400,11 +434,11 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e
     if (batch <= 0) return cudaSuccess;
 #define RUN(L)                                                                                                 \
     if (L >= 13)                                                                                               \
-        k_encrypt_asym_seq<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(  \
-            pt, e, u, roots, pk0s, pk1s, mods, np, out);                                                       \
-    else                                                                                                       \
-        k_encrypt_asym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(      \
-            pt, e, u, roots, pk0s, pk1s, mods, np, out)
+        k_encrypt_asym_seq<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(  \
+            pt, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch);                                     \
+    else                                                                                                    \
+        k_encrypt_asym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(      \
+            pt, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
@@ -416,8 +450,8 @@ cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e,
 {
     if (batch <= 0) return cudaSuccess;
 #define RUN(L)                                                                                              \
-    k_encrypt_sym<L><<<(unsigned)((size_t)batch * np), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, e, roots, ntt_s, mods, \
-                                                                                         np, out, quirk)
+    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, e, roots, ntt_s, mods, \
+                                                                                      np, out, quirk, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();

@@ -91,13 +91,19 @@ struct NttSmem
     static constexpr uint32_t WORDS = (seb_pad<LOGN>((1u << LOGN) - 1u) + 4u) & ~3u;
 };
 
+// An addend that is zero at run time but opaque to the compiler (a constant-bank operand).  The
+// butterfly is bound by the FMA pipe (IMAD.HI + 2 IMAD, profiles/README.md) while the ALU pipe has
+// slack, yet ptxas turns part of the two-input additions into IMAD.IADD; a three-input addition
+// can only be an IADD3, which keeps it on the ALU pipe.
+SEB_CONSTANT uint32_t c_seb_zero = 0;
+
 // Harvey lazy butterfly: X,Y in [0,4q) -> X+WY, X-WY in [0,4q) (ntt.c:94-105)
 __device__ __forceinline__ void seb_bfly(uint32_t &x, uint32_t &y, const uint2 w, const uint32_t q,
                                          const uint32_t two_q)
 {
     const uint32_t u = min(x, x - two_q);
     const uint32_t t = seb_mul_shoup_lazy(y, w.x, w.y, q);
-    x                = u + t;
+    x                = u + t + c_seb_zero;
     y                = u - t + two_q;
 }
 

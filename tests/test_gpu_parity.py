@@ -232,6 +232,46 @@ def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
             assert np.abs(dec - vals[0]).max() < 0.1
 
 
+@pytest.mark.parametrize("n,np_,asym", [(4096, 3, True), (1024, 1, False), (8192, 4, True)])
+def test_encrypt_large_magnitudes(n, np_, asym, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """reduce_set_pte (ckks_common.c:224-245) over the whole int64 range: messages from tiny to ~1e11 give
+    plaintext coefficients from below 2^32 (32-bit reduction path) up to ~2^62 (64-bit path), mixed
+    inside one warp, positive and negative."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, asym)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    batch, vlen = 6, n // 2
+    rng = np.random.default_rng(n)
+    vals = oracle_mod.make_values(batch, vlen, seed=5 * n)
+    vals[1] *= np.float32(1.0e4)
+    vals[2] *= np.float32(1.0e9)
+    vals[3] = (rng.standard_normal(vlen) * 10.0 ** rng.uniform(-3, 10, vlen)).astype(np.float32)
+    vals[4, ::7] *= np.float32(3.0e7)
+    vals[5] = 0
+    vals[5, 3] = np.float32(2.0e10)
+    seeds = oracle_mod.make_seeds(batch, b"big-%d" % n)
+    sseeds = oracle_mod.make_seeds(batch, b"big-share-%d" % n)
+    d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    if asym:
+        ctx.set_public_key(pk0, pk1)
+        ctx.encrypt_asym_device(dev(torch, vals), vlen, dev(torch, seeds), batch, d_out)
+    else:
+        ctx.set_secret_key(sk)
+        ctx.encrypt_sym_device(dev(torch, vals), vlen, dev(torch, sseeds), dev(torch, seeds), batch, d_out, False)
+    assert ctx.encode_failures() == 0
+    got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+    big = 0
+    for b in range(batch):
+        ok_pt, pt = orc.encode(n, vals[b])
+        big += int((np.abs(pt) >= (1 << 32)).sum())
+        if asym:
+            ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        else:
+            ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
+        assert ok and ok_pt and np.array_equal(got[b], exp), (n, b)
+    assert big > 1000  # the 64-bit path really ran
+
+
 def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs):
     """Host-pointer batch API: pageable and pinned buffers, more items than one chunk, ragged vlen."""
     torch = torch_cuda
