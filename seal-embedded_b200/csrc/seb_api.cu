@@ -128,6 +128,7 @@ struct Scratch  // per in-flight chunk
     uint32_t *ctr    = nullptr;
     uint32_t *ctr_a  = nullptr;
     int *fail        = nullptr;
+    uint32_t *mag    = nullptr;  // max |plaintext coefficient| per item, clipped to 32 bits
     // host-API staging
     size_t io_cap    = 0;
     float *d_values  = nullptr;
@@ -188,6 +189,7 @@ static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
     cudaFree(s.ctr);
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
+    cudaFree(s.mag);
     s.cap = 0;
     CU(cudaMalloc(&s.pt, batch * c->n * sizeof(int64_t)));
     CU(cudaMalloc(&s.e, batch * 2 * c->n));
@@ -195,6 +197,7 @@ static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
     CU(cudaMalloc(&s.ctr, batch * sizeof(uint32_t)));
     CU(cudaMalloc(&s.ctr_a, batch * sizeof(uint32_t)));
     CU(cudaMalloc(&s.fail, batch * sizeof(int)));
+    CU(cudaMalloc(&s.mag, batch * sizeof(uint32_t)));
     s.cap = batch;
     return 0;
 }
@@ -207,6 +210,7 @@ static void free_scratch(Scratch &s)
     cudaFree(s.ctr);
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
+    cudaFree(s.mag);
     cudaFree(s.d_values);
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
@@ -451,11 +455,12 @@ static int check_vlen(seb_ctx *c, size_t vlen)
 }
 
 static int run_encode(seb_ctx *c, const float *d_values, size_t vlen, size_t batch, int64_t *d_pt, int *d_fail,
-                      cudaStream_t st)
+                      uint32_t *d_mag, cudaStream_t st)
 {
     CU(cudaMemsetAsync(d_fail, 0, batch * sizeof(int), st));
+    if (d_mag) CU(cudaMemsetAsync(d_mag, 0, batch * sizeof(uint32_t), st));
     CU(seb_launch_encode(c->logn, d_values, vlen, (int)vlen, c->d_src_map, c->d_tw, c->scale / (double)c->n, d_pt,
-                         d_fail, (int)batch, st));
+                         d_fail, d_mag, (int)batch, st));
     c->launches++;
     return 0;
 }
@@ -467,7 +472,7 @@ extern "C" int seb_encode_device(seb_ctx *c, const float *d_values, size_t vlen,
     if (r) return r;
     if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
     c->last_batch = batch;
-    return run_encode(c, d_values, vlen, batch, d_pt, c->slot[0].fail, c->stream);
+    return run_encode(c, d_values, vlen, batch, d_pt, c->slot[0].fail, nullptr, c->stream);
 }
 
 extern "C" int seb_sample_asym_device(seb_ctx *c, const uint8_t *d_seeds, size_t batch, uint8_t *d_u, int8_t *d_e,
@@ -530,7 +535,7 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 {
     const int n = (int)c->n;
     prof_mark(c, st, 0);
-    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
+    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, s.mag, st);
     if (r) return r;
     prof_mark(c, st, 1);
     seb_launch_sample_ternary(d_seeds, s.u, s.ctr, n, (int)batch, st);
@@ -538,7 +543,7 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
     seb_launch_sample_cbd(d_seeds, s.ctr, s.e, n, 2, (int)batch, st);
     CU(cudaGetLastError());
     prof_mark(c, st, 3);
-    CU(seb_launch_encrypt_asym(c->logn, s.pt, s.e, s.u, c->d_roots, c->d_pk0, c->d_pk1, c->mods, (int)c->np, d_out,
+    CU(seb_launch_encrypt_asym(c->logn, s.pt, s.mag, s.e, s.u, c->d_roots, c->d_pk0, c->d_pk1, c->mods, (int)c->np, d_out,
                                (int)batch, st));
     prof_mark(c, st, 4);
     prof_next(c, st);
@@ -553,7 +558,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
 {
     const int n = (int)c->n;
     prof_mark(c, st, 0);
-    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, st);
+    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, s.mag, st);
     if (r) return r;
     prof_mark(c, st, 1);
     seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
@@ -564,7 +569,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
         seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch, st);
     CU(cudaGetLastError());
     prof_mark(c, st, 3);
-    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,
+    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,
                               (int)batch, st));
     prof_mark(c, st, 4);
     prof_next(c, st);

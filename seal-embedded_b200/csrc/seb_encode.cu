@@ -23,7 +23,8 @@ namespace cg = cooperative_groups;
 template <int LOGN, int CL>
 __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
     k_encode(const float *__restrict__ values, size_t v_stride, int vlen, const uint16_t *__restrict__ src_map,
-             const double2 *__restrict__ tw, double n_inv, int64_t *__restrict__ pt, int *__restrict__ fail)
+             const double2 *__restrict__ tw, double n_inv, int64_t *__restrict__ pt, int *__restrict__ fail,
+             uint32_t *__restrict__ mag)
 {
     constexpr int N     = 1 << LOGN;
     constexpr int NL    = N / CL;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
     const float *vals      = values + b * v_stride;
     int64_t *dst           = pt + b * N;
     int bad                = 0;
+    uint32_t mx            = 0;  // max |coefficient| this thread produced, clipped to 32 bits
 
     double xr[ENC_E], xi[ENC_E];
     EncRun<LOGN, LOGNL, 0>::run(xr, xi, sre, sim, t, pos0, vals, vlen, src_map, tw);
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
             const uint32_t base = ((g >> LSL) << (LSL + RL)) | off;
 #pragma unroll
             for (int j = 0; j < (1 << RL); j++)
-                dst[base | ((uint32_t)j << LSL)] = enc_finish(xr[i * (1 << RL) + j], n_inv, bad);
+                dst[base | ((uint32_t)j << LSL)] = enc_finish(xr[i * (1 << RL) + j], n_inv, bad, mx);
         }
     }
     else
@@ -87,11 +89,16 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
         {
             const uint32_t sk = enc_swz(k);
             const double re = enc_cross_re(rank, sre[sk], sim[sk], ore[sk], rank ? oim[sk] : 0.0, s);
-            dst[pos0 + k] = enc_finish(re, n_inv, bad);
+            dst[pos0 + k] = enc_finish(re, n_inv, bad, mx);
         }
         cluster.sync();  // partner may still be reading our shared memory
     }
     if (bad) fail[b] = 1;
+    if (mag)
+    {
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if ((threadIdx.x & 31) == 0) atomicMax(mag + b, mx);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -119,7 +126,7 @@ cudaError_t seb_encode_configure(int logn)
 
 template <int LOGN, int CL>
 static cudaError_t encode_launch(const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
-                                 const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                                 const double2 *tw, double n_inv, int64_t *pt, int *fail, uint32_t *mag, int batch,
                                  cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
@@ -134,21 +141,21 @@ static cudaError_t encode_launch(const float *values, size_t v_stride, int vlen,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs                = attr;
     cfg.numAttrs             = 1;
-    return cudaLaunchKernelEx(&cfg, k_encode<LOGN, CL>, values, v_stride, vlen, src_map, tw, n_inv, pt, fail);
+    return cudaLaunchKernelEx(&cfg, k_encode<LOGN, CL>, values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag);
 }
 
 cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
-                              const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                              const double2 *tw, double n_inv, int64_t *pt, int *fail, uint32_t *mag, int batch,
                               cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
     switch (logn)
     {
-        case 10: return encode_launch<10, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
-        case 11: return encode_launch<11, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
-        case 12: return encode_launch<12, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
-        case 13: return encode_launch<13, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
-        case 14: return encode_launch<14, 2>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, batch, st);
+        case 10: return encode_launch<10, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag, batch, st);
+        case 11: return encode_launch<11, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag, batch, st);
+        case 12: return encode_launch<12, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag, batch, st);
+        case 13: return encode_launch<13, 1>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag, batch, st);
+        case 14: return encode_launch<14, 2>(values, v_stride, vlen, src_map, tw, n_inv, pt, fail, mag, batch, st);
         default: return cudaErrorInvalidValue;
     }
 }

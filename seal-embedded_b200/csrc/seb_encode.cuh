@@ -118,10 +118,15 @@ struct EncRun
 
 // coeff = round(Re * scale/n); |coeff| > 2^63 fails the encode; the int64 conversion follows x86
 // (ckks_common.c:183-206)
-__device__ __forceinline__ int64_t enc_finish(double re, double n_inv, int &bad)
+__device__ __forceinline__ int64_t enc_finish(double re, double n_inv, int &bad, uint32_t &mag)
 {
     const double c = round(__dmul_rn(re, n_inv));
     if (fabs(c) > 9223372036854775808.0) bad = 1;
+    // magnitude class for the encrypt kernels' 32-bit reduction path: |c| clipped to 2^32 - 1
+    // (NaN compares false and clips too)
+    const double a = fabs(c);
+    const uint32_t m32 = a < 4294967295.0 ? (uint32_t)a : 0xFFFFFFFFu;
+    mag                = mag > m32 ? mag : m32;
     if (!(c < 9223372036854775808.0)) return (int64_t)0x8000000000000000ULL;  // NaN / 2^63: "indefinite"
     return (int64_t)c;
 }

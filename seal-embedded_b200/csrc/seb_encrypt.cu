@@ -16,42 +16,44 @@
 
 
 // ---------------------------------------------------------------------------------------------
-// on-load conversions (all produce values the lazy butterflies accept, i.e. < 4q)
+// on-load conversions.  Their results feed lazy butterflies, which accept ANY representative of
+// the residue below 4q, so none of them reduces to the canonical range (the reference's functions
+// are cited for the value being represented, not for the representative).
 // ---------------------------------------------------------------------------------------------
-// 2-bit field -> {q-1, 0, 1} (device/lib/sample.c:98-116)
+// 2-bit field t in {0,1,2} standing for t - 1 (device/lib/sample.c:98-116) -> t + q - 1 in {q-1, q, q+1}
 __device__ __forceinline__ uint32_t expand_ternary(const uint8_t *__restrict__ u, uint32_t pos, uint32_t q)
 {
     const uint32_t byte = __ldg(u + (pos >> 2));
-    const uint32_t t    = (byte >> (6 - 2 * (pos & 3))) & 3u;
-    return t == 0 ? q - 1 : t - 1;
+    return ((byte >> (6 - 2 * (pos & 3))) & 3u) + (q - 1u);
 }
-// small signed -> [0,q) (device/lib/ckks_common.c:259-265)
+// small signed e (device/lib/ckks_common.c:259-265) -> e + q in (0, 2q)
 __device__ __forceinline__ uint32_t reduce_small(const int8_t *__restrict__ e, uint32_t pos, uint32_t q)
 {
-    const int v = __ldg(e + pos);
-    return v < 0 ? q + (uint32_t)v : (uint32_t)v;
+    return (uint32_t)((int)__ldg(e + pos)) + q;
 }
-// (m + e) int64 -> |x| mod q, q - r for negatives (device/lib/ckks_common.c:224-245).
-// The result feeds a lazy butterfly, so any representative below 4q is as good as the canonical one.
-// |x| < 2^32 for every message the default scales can encode without overflow in practice
-// (|coefficient| <= max|v| * scale), so that case takes a 32-bit lazy Barrett step (one IMAD.HI);
-// anything larger falls back to the exact 64-bit reduction.  Both are exact residues.
+// (m + e) int64 (device/lib/ckks_common.c:224-245).
+// small == true promises |m + e| < 2q for every coefficient of this ciphertext (decided per CTA from
+// the encode kernel's max |m|), so the low words carry the whole value and
+// min(x, x + 2q) over unsigned words maps it into [0, 2q): one VIADDMNMX.  Otherwise: exact 64-bit
+// Barrett reduction of |x| and a conditional negation.
+template <bool SMALL>
 __device__ __forceinline__ uint32_t reduce_pte(const int64_t *__restrict__ pt, const int8_t *__restrict__ e,
                                                uint32_t pos, const SebModulus &m)
 {
+    if (SMALL)
+    {
+        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(pt + pos));  // little endian: low word
+        const uint32_t x  = lo + (uint32_t)((int)__ldg(e + pos));
+        return min(x, x + m.two_q);
+    }
     const uint64_t x  = (uint64_t)__ldg(pt + pos) + (uint64_t)(int64_t)__ldg(e + pos);
     const bool neg    = (int64_t)x < 0;
     const uint64_t ax = neg ? (uint64_t)0 - x : x;
-    uint32_t r;
-    if ((uint32_t)(ax >> 32) == 0)
-    {
-        const uint32_t lo = (uint32_t)ax;
-        r                 = lo - __umulhi(lo, m.ratio_hi) * m.q;  // [0, 2q): floor(2^32/q) underestimates by < 1
-        return neg ? m.two_q - r : r;                             // (0, 2q]
-    }
-    r = seb_barrett64(ax, m);
+    const uint32_t r  = seb_barrett64(ax, m);
     return neg ? m.q - r : r;
 }
+// CBD samples lie in [-21, 21] (device/lib/sample.c:278-284)
+#define SEB_E_BOUND 21u
 
 // ---------------------------------------------------------------------------------------------
 // NTT only
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, NttOcc<LOGN>::MINB)
 // ---------------------------------------------------------------------------------------------
 // asymmetric encrypt, one (ciphertext, prime)
 // ---------------------------------------------------------------------------------------------
+template <bool SMALL>
 struct LoadAsym
 {
     const uint8_t *u;
@@ -121,7 +124,7 @@ struct LoadAsym
     {
         if (p == 0) return expand_ternary(u, pos, m.q);
         if (p == 1) return reduce_small(e1, pos, m.q);
-        return reduce_pte(pt, e0, pos, m);
+        return reduce_pte<SMALL>(pt, e0, pos, m);
     }
 };
 
@@ -159,7 +162,8 @@ __device__ __forceinline__ void asym_store8(const uint32_t (&xu)[8], const uint3
 // Three polynomials at once (registers permitting): every twiddle fetched once for all three.
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
-    k_encrypt_asym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
+    k_encrypt_asym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
+                   const uint8_t *__restrict__ u,
                    const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
                    const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
                    uint32_t *__restrict__ out, size_t batch)
@@ -172,9 +176,19 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
     const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
 
-    LoadAsym ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
+    const seb_oct *tw = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
     uint32_t x[3][SEB_E];
-    seb_ntt_forward<LOGN, 3>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
+    if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // CTA-uniform: |m + e0| < 2q everywhere in this ciphertext
+    {
+        LoadAsym<true> ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
+        seb_ntt_first<LOGN, 3>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    else
+    {
+        LoadAsym<false> ld{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m};
+        seb_ntt_first<LOGN, 3>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    seb_ntt_rest<LOGN, 3>(x, smem, t, tw, m.q, m.two_q);
 
     using O           = NttOut<LOGN>;
     uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
@@ -203,16 +217,18 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
 // Large degrees (n >= 8192): the three transforms run one after another through one working
 // buffer so the register footprint stays that of a single NTT; ntt(e1) and ntt(m+e0) wait in
 // shared memory (in the slots of the thread that will consume them) for ntt(u)'s epilogue.
+template <bool SMALL>
 struct LoadOne
 {
-    LoadAsym a;
+    LoadAsym<SMALL> a;
     int which;
     __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return a(which, pos); }
 };
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
-    k_encrypt_asym_seq(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const uint8_t *__restrict__ u,
+    k_encrypt_asym_seq(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
+                       const uint8_t *__restrict__ u,
                        const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
                        const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
                        uint32_t *__restrict__ out, size_t batch)
@@ -229,12 +245,18 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
     using O            = NttOut<LOGN>;
 
     uint32_t x[1][SEB_E];
-    LoadOne ld{LoadAsym{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
+    const bool small = __ldg(mag + b) < m.two_q - SEB_E_BOUND;  // CTA-uniform, see k_encrypt_asym
+    LoadOne<true> lds{LoadAsym<true>{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
+    LoadOne<false> ldb{LoadAsym<false>{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
 #pragma unroll 1
     for (int which = 1; which <= 2; which++)  // 1: e1 -> buffer 1, 2: m+e0 -> buffer 2
     {
-        ld.which = which;
-        seb_ntt_forward<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+        lds.which = ldb.which = which;
+        if (small)
+            seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, lds);
+        else
+            seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ldb);
+        seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
 #pragma unroll
         for (int i = 0; i < O::GPL; i++)
 #pragma unroll
@@ -246,8 +268,9 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
             }
         __syncthreads();  // the working buffer is about to be overwritten by the next transform
     }
-    ld.which = 0;
-    seb_ntt_forward<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+    lds.which = 0;  // u: the same conversion in both variants
+    seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, lds);
+    seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
 
     uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
     uint32_t *c1      = c0 + N;
@@ -279,17 +302,22 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
 // ---------------------------------------------------------------------------------------------
 // symmetric encrypt, one (ciphertext, prime)
 // ---------------------------------------------------------------------------------------------
+template <bool SMALL>
 struct LoadSym
 {
     const int8_t *e;
     const int64_t *pt;
     SebModulus m;
-    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return reduce_pte(pt, e, pos, m); }
+    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const
+    {
+        return reduce_pte<SMALL>(pt, e, pos, m);
+    }
 };
 
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
-    k_encrypt_sym(const int64_t *__restrict__ pt, const int8_t *__restrict__ e, const seb_oct *__restrict__ roots,
+    k_encrypt_sym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
+                  const seb_oct *__restrict__ roots,
                   const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
                   uint32_t *__restrict__ out, int quirk, size_t batch)
 {
@@ -301,9 +329,19 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
     const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
 
-    LoadSym ld{e + b * N, pt + b * N, m};
+    const seb_oct *tw = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
     uint32_t x[1][SEB_E];
-    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
+    if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // CTA-uniform, see k_encrypt_asym
+    {
+        LoadSym<true> ld{e + b * N, pt + b * N, m};
+        seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    else
+    {
+        LoadSym<false> ld{e + b * N, pt + b * N, m};
+        seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
 
     using O           = NttOut<LOGN>;
     uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
@@ -427,7 +465,7 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, cons
     return cudaGetLastError();
 }
 
-cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
+cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const uint8_t *u,
                                     const seb_oct *roots, const seb_oct *pk0s, const seb_oct *pk1s,
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st)
 {
@@ -435,22 +473,22 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e
 #define RUN(L)                                                                                                 \
     if (L >= 13)                                                                                               \
         k_encrypt_asym_seq<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(  \
-            pt, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch);                                     \
+            pt, mag, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch);                                \
     else                                                                                                    \
         k_encrypt_asym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(      \
-            pt, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch)
+            pt, mag, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
 }
 
-cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const seb_oct *roots,
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
                                    const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
                                    int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
 #define RUN(L)                                                                                              \
-    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, e, roots, ntt_s, mods, \
+    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, mag, e, roots, ntt_s, mods, \
                                                                                       np, out, quirk, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN

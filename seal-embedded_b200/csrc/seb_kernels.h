@@ -26,8 +26,10 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
 // ---- encode (seb_encode.cu) ----
 // values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);
 // src_map[pos] = slot whose value lands on position pos; tw[i] = IFFT twiddle (re, im), i in [1,n)
+// fail[b] is set when item b overflows int64; mag[b] (may be NULL; zeroed by the caller) receives
+// max |coefficient| of item b clipped to 2^32 - 1
 cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
-                              const double2 *tw, double n_inv, int64_t *pt, int *fail, int batch,
+                              const double2 *tw, double n_inv, int64_t *pt, int *fail, uint32_t *mag, int batch,
                               cudaStream_t st);
 cudaError_t seb_encode_configure(int logn);
 
@@ -40,12 +42,13 @@ void seb_host_build_epi(int logn, const uint2 *natural, seb_oct *out);
 cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, const SebModuli &mods, int np,
                            size_t npolys_total, cudaStream_t st);
 // asym: out[b][p][0] = pk0 (.) ntt(u) + ntt(m+e0), out[b][p][1] = pk1 (.) ntt(u) + ntt(e1)
-cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const int8_t *e, const uint8_t *u,
+// mag: per item max |pt| clipped to 32 bits (from seb_launch_encode); selects the 32-bit reduction path
+cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const uint8_t *u,
                                     const seb_oct *roots, const seb_oct *pk0s, const seb_oct *pk1s,
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st);
 // sym: out[b][p][1] already holds a; out[b][p][0] = -(a (.) ntt(s)) + ntt(m+e);
 // quirk != 0 additionally overwrites out[b][p][1] with ntt(m+e) (reference byte stream)
-cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const int8_t *e, const seb_oct *roots,
+cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
                                    const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
                                    int batch, cudaStream_t st);
 cudaError_t seb_encrypt_configure(int logn);

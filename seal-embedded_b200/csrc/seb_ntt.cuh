@@ -290,6 +290,31 @@ __device__ __forceinline__ void seb_ntt_forward(uint32_t (&x)[NPOLY][SEB_E], uin
     SebNttRun<LOGN, 0, NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
 }
 
+// The same transform in two calls, for callers whose on-load conversion comes in several variants:
+// only pass 0 touches the loader, so only pass 0 is instantiated per variant.
+//   seb_ntt_first : pass 0 (+ the barrier that publishes its results)
+//   seb_ntt_rest  : passes 1 .. NPASS-1
+struct SebNoLoad
+{
+    __device__ __forceinline__ uint32_t operator()(int, uint32_t) const { return 0u; }
+};
+template <int LOGN, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_first(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
+                                              Loader &load)
+{
+    seb_ntt_pass<LOGN, 0, NPOLY>(x, smem, t, tw, q, two_q, load);
+    __syncthreads();
+}
+template <int LOGN, int NPOLY>
+__device__ __forceinline__ void seb_ntt_rest(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+                                             const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q)
+{
+    static_assert(NttPlan<LOGN>::NPASS >= 2, "plan with a single pass");
+    SebNoLoad none;
+    SebNttRun<LOGN, 1, NPOLY, SebNoLoad>::run(x, smem, t, tw, q, two_q, none);
+}
+
 template <int LOGN>
 struct NttOut
 {

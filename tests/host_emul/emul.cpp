@@ -174,6 +174,9 @@ static void enc_passes(std::vector<std::array<double, 2 * ENC_E>> &regs, double 
     if constexpr (P + 1 < enc_npass(LOGNL)) enc_passes<LOGN, LOGNL, P + 1>(regs, sre, sim, pos0, vals, vlen, src_map, tw);
 }
 
+static uint32_t g_emul_mag = 0;  // max |coefficient| (clipped) of the last emulated encode
+extern "C" uint32_t emul_encode_mag(void) { return g_emul_mag; }
+
 template <int LOGN, int CL>
 static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const double2 *tw, double n_inv,
                     int64_t *out)
@@ -185,6 +188,7 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
     constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
     constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
     int bad             = 0;
+    g_emul_mag          = 0;
     std::vector<double> sre[2], sim[2];
     for (int rank = 0; rank < CL; rank++)
     {
@@ -202,7 +206,7 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
                 {
                     const uint32_t pos = base | ((uint32_t)j << LSL);
                     if (CL == 1)
-                        out[pos] = enc_finish(regs[t][i * (1 << RL) + j], n_inv, bad);
+                        out[pos] = enc_finish(regs[t][i * (1 << RL) + j], n_inv, bad, g_emul_mag);
                     else
                     {
                         sre[rank][enc_swz(pos)] = regs[t][i * (1 << RL) + j];
@@ -218,7 +222,7 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
                 const uint32_t sk = enc_swz(k);
                 const double re   = enc_cross_re(rank, sre[rank][sk], sim[rank][sk], sre[rank ^ 1][sk],
                                                  sim[rank ^ 1][sk], tw[1]);
-                out[rank * NL + k] = enc_finish(re, n_inv, bad);
+                out[rank * NL + k] = enc_finish(re, n_inv, bad, g_emul_mag);
             }
     return bad;
 }

@@ -272,6 +272,39 @@ def test_encrypt_large_magnitudes(n, np_, asym, seb, torch_cuda, oracle_mod, orc
     assert big > 1000  # the 64-bit path really ran
 
 
+@pytest.mark.parametrize("n,np_", [(4096, 3), (2048, 1)])
+def test_encrypt_reduction_path_boundary(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """The encrypt kernels pick a 32-bit reduction of m + e0 when max |m| < 2q - 21 and the 64-bit one
+    otherwise: constant messages put |m[0]| right at that switch (both signs, both sides) for the
+    30-bit and the 27-bit primes."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    ctx.set_public_key(pk0, pk1)
+    q0 = ctx.primes[0]
+    centre = np.float32((2 * q0 - 21) / ctx.scale)
+    cs = [centre]
+    for _ in range(3):
+        cs = [np.nextafter(cs[0], np.float32(0)), *cs, np.nextafter(cs[-1], np.float32(1e9))]
+    cs = cs + [-c for c in cs] + [np.float32(q0 / ctx.scale), np.float32(-4.0 * q0 / ctx.scale)]
+    batch, vlen = len(cs), n // 2
+    vals = np.stack([np.full(vlen, c, np.float32) for c in cs])
+    seeds = oracle_mod.make_seeds(batch, b"edge-%d" % n)
+    d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    ctx.encrypt_asym_device(dev(torch, vals), vlen, dev(torch, seeds), batch, d_out)
+    assert ctx.encode_failures() == 0
+    got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+    below = above = 0
+    for b in range(batch):
+        ok_pt, pt = orc.encode(n, vals[b])
+        mx = int(np.abs(pt).max())
+        below += mx < 2 * q0 - 21
+        above += mx >= 2 * q0 - 21
+        ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        assert ok and ok_pt and np.array_equal(got[b], exp), (n, b, mx)
+    assert below >= 3 and above >= 3
+
+
 def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs):
     """Host-pointer batch API: pageable and pinned buffers, more items than one chunk, ragged vlen."""
     torch = torch_cuda

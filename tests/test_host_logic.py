@@ -36,6 +36,7 @@ def E(emul):
     emul.emul_shoup_lazy.restype = C.c_uint32
     emul.emul_encode.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_double),
                                  C.c_double, C.POINTER(C.c_int64)]
+    emul.emul_encode_mag.restype = C.c_uint32
     emul.emul_keccak.argtypes = [C.POINTER(C.c_uint64)]
     emul.emul_prng_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64)]
     emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
@@ -182,6 +183,8 @@ def test_encode_emulation_matches_oracle(logn, E, orc, oracle_mod):
                             _p(out, C.c_int64))
         ok, exp = orc.encode(n, v[:vlen])
         assert bad == 0 and ok and np.array_equal(out, exp), (logn, vlen)
+        # per-item magnitude handed to the encrypt kernels: max |coefficient| clipped to 32 bits
+        assert E.emul_encode_mag() == min(int(np.abs(exp).max()), 0xFFFFFFFF)
     # overflow flag (ckks_common.c:195-204)
     v = np.full(n // 2, 3.0e38, np.float32)
     out = np.zeros(n, np.int64)
