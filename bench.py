@@ -129,7 +129,7 @@ def run_reference_arm(args) -> None:
             "cpu_baseline": arm.describe(value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line, default=float), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -383,12 +383,27 @@ def run_b200_arm(args) -> None:
             "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
             "kernels_ms": {nm: float(v) for nm, v in zip(names, avg)},
             "roofline": roofline, "ntt_microbench": ntt_micro, "cpu_baseline": cpu}
-    print(json.dumps(line, default=float), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of this process, on the process's original stdout."""
+    data = (json.dumps(line, default=float) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner,
+    # NCCL_DEBUG output, torchrun notices) is sent to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -67,12 +67,12 @@ struct LoadPlain
 // item index of this CTA for a grid built by seb_grid()
 __device__ __forceinline__ size_t seb_item() { return (size_t)blockIdx.z * gridDim.y + blockIdx.y; }
 
-// resident CTAs per SM the NTT-only kernel is compiled for (tools/ubench/ubench_ntt: 5 x 256 threads at
-// 48 registers beats 4 x 64 registers for n = 4096)
+// resident CTAs per SM the NTT-only kernel is compiled for, per degree: the best of the sweep in
+// profiles/r01_ubench_ntt_occupancy.txt (48 registers for n <= 4096, 32 above)
 template <int LOGN>
 struct NttOcc
 {
-    static constexpr int MINB = LOGN == 12 ? 5 : 1;
+    static constexpr int MINB = LOGN == 10 ? 20 : LOGN == 11 ? 10 : LOGN == 12 ? 5 : LOGN == 13 ? 4 : 2;
 };
 
 template <int LOGN>
