@@ -33,8 +33,9 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
     constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
     constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
     extern __shared__ double esm[];
-    double *sre = esm;
-    double *sim = esm + NL;
+    double *sre   = esm;
+    double *sim   = esm + NL;
+    float *svals  = reinterpret_cast<float *>(esm + 2 * NL);  // n/2 floats: the message, zero padded
 
     const int t            = threadIdx.x;
     const size_t b         = blockIdx.x / CL;
@@ -45,8 +46,12 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
     int bad                = 0;
     uint32_t mx            = 0;  // max |coefficient| this thread produced, clipped to 32 bits
 
+    // stage the message with coalesced loads; the gather of pass 0 then reads shared memory
+    for (int i = t; i < N / 2; i += T) svals[i] = i < vlen ? __ldg(vals + i) : 0.0f;
+    __syncthreads();
+
     double xr[ENC_E], xi[ENC_E];
-    EncRun<LOGN, LOGNL, 0>::run(xr, xi, sre, sim, t, pos0, vals, vlen, src_map, tw);
+    EncRun<LOGN, LOGNL, 0>::run(xr, xi, sre, sim, t, pos0, svals, src_map, tw);
 
     if (CL == 1)
     {
@@ -108,7 +113,7 @@ template <int LOGN, int CL>
 static cudaError_t encode_cfg()
 {
     return cudaFuncSetAttribute(k_encode<LOGN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(double) * 2 * ((1 << LOGN) / CL)));
+                                (int)(sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * ((1 << LOGN) / 2)));
 }
 
 cudaError_t seb_encode_configure(int logn)
@@ -132,7 +137,7 @@ static cudaError_t encode_launch(const float *values, size_t v_stride, int vlen,
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = dim3((unsigned)batch * CL);
     cfg.blockDim           = dim3((1 << LOGN) / CL / ENC_E);
-    cfg.dynamicSmemBytes   = sizeof(double) * 2 * ((1 << LOGN) / CL);
+    cfg.dynamicSmemBytes   = sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * ((1 << LOGN) / 2);
     cfg.stream             = st;
     cudaLaunchAttribute attr[1];
     attr[0].id               = cudaLaunchAttributeClusterDimension;

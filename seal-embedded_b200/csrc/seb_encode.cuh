@@ -25,11 +25,12 @@ __device__ __forceinline__ uint32_t enc_swz(uint32_t i)
 
 // one pass = R fused Gentleman-Sande stages starting at butterfly distance S = 2^LS
 // (fft.c:119-143: vec[k] = u + v; vec[k+tt] = (u - v) * s)
+// svals: the message of this ciphertext zero-padded to n/2 floats (staged in shared memory by the
+// kernel: the scatter of ckks_common.c:139-153 is done as a gather from it)
 template <int LOGN, int LOGNL, int P>
 __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E], double *sre, double *sim,
-                                         const int t, const uint32_t cta_pos0, const float *__restrict__ vals,
-                                         const int vlen, const uint16_t *__restrict__ src_map,
-                                         const double2 *__restrict__ tw)
+                                         const int t, const uint32_t cta_pos0, const float *svals,
+                                         const uint16_t *__restrict__ src_map, const double2 *__restrict__ tw)
 {
     constexpr int NL   = 1 << LOGNL;
     constexpr int T    = NL / ENC_E;
@@ -45,19 +46,27 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
         const uint32_t off  = g & ((1u << LS) - 1u);
         const uint32_t blk  = g >> LS;
         const uint32_t base = (blk << (LS + R)) | off;  // local position of element j = 0
-#pragma unroll
-        for (int j = 0; j < (1 << R); j++)
+        if (P == 0)
         {
-            const uint32_t pos = base | ((uint32_t)j << LS);
-            if (P == 0)
+            // pass 0 works on 8 consecutive positions (LS = 0, R = 3): their 8 map entries are one
+            // 128-bit load; both conjugate slots of value i receive values[i]
+            static_assert(P != 0 || (LS == 0 && R == 3), "pass 0 is expected to be radix-8 on contiguous data");
+            const uint4 mp = __ldg(reinterpret_cast<const uint4 *>(src_map + cta_pos0 + base));
+            const uint32_t mw[4] = {mp.x, mp.y, mp.z, mp.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++)
             {
-                // scatter (ckks_common.c:139-153) done as a gather: both conjugate slots get values[i]
-                const uint32_t slot      = __ldg(src_map + cta_pos0 + pos);
-                xr[i * (1 << R) + j] = (int)slot < vlen ? (double)__ldg(vals + slot) : 0.0;
-                xi[i * (1 << R) + j] = 0.0;
+                const uint32_t slot = (mw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                xr[i * 8 + j]       = (double)svals[slot];
+                xi[i * 8 + j]       = 0.0;
             }
-            else
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
             {
+                const uint32_t pos   = base | ((uint32_t)j << LS);
                 xr[i * (1 << R) + j] = sre[enc_swz(pos)];
                 xi[i * (1 << R) + j] = sim[enc_swz(pos)];
             }
@@ -103,15 +112,15 @@ template <int LOGN, int LOGNL, int P>
 struct EncRun
 {
     __device__ __forceinline__ static void run(double (&xr)[ENC_E], double (&xi)[ENC_E], double *sre, double *sim,
-                                               int t, uint32_t cta_pos0, const float *vals, int vlen,
+                                               int t, uint32_t cta_pos0, const float *svals,
                                                const uint16_t *src_map, const double2 *tw)
     {
-        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, cta_pos0, vals, vlen, src_map, tw);
+        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, cta_pos0, svals, src_map, tw);
         if (P + 1 < enc_npass(LOGNL))
         {
             __syncthreads();
-            EncRun<LOGN, LOGNL, (P + 1 < enc_npass(LOGNL) ? P + 1 : P)>::run(xr, xi, sre, sim, t, cta_pos0, vals,
-                                                                             vlen, src_map, tw);
+            EncRun<LOGN, LOGNL, (P + 1 < enc_npass(LOGNL) ? P + 1 : P)>::run(xr, xi, sre, sim, t, cta_pos0, svals,
+                                                                             src_map, tw);
         }
     }
 };

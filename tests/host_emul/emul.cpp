@@ -162,16 +162,16 @@ extern "C" uint32_t emul_shoup_lazy(uint32_t x, uint32_t w, uint32_t q)
 // ---------------------------------------------------------------------------------------------
 template <int LOGN, int LOGNL, int P>
 static void enc_passes(std::vector<std::array<double, 2 * ENC_E>> &regs, double *sre, double *sim, uint32_t pos0,
-                       const float *vals, int vlen, const uint16_t *src_map, const double2 *tw)
+                       const float *svals, const uint16_t *src_map, const double2 *tw)
 {
     constexpr int T = (1 << LOGNL) / ENC_E;
     for (int t = 0; t < T; t++)
     {
         double(&xr)[ENC_E] = *reinterpret_cast<double(*)[ENC_E]>(regs[t].data());
         double(&xi)[ENC_E] = *reinterpret_cast<double(*)[ENC_E]>(regs[t].data() + ENC_E);
-        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, pos0, vals, vlen, src_map, tw);
+        enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, pos0, svals, src_map, tw);
     }
-    if constexpr (P + 1 < enc_npass(LOGNL)) enc_passes<LOGN, LOGNL, P + 1>(regs, sre, sim, pos0, vals, vlen, src_map, tw);
+    if constexpr (P + 1 < enc_npass(LOGNL)) enc_passes<LOGN, LOGNL, P + 1>(regs, sre, sim, pos0, svals, src_map, tw);
 }
 
 static uint32_t g_emul_mag = 0;  // max |coefficient| (clipped) of the last emulated encode
@@ -190,12 +190,14 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
     int bad             = 0;
     g_emul_mag          = 0;
     std::vector<double> sre[2], sim[2];
+    std::vector<float> svals(N / 2, 0.0f);  // the kernel's staged, zero-padded message
+    for (int i = 0; i < vlen && i < N / 2; i++) svals[i] = vals[i];
     for (int rank = 0; rank < CL; rank++)
     {
         sre[rank].assign(NL, 1e300);
         sim[rank].assign(NL, 1e300);
         std::vector<std::array<double, 2 * ENC_E>> regs(T);
-        enc_passes<LOGN, LOGNL, 0>(regs, sre[rank].data(), sim[rank].data(), rank * NL, vals, vlen, src_map, tw);
+        enc_passes<LOGN, LOGNL, 0>(regs, sre[rank].data(), sim[rank].data(), rank * NL, svals.data(), src_map, tw);
         for (int t = 0; t < T; t++)
             for (int i = 0; i < (ENC_E >> RL); i++)
             {
