@@ -20,8 +20,17 @@ namespace cg = cooperative_groups;
 
 #include "seb_encode.cuh"
 
+// resident CTAs per SM the kernel is compiled for: 64 registers per thread at every degree (two
+// 512-thread CTAs per SM for n = 4096)
 template <int LOGN, int CL>
-__global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
+struct EncOcc
+{
+    static constexpr int T    = (1 << LOGN) / CL / ENC_E;
+    static constexpr int MINB = T >= 1024 ? 1 : 1024 / T;
+};
+
+template <int LOGN, int CL>
+__global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MINB)
     k_encode(const float *__restrict__ values, size_t v_stride, int vlen, const uint16_t *__restrict__ src_map,
              const double2 *__restrict__ tw, double n_inv, int64_t *__restrict__ pt, int *__restrict__ fail,
              uint32_t *__restrict__ mag)
@@ -46,8 +55,16 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E)
     int bad                = 0;
     uint32_t mx            = 0;  // max |coefficient| this thread produced, clipped to 32 bits
 
-    // stage the message with coalesced loads; the gather of pass 0 then reads shared memory
-    for (int i = t; i < N / 2; i += T) svals[i] = i < vlen ? __ldg(vals + i) : 0.0f;
+    // stage the message with coalesced loads (all issued before the first store, so their latencies
+    // overlap); the gather of pass 0 then reads shared memory
+    {
+        constexpr int PER = (N / 2) / T;
+        float v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) v[k] = (t + k * T) < vlen ? __ldg(vals + t + k * T) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < PER; k++) svals[t + k * T] = v[k];
+    }
     __syncthreads();
 
     double xr[ENC_E], xi[ENC_E];

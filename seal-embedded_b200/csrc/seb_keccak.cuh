@@ -65,18 +65,60 @@ SEB_CONSTANT uint32_t c_keccak_rc_hi[24] = {
 
 // theta + rho + pi for lane SRC: B[DST] = rotl(A[SRC] ^ C[x-1] ^ rotl(C[x+1], 1), ROT)
 #define SEB_KECCAK_RP(SRC, DST, ROT)                                                                  \
+    if (!PRUNE || (DST) < 14)                                                                         \
     {                                                                                                 \
         const uint32_t tl_ = seb_xor3(lo[SRC], cl[((SRC) % 5 + 4) % 5], rl[((SRC) % 5 + 1) % 5]);    \
         const uint32_t th_ = seb_xor3(hi[SRC], ch[((SRC) % 5 + 4) % 5], rh[((SRC) % 5 + 1) % 5]);    \
         seb_rotl64<ROT>(tl_, th_, bl[DST], bh[DST]);                                                  \
     }
 
-// 24 rounds on 32-bit halves, 180 ALU operations per round: theta parities 20 (3-input XORs), their
-// rotations 10, theta-apply fused into a 3-input XOR 50, rho 48 funnel shifts, chi 50, iota 2.
+// One round on 32-bit halves, 180 ALU operations: theta parities 20 (3-input XORs), their rotations
+// 10, theta-apply fused into a 3-input XOR 50, rho 48 funnel shifts, chi 50, iota 2.
+// PRUNE: only output lanes 0..11 (the first 96 bytes of the rate) are wanted, which need B lanes
+// 0..13 only: 112 operations.
+template <bool PRUNE>
+__device__ __forceinline__ void seb_keccak_round(uint32_t (&lo)[25], uint32_t (&hi)[25], const int round)
+{
+    uint32_t cl[5], ch[5], rl[5], rh[5], bl[25], bh[25];
+#pragma unroll
+    for (int x = 0; x < 5; x++)
+    {
+        cl[x] = seb_xor3(seb_xor3(lo[x], lo[x + 5], lo[x + 10]), lo[x + 15], lo[x + 20]);
+        ch[x] = seb_xor3(seb_xor3(hi[x], hi[x + 5], hi[x + 10]), hi[x + 15], hi[x + 20]);
+    }
+#pragma unroll
+    for (int x = 0; x < 5; x++) seb_rotl64<1>(cl[x], ch[x], rl[x], rh[x]);
+    SEB_KECCAK_RP(0, 0, 0) SEB_KECCAK_RP(1, 10, 1) SEB_KECCAK_RP(2, 20, 62) SEB_KECCAK_RP(3, 5, 28)
+    SEB_KECCAK_RP(4, 15, 27) SEB_KECCAK_RP(5, 16, 36) SEB_KECCAK_RP(6, 1, 44) SEB_KECCAK_RP(7, 11, 6)
+    SEB_KECCAK_RP(8, 21, 55) SEB_KECCAK_RP(9, 6, 20) SEB_KECCAK_RP(10, 7, 3) SEB_KECCAK_RP(11, 17, 10)
+    SEB_KECCAK_RP(12, 2, 43) SEB_KECCAK_RP(13, 12, 25) SEB_KECCAK_RP(14, 22, 39) SEB_KECCAK_RP(15, 23, 41)
+    SEB_KECCAK_RP(16, 8, 45) SEB_KECCAK_RP(17, 18, 15) SEB_KECCAK_RP(18, 3, 21) SEB_KECCAK_RP(19, 13, 8)
+    SEB_KECCAK_RP(20, 14, 18) SEB_KECCAK_RP(21, 24, 2) SEB_KECCAK_RP(22, 9, 61) SEB_KECCAK_RP(23, 19, 56)
+    SEB_KECCAK_RP(24, 4, 14)
+#pragma unroll
+    for (int y = 0; y < 25; y += 5)
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+            if (!PRUNE || y + x < 12)
+            {
+                lo[y + x] = seb_chi(bl[y + x], bl[y + (x + 1) % 5], bl[y + (x + 2) % 5]);
+                hi[y + x] = seb_chi(bh[y + x], bh[y + (x + 1) % 5], bh[y + (x + 2) % 5]);
+            }
+    lo[0] ^= c_keccak_rc_lo[round];
+    hi[0] ^= c_keccak_rc_hi[round];
+}
+#undef SEB_KECCAK_RP
+
+// Keccak-f[1600].  NOUT = how many leading lanes of the result the caller reads: 25 for a full
+// permutation (sponges that keep squeezing), <= 12 when only the first 96 bytes are used — every
+// call of the ternary and centered-binomial samplers (device/lib/sample.c:223-241,311-356) — in
+// which case the last round is pruned and lanes >= NOUT of `a` are left unspecified.
 // The round loop stays rolled (one round ~190 instructions) so the kernels stay inside the
 // instruction cache; tools/ubench measured no gain from unrolling by 2.
+template <int NOUT = 25>
 __device__ __forceinline__ void seb_keccak_f1600(uint64_t (&a)[25])
 {
+    constexpr bool PRUNE = NOUT <= 12;
     uint32_t lo[25], hi[25];
 #pragma unroll
     for (int i = 0; i < 25; i++)
@@ -85,39 +127,11 @@ __device__ __forceinline__ void seb_keccak_f1600(uint64_t (&a)[25])
         hi[i] = (uint32_t)(a[i] >> 32);
     }
 #pragma unroll 1
-    for (int round = 0; round < 24; round++)
-    {
-        uint32_t cl[5], ch[5], rl[5], rh[5], bl[25], bh[25];
+    for (int round = 0; round < (PRUNE ? 23 : 24); round++) seb_keccak_round<false>(lo, hi, round);
+    if (PRUNE) seb_keccak_round<true>(lo, hi, 23);
 #pragma unroll
-        for (int x = 0; x < 5; x++)
-        {
-            cl[x] = seb_xor3(seb_xor3(lo[x], lo[x + 5], lo[x + 10]), lo[x + 15], lo[x + 20]);
-            ch[x] = seb_xor3(seb_xor3(hi[x], hi[x + 5], hi[x + 10]), hi[x + 15], hi[x + 20]);
-        }
-#pragma unroll
-        for (int x = 0; x < 5; x++) seb_rotl64<1>(cl[x], ch[x], rl[x], rh[x]);
-        SEB_KECCAK_RP(0, 0, 0) SEB_KECCAK_RP(1, 10, 1) SEB_KECCAK_RP(2, 20, 62) SEB_KECCAK_RP(3, 5, 28)
-        SEB_KECCAK_RP(4, 15, 27) SEB_KECCAK_RP(5, 16, 36) SEB_KECCAK_RP(6, 1, 44) SEB_KECCAK_RP(7, 11, 6)
-        SEB_KECCAK_RP(8, 21, 55) SEB_KECCAK_RP(9, 6, 20) SEB_KECCAK_RP(10, 7, 3) SEB_KECCAK_RP(11, 17, 10)
-        SEB_KECCAK_RP(12, 2, 43) SEB_KECCAK_RP(13, 12, 25) SEB_KECCAK_RP(14, 22, 39) SEB_KECCAK_RP(15, 23, 41)
-        SEB_KECCAK_RP(16, 8, 45) SEB_KECCAK_RP(17, 18, 15) SEB_KECCAK_RP(18, 3, 21) SEB_KECCAK_RP(19, 13, 8)
-        SEB_KECCAK_RP(20, 14, 18) SEB_KECCAK_RP(21, 24, 2) SEB_KECCAK_RP(22, 9, 61) SEB_KECCAK_RP(23, 19, 56)
-        SEB_KECCAK_RP(24, 4, 14)
-#pragma unroll
-        for (int y = 0; y < 25; y += 5)
-#pragma unroll
-            for (int x = 0; x < 5; x++)
-            {
-                lo[y + x] = seb_chi(bl[y + x], bl[y + (x + 1) % 5], bl[y + (x + 2) % 5]);
-                hi[y + x] = seb_chi(bh[y + x], bh[y + (x + 1) % 5], bh[y + (x + 2) % 5]);
-            }
-        lo[0] ^= c_keccak_rc_lo[round];
-        hi[0] ^= c_keccak_rc_hi[round];
-    }
-#pragma unroll
-    for (int i = 0; i < 25; i++) a[i] = ((uint64_t)hi[i] << 32) | lo[i];
+    for (int i = 0; i < (PRUNE ? 12 : 25); i++) a[i] = ((uint64_t)hi[i] << 32) | lo[i];
 }
-#undef SEB_KECCAK_RP
 
 // SHAKE256 absorb of (seed || LE64(counter)): 72 bytes, domain byte 0x1F at offset 72, final bit
 // 0x80 at offset 135 (device/lib/shake256/fips202.c:46-66).  seed8 = the seed as 8 LE words.

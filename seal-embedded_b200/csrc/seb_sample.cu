@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restric
     {
         uint64_t a[25];
         seb_prng_init(a, seed, cbase + (uint64_t)lane);
-        seb_keccak_f1600(a);
+        seb_keccak_f1600<12>(a);  // 96 bytes (or 1) are read from each call
 
         uint32_t m0, m1, m2;
         uint32_t packed[6];
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ 
     uint64_t s[8], a[25];
     load_seed(seeds, b, s);
     seb_prng_init(a, s, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
-    seb_keccak_f1600(a);
+    seb_keccak_f1600<12>(a);  // 96 bytes per call
 
     uint32_t o[4];
     seb_cbd_block(a, o);
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__
             {
                 uint64_t a[25];
                 seb_prng_init(a, s, wave_base + (uint64_t)lane);
-                seb_keccak_f1600(a);
+                seb_keccak_f1600<12>(a);  // 4 bytes per call
                 cand     = (uint32_t)a[0];
                 avail    = __ballot_sync(0xFFFFFFFFu, cand < max_multiple);
                 cur_base = wave_base;
