@@ -5,12 +5,14 @@
 //                     expand u / reduce e1 / reduce (m+e0) on load, three NTTs through shared
 //                     memory sharing every twiddle fetch, then
 //                       c1 = pk1 (.) ntt(u) + ntt(e1),  c0 = pk0 (.) ntt(u) + ntt(m+e0)
-//                     straight from registers with 128-bit stores.
+//                     straight from registers with 256-bit stores.
 //   k_encrypt_sym   : one prime of ckks_encode_encrypt_sym (device/lib/ckks_sym.c:199-301) with
 //                     ntt(s) precomputed at setup:  c0 = -(a (.) ntt(s)) + ntt(m+e)
 //
 // One CTA of n/16 threads per polynomial slot; grid = (prime, item low, item high) so the CTAs that
 // re-read one ciphertext's m/e/u are scheduled together and hit L2, and no thread divides by np.
+#include <stdlib.h>
+
 #include "seb_kernels.h"
 #include "seb_ntt.cuh"
 
@@ -161,7 +163,8 @@ __device__ __forceinline__ void asym_store8(const uint32_t (&xu)[8], const uint3
 
 // Three polynomials at once (registers permitting): every twiddle fetched once for all three.
 template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
+__global__ void __launch_bounds__((1 << LOGN) / SEB_E,
+                                  (LOGN == 10 ? 12 : LOGN == 11 ? 6 : LOGN == 12 ? 3 : LOGN == 13 ? 2 : 1))
     k_encrypt_asym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
                    const uint8_t *__restrict__ u,
                    const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
@@ -209,91 +212,6 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 12 ? 3 : 1))
                 xe[c] = x[1][r + c];
                 xp[c] = x[2][r + c];
             }
-            const uint32_t ei = seb_epi_index<LOGN>(t, i, 2 * k);
-            asym_store8(xu, xe, xp, k0 + ei, k1 + ei, O::T, c0, c1, O::pos(t, i) + 8 * k, m.q, m.two_q);
-        }
-}
-
-// Large degrees (n >= 8192): the three transforms run one after another through one working
-// buffer so the register footprint stays that of a single NTT; ntt(e1) and ntt(m+e0) wait in
-// shared memory (in the slots of the thread that will consume them) for ntt(u)'s epilogue.
-template <bool SMALL>
-struct LoadOne
-{
-    LoadAsym<SMALL> a;
-    int which;
-    __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return a(which, pos); }
-};
-
-template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E, (LOGN == 13 ? 2 : 1))
-    k_encrypt_asym_seq(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
-                       const uint8_t *__restrict__ u,
-                       const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,
-                       const seb_oct *__restrict__ pk1s, const __grid_constant__ SebModuli mods, int np,
-                       uint32_t *__restrict__ out, size_t batch)
-{
-    constexpr int N          = 1 << LOGN;
-    constexpr uint32_t WORDS = NttSmem<LOGN>::WORDS;
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int t        = threadIdx.x;
-    const size_t b     = seb_item();
-    if (b >= batch) return;
-    const int p        = (int)blockIdx.x;
-    const SebModulus m = mods.m[p];
-    const seb_oct *tw  = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
-    using O            = NttOut<LOGN>;
-
-    uint32_t x[1][SEB_E];
-    const bool small = __ldg(mag + b) < m.two_q - SEB_E_BOUND;  // CTA-uniform, see k_encrypt_asym
-    LoadOne<true> lds{LoadAsym<true>{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
-    LoadOne<false> ldb{LoadAsym<false>{u + b * (N / 4), e + b * 2 * N, e + b * 2 * N + N, pt + b * N, m}, 1};
-#pragma unroll 1
-    for (int which = 1; which <= 2; which++)  // 1: e1 -> buffer 1, 2: m+e0 -> buffer 2
-    {
-        lds.which = ldb.which = which;
-        if (small)
-            seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, lds);
-        else
-            seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ldb);
-        seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
-#pragma unroll
-        for (int i = 0; i < O::GPL; i++)
-#pragma unroll
-            for (int k = 0; k < O::RUN / 4; k++)
-            {
-                const int r = i * O::RUN + 4 * k;
-                *reinterpret_cast<uint4 *>(smem + which * WORDS + seb_pad<LOGN>(O::pos(t, i)) + 4 * k) =
-                    make_uint4(x[0][r], x[0][r + 1], x[0][r + 2], x[0][r + 3]);
-            }
-        __syncthreads();  // the working buffer is about to be overwritten by the next transform
-    }
-    lds.which = 0;  // u: the same conversion in both variants
-    seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, lds);
-    seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
-
-    uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1      = c0 + N;
-    const seb_oct *k0 = pk0s + (size_t)p * (N / 4);
-    const seb_oct *k1 = pk1s + (size_t)p * (N / 4);
-#pragma unroll
-    for (int i = 0; i < O::GPL; i++)
-#pragma unroll
-        for (int k = 0; k < O::RUN / 8; k++)
-        {
-            const int r       = i * O::RUN + 8 * k;
-            const uint32_t sp = seb_pad<LOGN>(O::pos(t, i)) + 8 * k;
-            uint32_t xu[8], xe[8], xp[8];
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-            {
-                const uint4 ve = *reinterpret_cast<const uint4 *>(smem + WORDS + sp + 4 * h);
-                const uint4 vp = *reinterpret_cast<const uint4 *>(smem + 2 * WORDS + sp + 4 * h);
-                xe[4 * h + 0] = ve.x, xe[4 * h + 1] = ve.y, xe[4 * h + 2] = ve.z, xe[4 * h + 3] = ve.w;
-                xp[4 * h + 0] = vp.x, xp[4 * h + 1] = vp.y, xp[4 * h + 2] = vp.z, xp[4 * h + 3] = vp.w;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; c++) xu[c] = x[0][r + c];
             const uint32_t ei = seb_epi_index<LOGN>(t, i, 2 * k);
             asym_store8(xu, xe, xp, k0 + ei, k1 + ei, O::T, c0, c1, O::pos(t, i) + 8 * k, m.q, m.two_q);
         }
@@ -445,8 +363,6 @@ cudaError_t seb_encrypt_configure(int logn)
         if (err == cudaSuccess)                                                                                   \
             err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
         if (err == cudaSuccess)                                                                                   \
-            err = cudaFuncSetAttribute(k_encrypt_asym_seq<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
-        if (err == cudaSuccess)                                                                                   \
             err = cudaFuncSetAttribute(k_encrypt_sym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<L>::WORDS);    \
     }
     SEB_DISPATCH_LOGN(logn, CFG)
@@ -470,13 +386,9 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t 
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
-#define RUN(L)                                                                                                 \
-    if (L >= 13)                                                                                               \
-        k_encrypt_asym_seq<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(  \
-            pt, mag, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch);                                \
-    else                                                                                                    \
-        k_encrypt_asym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>(      \
-            pt, mag, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch)
+#define RUN(L)                                                                                            \
+    k_encrypt_asym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 12 * NttSmem<L>::WORDS, st>>>( \
+        pt, mag, e, u, roots, pk0s, pk1s, mods, np, out, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
