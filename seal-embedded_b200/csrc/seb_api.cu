@@ -129,6 +129,8 @@ struct Scratch  // per in-flight chunk
     uint32_t *ctr_a  = nullptr;
     int *fail        = nullptr;
     uint32_t *mag    = nullptr;  // max |plaintext coefficient| per item, clipped to 32 bits
+    uint16_t *rej_idx = nullptr;  // [cap][n/8] uniform sampler: indices of rejected words (symmetric mode)
+    uint32_t *rej_cnt = nullptr;  // [cap]
     // host-API staging
     size_t io_cap    = 0;
     float *d_values  = nullptr;
@@ -153,6 +155,7 @@ struct seb_ctx
     uint32_t psis[SEB_MAX_PRIMES]   = {0};
     SebModuli mods;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t rej_cap = 0;  // capacity of the uniform sampler's per-ciphertext reject lists (n/8)
     // resident tables
     seb_oct *d_roots    = nullptr;  // [np][seb_table_octs]: per-pass twiddle tables
     double2 *d_tw       = nullptr;  // [n]
@@ -190,6 +193,10 @@ static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
     cudaFree(s.mag);
+    cudaFree(s.rej_idx);
+    cudaFree(s.rej_cnt);
+    s.rej_idx = nullptr;
+    s.rej_cnt = nullptr;
     s.cap = 0;
     CU(cudaMalloc(&s.pt, batch * c->n * sizeof(int64_t)));
     CU(cudaMalloc(&s.e, batch * 2 * c->n));
@@ -198,6 +205,11 @@ static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
     CU(cudaMalloc(&s.ctr_a, batch * sizeof(uint32_t)));
     CU(cudaMalloc(&s.fail, batch * sizeof(int)));
     CU(cudaMalloc(&s.mag, batch * sizeof(uint32_t)));
+    if (!c->asym)
+    {
+        CU(cudaMalloc(&s.rej_idx, batch * (size_t)(c->rej_cap ? c->rej_cap : 1) * sizeof(uint16_t)));
+        CU(cudaMalloc(&s.rej_cnt, batch * sizeof(uint32_t)));
+    }
     s.cap = batch;
     return 0;
 }
@@ -211,6 +223,8 @@ static void free_scratch(Scratch &s)
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
     cudaFree(s.mag);
+    cudaFree(s.rej_idx);
+    cudaFree(s.rej_cnt);
     cudaFree(s.d_values);
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
@@ -325,6 +339,11 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     }
     // parameters.c:197-225: the default scale is tied to the degree
     c->scale = scale > 0 ? scale : (n == 1024 ? 1048576.0 : 33554432.0);
+    // 1.9 % of the words are rejected under a 30-bit prime: n/8 entries is > 40 standard deviations of
+    // head-room; overflowing lists fall back to a scan (SEB_UNIFORM_LIST_CAP lets tests force that)
+    c->rej_cap = (uint32_t)(n / 8);
+    if (const char *v = getenv("SEB_UNIFORM_LIST_CAP"))
+        if (*v && (uint32_t)atoi(v) < c->rej_cap) c->rej_cap = (uint32_t)atoi(v);
 
     auto bail = [&](const char *what, cudaError_t e) -> seb_ctx * {
         fail(SE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -501,7 +520,11 @@ extern "C" int seb_sample_uniform_device(seb_ctx *c, const uint8_t *d_seeds, uin
 {
     if (!c || !d_seeds || !d_ctr || !d_out || prime_idx >= c->np)
         return fail(SE_ERR_INVALD_ARGUMENT, "bad argument");
-    seb_launch_uniform(d_seeds, d_ctr, d_out, ct_stride, (int)c->n, c->mods.m[prime_idx], (int)batch, c->stream);
+    if (c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "the uniform sampler belongs to a symmetric context");
+    int r = ensure_scratch(c, c->slot[0], batch);
+    if (r) return r;
+    seb_launch_uniform(d_seeds, d_ctr, d_out, ct_stride, (int)c->n, c->mods.m[prime_idx], (int)batch,
+                       c->slot[0].rej_idx, c->slot[0].rej_cnt, c->rej_cap, c->stream);
     c->launches += 2;
     CU(cudaGetLastError());
     return 0;
@@ -566,7 +589,8 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
     const size_t ct_stride = 2 * c->np * c->n;
     for (size_t p = 0; p < c->np; p++)
-        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch, st);
+        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch,
+                           s.rej_idx, s.rej_cnt, c->rej_cap, st);
     CU(cudaGetLastError());
     prof_mark(c, st, 3);
     CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,

@@ -20,8 +20,10 @@ void seb_launch_sample_ternary(const uint8_t *seeds, uint8_t *u_out, uint32_t *c
                                cudaStream_t st);
 void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_t *e_out, int n, int npoly,
                            int batch, cudaStream_t st);
+// rej_idx [batch][rej_cap] / rej_cnt [batch]: scratch for the per-ciphertext lists of rejected words
 void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
-                        const SebModulus &mod, int batch, cudaStream_t st);
+                        const SebModulus &mod, int batch, uint16_t *rej_idx, uint32_t *rej_cnt, uint32_t rej_cap,
+                        cudaStream_t st);
 
 // ---- encode (seb_encode.cu) ----
 // values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);

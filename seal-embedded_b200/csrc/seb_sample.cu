@@ -164,19 +164,25 @@ __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // Thread per ciphertext: the 4n-byte squeeze is one sequential sponge.  Accepted words are
 // stored already reduced mod q (< q <= max_multiple); rejected words are stored raw
-// (>= max_multiple), which is how k_uniform_fix finds them.
-__global__ void __launch_bounds__(128) k_uniform_bulk(const uint8_t *__restrict__ seeds,
+// (>= max_multiple) and their indices appended, in ascending order, to the ciphertext's reject list
+// (rej_idx[b][0..cap), rej_cnt[b] = how many there were, which may exceed cap).
+__global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__ seeds,
                                                       const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
                                                       size_t ct_stride, int n, SebModulus mod,
-                                                      uint32_t max_multiple, int batch)
+                                                      uint32_t max_multiple, int batch,
+                                                      uint16_t *__restrict__ rej_idx, uint32_t *__restrict__ rej_cnt,
+                                                      uint32_t cap)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     uint64_t s[8], a[25];
     load_seed(seeds, (size_t)b, s);
     seb_prng_init(a, s, (uint64_t)ctr[b]);
-    uint2 *dst = reinterpret_cast<uint2 *>(out + (size_t)b * ct_stride);
-    int left   = n / 2;  // 64-bit lanes still to emit
+    uint2 *dst     = reinterpret_cast<uint2 *>(out + (size_t)b * ct_stride);
+    uint16_t *list = rej_idx + (size_t)b * cap;
+    uint32_t cnt   = 0;
+    uint32_t word  = 0;    // index of the next word of the polynomial
+    int left       = n / 2;  // 64-bit lanes still to emit
     while (left > 0)
     {
         seb_keccak_f1600(a);
@@ -186,22 +192,41 @@ __global__ void __launch_bounds__(128) k_uniform_bulk(const uint8_t *__restrict_
             if (k < left)
             {
                 uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
-                if (lo < max_multiple) lo = seb_barrett32(lo, mod);
-                if (hi < max_multiple) hi = seb_barrett32(hi, mod);
+                if (lo < max_multiple)
+                    lo = seb_barrett32(lo, mod);
+                else
+                {
+                    if (cnt < cap) list[cnt] = (uint16_t)(word + 2 * k);
+                    cnt++;
+                }
+                if (hi < max_multiple)
+                    hi = seb_barrett32(hi, mod);
+                else
+                {
+                    if (cnt < cap) list[cnt] = (uint16_t)(word + 2 * k + 1);
+                    cnt++;
+                }
                 dst[k] = make_uint2(lo, hi);
             }
         }
         dst += 17;
+        word += 34;
         left -= 17;
     }
+    rej_cnt[b] = cnt;
 }
 
 // Warp per ciphertext: the k-th rejected index (ascending) receives the k-th accepted
 // candidate LE32(X(seed, c0+1+t, 4)), t = 0,1,...; the counter ends one past the last candidate
-// consumed (sample.c:49-56).
+// consumed (sample.c:49-56).  Candidates are generated 32 counters at a time; with the reject list
+// of the bulk kernel every accepted candidate of a wave is placed in parallel (its rank among the
+// accepted candidates so far selects the list entry).  A list that overflowed its capacity (never
+// with SHAKE output and cap = n/8, but it must stay correct) falls back to scanning the row.
 __global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
                                                      uint32_t *__restrict__ out, size_t ct_stride, int n,
-                                                     SebModulus mod, uint32_t max_multiple, int batch)
+                                                     SebModulus mod, uint32_t max_multiple, int batch,
+                                                     const uint16_t *__restrict__ rej_idx,
+                                                     const uint32_t *__restrict__ rej_cnt, uint32_t cap)
 {
     const int lane = threadIdx.x & 31;
     const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -213,33 +238,58 @@ __global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__
     const uint64_t c0  = (uint64_t)ctr[b];
     uint64_t wave_base = c0 + 1;  // counter of lane 0's candidate in the next wave to generate
     uint64_t last_used = c0;      // counter of the last candidate consumed
-    uint32_t avail     = 0;       // accepted, unused candidates of the current wave (bit = lane)
-    uint32_t cand      = 0;
-    uint64_t cur_base  = 0;
+    const uint32_t cnt = rej_cnt[b];
 
-    for (int base = 0; base < n; base += 32)
+    if (cnt <= cap)
     {
-        const uint32_t w = row[base + lane];
-        uint32_t rm      = __ballot_sync(0xFFFFFFFFu, w >= max_multiple);
-        while (rm)
+        const uint16_t *list = rej_idx + (size_t)b * cap;
+        uint32_t done        = 0;  // rejected words already replaced
+        while (done < cnt)
         {
-            while (avail == 0)
+            uint64_t a[25];
+            seb_prng_init(a, s, wave_base + (uint64_t)lane);
+            seb_keccak_f1600<12>(a);  // 4 bytes per call
+            const uint32_t cand  = (uint32_t)a[0];
+            const bool ok        = cand < max_multiple;
+            const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
+            const uint32_t rank  = done + (uint32_t)__popc(avail & ((1u << lane) - 1u));  // this candidate's turn
+            const bool used      = ok && rank < cnt;
+            if (used) row[list[rank]] = seb_barrett32(cand, mod);
+            const uint32_t um = __ballot_sync(0xFFFFFFFFu, used);
+            if (um) last_used = wave_base + (uint64_t)(31 - __clz(um));
+            done += (uint32_t)__popc(um);
+            wave_base += 32;
+        }
+    }
+    else
+    {
+        uint32_t avail    = 0;  // accepted, unused candidates of the current wave (bit = lane)
+        uint32_t cand     = 0;
+        uint64_t cur_base = 0;
+        for (int base = 0; base < n; base += 32)
+        {
+            const uint32_t w = row[base + lane];
+            uint32_t rm      = __ballot_sync(0xFFFFFFFFu, w >= max_multiple);
+            while (rm)
             {
-                uint64_t a[25];
-                seb_prng_init(a, s, wave_base + (uint64_t)lane);
-                seb_keccak_f1600<12>(a);  // 4 bytes per call
-                cand     = (uint32_t)a[0];
-                avail    = __ballot_sync(0xFFFFFFFFu, cand < max_multiple);
-                cur_base = wave_base;
-                wave_base += 32;
+                while (avail == 0)
+                {
+                    uint64_t a[25];
+                    seb_prng_init(a, s, wave_base + (uint64_t)lane);
+                    seb_keccak_f1600<12>(a);
+                    cand     = (uint32_t)a[0];
+                    avail    = __ballot_sync(0xFFFFFFFFu, cand < max_multiple);
+                    cur_base = wave_base;
+                    wave_base += 32;
+                }
+                const int rp     = __ffs(rm) - 1;
+                const int cl     = __ffs(avail) - 1;
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, cand, cl);
+                if (lane == rp) row[base + rp] = seb_barrett32(v, mod);
+                rm &= rm - 1;
+                avail &= avail - 1;
+                last_used = cur_base + (uint64_t)cl;
             }
-            const int rp     = __ffs(rm) - 1;
-            const int cl     = __ffs(avail) - 1;
-            const uint32_t v = __shfl_sync(0xFFFFFFFFu, cand, cl);
-            if (lane == rp) row[base + rp] = seb_barrett32(v, mod);
-            rm &= rm - 1;
-            avail &= avail - 1;
-            last_used = cur_base + (uint64_t)cl;
         }
     }
     if (lane == 0) ctr[b] = (uint32_t)(last_used + 1);
@@ -273,11 +323,16 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
 }
 
 void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
-                        const SebModulus &mod, int batch, cudaStream_t st)
+                        const SebModulus &mod, int batch, uint16_t *rej_idx, uint32_t *rej_cnt, uint32_t rej_cap,
+                        cudaStream_t st)
 {
     if (batch <= 0) return;
     // max_multiple = 0xFFFFFFFF - (0xFFFFFFFF mod q) - 1 (sample.c:45-46)
     const uint32_t max_multiple = 0xFFFFFFFFu - (0xFFFFFFFFu % mod.q) - 1u;
-    k_uniform_bulk<<<(batch + 127) / 128, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch);
-    k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch);
+    // one sequential sponge per thread: single-warp CTAs spread a small batch over all SM sub-partitions
+    // (131072-item config D leaves 16384 items = 512 warps per GPU for 592 sub-partitions)
+    k_uniform_bulk<<<(batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
+                                                     rej_idx, rej_cnt, rej_cap);
+    k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                   rej_cnt, rej_cap);
 }

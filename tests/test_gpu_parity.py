@@ -159,6 +159,46 @@ def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert ctr[b] == c
 
 
+@pytest.mark.parametrize("cap", ["0", "3", "70"])
+def test_sampler_uniform_list_overflow(cap, seb, torch_cuda, oracle_mod, orc, monkeypatch):
+    """The uniform sampler's reject lists have a fixed capacity; ciphertexts that overflow it take the
+    scanning fix-up.  Forced here with tiny capacities (none / most / some ciphertexts overflow at
+    n = 4096, where ~76 of 4096 words are rejected per prime) and through the full symmetric path."""
+    torch = torch_cuda
+    monkeypatch.setenv("SEB_UNIFORM_LIST_CAP", cap)
+    n, np_, batch = 4096, 3, 7
+    ctx = seb.Context(n, np_, False, device=0)
+    try:
+        seeds = oracle_mod.make_seeds(batch, b"uniform-cap")
+        d_seeds = dev(torch, seeds)
+        d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+        for p in range(np_):
+            ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+        torch.cuda.synchronize()
+        out = host(d_out, np.uint32).reshape(batch, np_, n)
+        ctr = host(d_ctr, np.uint32)
+        for b in range(batch):
+            c = 0
+            for p, q in enumerate(ctx.primes):
+                exp, c = orc.sample_uniform(n, q, seeds[b], c)
+                assert np.array_equal(out[b, p], exp), (cap, b, p)
+            assert ctr[b] == c
+        sk = oracle_mod.make_sk(n)
+        ctx.set_secret_key(sk)
+        vals = oracle_mod.make_values(batch, n // 2, seed=17)
+        eseeds = oracle_mod.make_seeds(batch, b"uniform-cap-e")
+        d_ct = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+        ctx.encrypt_sym_device(dev(torch, vals), n // 2, d_seeds, dev(torch, eseeds), batch, d_ct, False)
+        assert ctx.encode_failures() == 0
+        got = host(d_ct, np.uint32).reshape(batch, np_, 2, n)
+        for b in range(batch):
+            ok, exp = orc.encrypt_sym(n, np_, vals[b], seeds[b], eseeds[b], sk)
+            assert ok and np.array_equal(got[b], exp), (cap, b)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (8192, 6), (16384, 13)])
 def test_ntt(n, np_, seb, torch_cuda, orc, ctxs):
     """ntt.c:168-189 for every tabulated (n, q): random residues plus the delta and all-(q-1) edge
