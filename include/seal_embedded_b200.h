@@ -199,6 +199,14 @@ int seb_sample_uniform_device(seb_ctx *ctx, const uint8_t *d_seeds, uint32_t *d_
                               size_t batch, uint32_t *d_out, size_t ct_stride);
 /* ntt_inpl, in place: d_polys [batch][nprimes][n] (polynomial k uses prime k % nprimes) */
 int seb_ntt_device(seb_ctx *ctx, uint32_t *d_polys, size_t batch);
+/* ---- verifier (the receiving side, so whole batches can be round-tripped on the GPU) ---- */
+/* inverse of seb_ntt_device: intt (device/lib/intt.c:226-501), in place, canonical residues */
+int seb_intt_device(seb_ctx *ctx, uint32_t *d_polys, size_t batch);
+/* ckks_decrypt + intt + ckks_decode under prime prime_idx (device/test/ckks_tests_common.c:59-171):
+ * d_ct [batch][nprimes][2][n] -> d_values_out [batch][vlen] fp32.  Needs seb_set_secret_key (also on
+ * an asymmetric context).  Symmetric ciphertexts must carry c1 = a (ref_quirk off). */
+int seb_decrypt_decode_device(seb_ctx *ctx, const uint32_t *d_ct, size_t batch, size_t prime_idx, size_t vlen,
+                              float *d_values_out);
 /* first 136-byte block of SHAKE256(seed_i || LE64(counter_i)): d_out [count][17] u64 */
 int seb_prng_blocks_device(seb_ctx *ctx, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
                            uint64_t *d_out);

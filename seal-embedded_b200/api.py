@@ -87,6 +87,7 @@ EXPORTED_SYMBOLS = [
     "seb_encrypt_asym_device", "seb_encrypt_sym_device", "seb_encode_failures", "seb_encrypt_asym_host",
     "seb_encrypt_sym_host", "seb_encode_device", "seb_sample_asym_device", "seb_sample_cbd_device",
     "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
+    "seb_intt_device", "seb_decrypt_decode_device",
 ]
 
 
@@ -131,6 +132,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_sample_uniform_device.argtypes = [vp, vp, vp, sz, sz, vp, sz]
     L.seb_ntt_device.argtypes = [vp, vp, sz]
     L.seb_prng_blocks_device.argtypes = [vp, vp, vp, sz, vp]
+    L.seb_intt_device.argtypes = [vp, vp, sz]
+    L.seb_decrypt_decode_device.argtypes = [vp, vp, sz, sz, sz, vp]
     L.seb_profile_begin.argtypes = [vp, i32]
     L.seb_profile_end.argtypes = [vp, vp]
     L.se_setup_custom.argtypes = [sz, sz, vp, vp, C.c_double, i32]
@@ -286,6 +289,12 @@ class Context:
 
     def ntt_device(self, d_polys, batch: int) -> None:
         self._check(self.lib.seb_ntt_device(self.h, _addr(d_polys), batch))
+
+    def intt_device(self, d_polys, batch: int) -> None:
+        self._check(self.lib.seb_intt_device(self.h, _addr(d_polys), batch))
+
+    def decrypt_decode_device(self, d_ct, batch: int, prime_idx: int, vlen: int, d_values_out) -> None:
+        self._check(self.lib.seb_decrypt_decode_device(self.h, _addr(d_ct), batch, prime_idx, vlen, _addr(d_values_out)))
 
     def prng_blocks_device(self, d_seeds, d_counters, count: int, d_out) -> None:
         self._check(self.lib.seb_prng_blocks_device(self.h, _addr(d_seeds), _addr(d_counters), count, _addr(d_out)))

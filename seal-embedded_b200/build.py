@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + ARCH
 # per-file extras: the FP64 encode must never contract a*b+c into an FMA (bit-exactness)
 EXTRA = {"seb_encode.cu": ["-fmad=false"]}
-CU_SOURCES = ["seb_api.cu", "seb_sample.cu", "seb_encode.cu", "seb_encrypt.cu"]
+CU_SOURCES = ["seb_api.cu", "seb_sample.cu", "seb_encode.cu", "seb_encrypt.cu", "seb_verify.cu"]
 C_SOURCES = ["seal_embedded.c"]
 
 

@@ -162,6 +162,13 @@ struct seb_ctx
     uint16_t *d_src_map = nullptr;  // [n]
     seb_oct *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n/4] Shoup pairs, epilogue order
     seb_oct *d_ntt_s = nullptr;                  // [np][n/4] Shoup pairs, epilogue order
+    // verifier (seb_verify.cu)
+    uint32_t *d_ntt_s_nat = nullptr;  // [np][n] ntt(s), reference order
+    uint2 *d_iroots       = nullptr;  // [np][n] inverse roots, Shoup pairs
+    uint2 *d_ninv         = nullptr;  // [np] n^-1
+    uint16_t *d_index_map = nullptr;  // [n] ckks_calc_index_map
+    double2 *d_work       = nullptr;  // [verify_ctas][n] FFT scratch
+    int sms = 0, verify_ctas = 0;
     bool have_pk = false, have_sk = false;
     Scratch slot[2];
     size_t last_batch = 0;
@@ -262,6 +269,27 @@ static int build_tables(seb_ctx *c)
     CU(cudaMalloc(&c->d_roots, tabs.size() * sizeof(seb_oct)));
     CU(cudaMemcpy(c->d_roots, tabs.data(), tabs.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
 
+    // inverse roots for the verifier's INTT: iroots[bitrev(i)] = psi^-i, and n^-1
+    {
+        std::vector<uint2> inv(c->np * n), ninv(c->np);
+        for (size_t p = 0; p < c->np; p++)
+        {
+            const uint32_t q = c->primes[p], ipsi = powmod(c->psis[p], 2 * n - 1, q);
+            uint32_t pw      = 1;
+            for (size_t i = 0; i < n; i++)
+            {
+                inv[p * n + bitrev(i, c->logn)] = make_uint2(pw, shoup(pw, q));
+                pw                              = mulmod(pw, ipsi, q);
+            }
+            const uint32_t ni = powmod((uint32_t)(n % q), (uint64_t)q - 2, q);
+            ninv[p]           = make_uint2(ni, shoup(ni, q));
+        }
+        CU(cudaMalloc(&c->d_iroots, inv.size() * sizeof(uint2)));
+        CU(cudaMemcpy(c->d_iroots, inv.data(), inv.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_ninv, ninv.size() * sizeof(uint2)));
+        CU(cudaMemcpy(c->d_ninv, ninv.data(), ninv.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+
     // IFFT twiddles from the host libm, same expression as fft.c:27-45 (+ conj at fft.c:129)
     std::vector<double2> tw(n);
     const size_t m = 2 * n;
@@ -276,7 +304,7 @@ static int build_tables(seb_ctx *c)
     CU(cudaMemcpy(c->d_tw, tw.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
 
     // index map (ckks_common.c:32-68) inverted: position -> slot
-    std::vector<uint16_t> src(n);
+    std::vector<uint16_t> src(n), fwd(n);
     uint64_t pos = 1;
     for (size_t i = 0; i < n / 2; i++)
     {
@@ -284,10 +312,14 @@ static int build_tables(seb_ctx *c)
         const size_t b            = n - 1 - a;
         src[bitrev(a, c->logn)]   = (uint16_t)i;
         src[bitrev(b, c->logn)]   = (uint16_t)i;
+        fwd[i]                    = (uint16_t)bitrev(a, c->logn);
+        fwd[i + n / 2]            = (uint16_t)bitrev(b, c->logn);
         pos                       = (pos * 3) & (m - 1);
     }
     CU(cudaMalloc(&c->d_src_map, n * sizeof(uint16_t)));
     CU(cudaMemcpy(c->d_src_map, src.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_index_map, n * sizeof(uint16_t)));
+    CU(cudaMemcpy(c->d_index_map, fwd.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -358,6 +390,10 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     c->stream = c->own_stream;
     if ((e = seb_encode_configure(logn)) != cudaSuccess) return bail("encode kernel attributes", e);
     if ((e = seb_encrypt_configure(logn)) != cudaSuccess) return bail("encrypt kernel attributes", e);
+    if ((e = seb_verify_configure((int)n)) != cudaSuccess) return bail("verifier kernel attributes", e);
+    if ((e = cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device)) != cudaSuccess)
+        return bail("cudaDeviceGetAttribute", e);
+    c->verify_ctas = c->sms * (n <= 4096 ? 4 : n <= 8192 ? 2 : 1);
     if (build_tables(c) != 0)
     {
         seb_destroy(c);
@@ -378,6 +414,11 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaFree(c->d_pk0);
     cudaFree(c->d_pk1);
     cudaFree(c->d_ntt_s);
+    cudaFree(c->d_ntt_s_nat);
+    cudaFree(c->d_iroots);
+    cudaFree(c->d_ninv);
+    cudaFree(c->d_index_map);
+    cudaFree(c->d_work);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -453,6 +494,8 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "ntt(s): %s", cudaGetErrorString(e));
     int r = upload_shoup(c, s.data(), &c->d_ntt_s);
     if (r) return r;
+    if (!c->d_ntt_s_nat) CU(cudaMalloc(&c->d_ntt_s_nat, s.size() * sizeof(uint32_t)));
+    CU(cudaMemcpy(c->d_ntt_s_nat, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     c->have_sk = true;
     return 0;
 }
@@ -534,6 +577,30 @@ extern "C" int seb_ntt_device(seb_ctx *c, uint32_t *d_polys, size_t batch)
 {
     if (!c || !d_polys) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
     CU(seb_launch_ntt(c->logn, d_polys, c->d_roots, c->mods, (int)c->np, batch * c->np, c->stream));
+    c->launches++;
+    return 0;
+}
+
+extern "C" int seb_intt_device(seb_ctx *c, uint32_t *d_polys, size_t batch)
+{
+    if (!c || !d_polys) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(seb_launch_intt(d_polys, c->d_iroots, c->d_ninv, c->mods, (int)c->n, (int)c->np, batch * c->np, c->sms * 8,
+                       c->stream));
+    c->launches++;
+    return 0;
+}
+
+extern "C" int seb_decrypt_decode_device(seb_ctx *c, const uint32_t *d_ct, size_t batch, size_t prime_idx,
+                                         size_t vlen, float *d_values_out)
+{
+    if (!c || !d_ct || !d_values_out || prime_idx >= c->np) return fail(SE_ERR_INVALD_ARGUMENT, "bad argument");
+    if (!c->have_sk) return fail(SE_ERR_NO_KEY, "no secret key loaded");
+    int r = check_vlen(c, vlen);
+    if (r) return r;
+    if (!c->d_work) CU(cudaMalloc(&c->d_work, (size_t)c->verify_ctas * c->n * sizeof(double2)));
+    CU(seb_launch_decrypt_decode(d_ct, c->d_ntt_s_nat, c->d_iroots, c->d_ninv, c->d_tw, c->d_index_map, c->mods,
+                                 (int)c->n, (int)c->np, (int)prime_idx, c->scale, c->d_work, c->verify_ctas, (int)vlen,
+                                 d_values_out, batch, c->stream));
     c->launches++;
     return 0;
 }

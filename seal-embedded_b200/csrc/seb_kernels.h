@@ -54,3 +54,14 @@ cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *
                                    const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
                                    int batch, cudaStream_t st);
 cudaError_t seb_encrypt_configure(int logn);
+
+// ---- verifier: inverse NTT, decrypt + decode (seb_verify.cu) ----
+// iroots: per prime n Shoup pairs, iroots[i] = inverse of the forward table's root i; ninvs: n^-1 per prime
+cudaError_t seb_verify_configure(int n);
+cudaError_t seb_launch_intt(uint32_t *polys, const uint2 *iroots, const uint2 *ninvs, const SebModuli &mods, int n,
+                            int np, size_t npolys, int max_ctas, cudaStream_t st);
+// work: work_ctas slices of n double2
+cudaError_t seb_launch_decrypt_decode(const uint32_t *ct, const uint32_t *s_hat, const uint2 *iroots,
+                                      const uint2 *ninvs, const double2 *tw, const uint16_t *index_map,
+                                      const SebModuli &mods, int n, int np, int prime, double scale, double2 *work,
+                                      int work_ctas, int vlen, float *values_out, size_t batch, cudaStream_t st);

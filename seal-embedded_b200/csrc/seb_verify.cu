@@ -1,0 +1,152 @@
+// seb_verify.cu — the receiving side of the round trip, batched, so that parity and property tests can
+// check EVERY ciphertext of a full-size batch on the GPU instead of a handful on the host:
+//
+//   k_intt             : inverse negacyclic NTT (the inverse of ntt_inpl, device/lib/ntt.c:124-189;
+//                        the reference's own inverse is device/lib/intt.c:226-501), bit-reversed
+//                        order in, natural order out, scaled by n^-1, canonical residues
+//   k_decrypt_decode   : ckks_decrypt (device/test/ckks_tests_common.c:132-171): pt^ = c0 + c1 (.) s^,
+//                        then intt, then ckks_decode (ckks_tests_common.c:59-118: centred lift, /scale,
+//                        forward FFT fft_inpl device/lib/fft.c:146-213, gather through the index map)
+//
+// This is SURVEY.md 8(f) row 3 ("GPU INTT/decode verifier").  It is a verifier, not a hot path: one
+// CTA per polynomial, radix-2 stages with a barrier each, exact Barrett arithmetic, FP64 FFT in an
+// L2-resident global scratch slice per CTA.  Decoded values carry the reference's tolerance (0.1
+// against the message, device/test/ckks_tests_common.c:228), not bit-exactness.
+#include "seb_kernels.h"
+
+#define SEB_VERIFY_THREADS 256
+
+// x * w mod q, exact, for a Shoup pair (w, floor(w*2^32/q)) and x < 2^32
+__device__ __forceinline__ uint32_t mul_shoup(uint32_t x, uint2 w, uint32_t q)
+{
+    return seb_csub(seb_mul_shoup_lazy(x, w.x, w.y, q), q);
+}
+
+// In-place inverse transform of the n residues in `v` (shared memory) by the whole CTA.
+// iroots[h + j] = (psi^bitrev(h + j))^-1 as Shoup pairs, i.e. the inverses of the forward table
+// (device/lib/ntt.c:40-52) at the same indices; ninv = n^-1 mod q.
+__device__ __forceinline__ void intt_smem(uint32_t *v, const int n, const uint2 *__restrict__ iroots, const uint2 ninv,
+                                          const uint32_t q)
+{
+    // undo the forward stages last to first: (x, y) -> (x + y, (x - y) * w^-1)
+    for (int lt = 0, h = n >> 1; h >= 1; lt++, h >>= 1)
+    {
+        const int tt = 1 << lt;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x)
+        {
+            const int j     = i >> lt;
+            const int k     = (j << (lt + 1)) + (i - (j << lt));
+            const uint32_t x = v[k], y = v[k + tt];
+            v[k]            = seb_csub(x + y, q);
+            v[k + tt]       = mul_shoup(x + q - y, __ldg(iroots + h + j), q);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = mul_shoup(v[i], ninv, q);
+    __syncthreads();
+}
+
+// polys [batch][np][n], in place (polynomial k uses prime k % np): the inverse of k_ntt_forward
+__global__ void __launch_bounds__(SEB_VERIFY_THREADS)
+    k_intt(uint32_t *__restrict__ polys, const uint2 *__restrict__ iroots, const uint2 *__restrict__ ninvs,
+           const __grid_constant__ SebModuli mods, int n, int np, size_t npolys)
+{
+    extern __shared__ __align__(16) uint32_t vs[];
+    for (size_t poly = blockIdx.x; poly < npolys; poly += gridDim.x)
+    {
+        const int p     = (int)(poly % (size_t)np);
+        const uint32_t q = mods.m[p].q;
+        uint32_t *data  = polys + poly * (size_t)n;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) vs[i] = data[i];
+        intt_smem(vs, n, iroots + (size_t)p * n, __ldg(ninvs + p), q);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) data[i] = vs[i];
+    }
+}
+
+// ct [batch][np][2][n]; s_hat [np][n] = ntt(s) in the reference's (bit-reversed) order;
+// tw = the IFFT twiddle table (cos, -sin)(2 pi bitrev(i) / 2n): the forward FFT uses its conjugate;
+// index_map as ckks_calc_index_map (ckks_common.c:32-68); work: gridDim.x slices of n double2;
+// values_out [batch][vlen]
+__global__ void __launch_bounds__(SEB_VERIFY_THREADS)
+    k_decrypt_decode(const uint32_t *__restrict__ ct, const uint32_t *__restrict__ s_hat,
+                     const uint2 *__restrict__ iroots, const uint2 *__restrict__ ninvs,
+                     const double2 *__restrict__ tw, const uint16_t *__restrict__ index_map,
+                     const __grid_constant__ SebModuli mods, int n, int np, int prime, double scale,
+                     double2 *__restrict__ work, int vlen, float *__restrict__ values_out, size_t batch)
+{
+    extern __shared__ __align__(16) uint32_t vs[];
+    const SebModulus m = mods.m[prime];
+    const uint32_t q   = m.q;
+    double2 *x         = work + (size_t)blockIdx.x * n;
+    for (size_t b = blockIdx.x; b < batch; b += gridDim.x)
+    {
+        const uint32_t *c0 = ct + ((b * np + prime) * 2) * (size_t)n;
+        const uint32_t *c1 = c0 + n;
+        __syncthreads();
+        // ckks_decrypt: c0 + c1 (.) ntt(s)
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t prod = seb_barrett64((uint64_t)c1[i] * __ldg(s_hat + (size_t)prime * n + i), m);
+            vs[i]               = seb_csub(prod + c0[i], q);
+        }
+        intt_smem(vs, n, iroots + (size_t)prime * n, __ldg(ninvs + prime), q);
+        // ckks_decode: representative in (-q/2, q/2], divided by the scale
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t v = vs[i];
+            const double d   = (v > q / 2) ? -(double)(q - v) : (double)v;
+            x[i]             = make_double2(d / scale, 0.0);
+        }
+        // fft_inpl (fft.c:146-213): h groups of 2*tt, root e^{+i theta_(h+j)} applied to the upper half
+        for (int h = 1, lt = 31 - __clz(n >> 1); lt >= 0; h <<= 1, lt--)
+        {
+            const int tt = 1 << lt;
+            __syncthreads();
+            for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x)
+            {
+                const int j     = i >> lt;
+                const int k     = (j << (lt + 1)) + (i - (j << lt));
+                const double2 s = __ldg(tw + h + j);  // (cos, -sin)
+                const double2 u = x[k], a = x[k + tt];
+                const double vr = a.x * s.x + a.y * s.y;   // a * (cos + i sin)
+                const double vi = a.y * s.x - a.x * s.y;
+                x[k]            = make_double2(u.x + vr, u.y + vi);
+                x[k + tt]       = make_double2(u.x - vr, u.y - vi);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < vlen; i += blockDim.x)
+            values_out[b * (size_t)vlen + i] = (float)x[__ldg(index_map + i)].x;
+    }
+}
+
+cudaError_t seb_verify_configure(int n)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_intt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * n);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_decrypt_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * n);
+    return e;
+}
+
+cudaError_t seb_launch_intt(uint32_t *polys, const uint2 *iroots, const uint2 *ninvs, const SebModuli &mods, int n,
+                            int np, size_t npolys, int max_ctas, cudaStream_t st)
+{
+    if (npolys == 0) return cudaSuccess;
+    const size_t grid = npolys < (size_t)max_ctas ? npolys : (size_t)max_ctas;
+    k_intt<<<(unsigned)grid, SEB_VERIFY_THREADS, 4 * (size_t)n, st>>>(polys, iroots, ninvs, mods, n, np, npolys);
+    return cudaGetLastError();
+}
+
+cudaError_t seb_launch_decrypt_decode(const uint32_t *ct, const uint32_t *s_hat, const uint2 *iroots,
+                                      const uint2 *ninvs, const double2 *tw, const uint16_t *index_map,
+                                      const SebModuli &mods, int n, int np, int prime, double scale, double2 *work,
+                                      int work_ctas, int vlen, float *values_out, size_t batch, cudaStream_t st)
+{
+    if (batch == 0) return cudaSuccess;
+    const size_t grid = batch < (size_t)work_ctas ? batch : (size_t)work_ctas;
+    k_decrypt_decode<<<(unsigned)grid, SEB_VERIFY_THREADS, 4 * (size_t)n, st>>>(
+        ct, s_hat, iroots, ninvs, tw, index_map, mods, n, np, prime, scale, work, vlen, values_out, batch);
+    return cudaGetLastError();
+}

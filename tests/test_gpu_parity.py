@@ -223,6 +223,61 @@ def test_ntt(n, np_, seb, torch_cuda, orc, ctxs):
         assert np.all(got[1, p] == 1)  # NTT(delta_0) = all ones
 
 
+@pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (8192, 6), (16384, 13)])
+def test_intt(n, np_, seb, torch_cuda, orc, ctxs):
+    """Verifier INTT (inverse of ntt_inpl; reference: intt.c:226-501): equals the oracle's inverse and undoes
+    the forward kernel on every tabulated (n, q)."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, True)
+    rng = np.random.default_rng(n + 5)
+    batch = 3
+    x = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes]) for _ in range(batch)])
+    x[0, 0, :3] = (0, 1, ctx.primes[0] - 1)
+    d = dev(torch, x)
+    ctx.intt_device(d, batch)
+    torch.cuda.synchronize()
+    got = host(d, np.uint32).reshape(batch, np_, n)
+    for b in range(batch):
+        for p, q in enumerate(ctx.primes):
+            assert np.array_equal(got[b, p], orc.intt(n, q, x[b, p])), (n, b, p)
+    ctx.ntt_device(d, batch)  # ntt(intt(x)) = x
+    torch.cuda.synchronize()
+    assert np.array_equal(host(d, np.uint32).reshape(batch, np_, n), x)
+
+
+@pytest.mark.parametrize("n,np_,asym", [(1024, 1, False), (4096, 3, True), (4096, 3, False), (8192, 4, True),
+                                        (16384, 6, False)])
+def test_decrypt_decode(n, np_, asym, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """Verifier decrypt + decode (device/test/ckks_tests_common.c:59-171) against the oracle's, every prime,
+    ragged vlen; and the reference's acceptance criterion: decoded values within 0.1 of the message."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, asym)
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    ctx.set_secret_key(sk)
+    batch, vlen = 4, n // 2
+    vals = oracle_mod.make_values(batch, vlen, seed=31 * n)
+    seeds = oracle_mod.make_seeds(batch, b"dd-%d" % n)
+    sseeds = oracle_mod.make_seeds(batch, b"dd-share-%d" % n)
+    d_ct = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    if asym:
+        ctx.set_public_key(pk0, pk1)
+        ctx.encrypt_asym_device(dev(torch, vals), vlen, dev(torch, seeds), batch, d_ct)
+    else:
+        ctx.encrypt_sym_device(dev(torch, vals), vlen, dev(torch, sseeds), dev(torch, seeds), batch, d_ct, False)
+    assert ctx.encode_failures() == 0
+    ct = host(d_ct, np.uint32).reshape(batch, np_, 2, n)
+    for p in range(np_):
+        for vl in (vlen, 37):
+            d_dec = torch.full((batch, vl), 1e9, dtype=torch.float32, device="cuda")
+            ctx.decrypt_decode_device(d_ct, batch, p, vl, d_dec)
+            torch.cuda.synchronize()
+            dec = d_dec.cpu().numpy()
+            for b in range(batch):
+                exp = orc.decrypt_decode(n, np_, ct[b], sk, vl, prime_idx=p)
+                assert np.allclose(dec[b], exp, rtol=0, atol=1e-4), (n, p, b, np.abs(dec[b] - exp).max())
+            assert np.abs(dec - vals[:, :vl]).max() < 0.1
+
+
 @pytest.mark.parametrize("n,np_", CONFIGS)
 def test_encrypt_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """seal_embedded.c:98-215 asymmetric branch == ckks_asym.c:173-286, full ciphertext bit-exact."""
@@ -495,6 +550,13 @@ def test_full_size_properties(seb, torch_cuda, oracle_mod, orc, ctxs):
         assert ctx.encode_failures() == 0
         assert torch.equal(d_o2.view(hi - lo, -1).to(torch.int64).sum(dim=1), sums[lo:hi])
         assert torch.equal(d_o2.view(hi - lo, -1)[:, ::97].to(torch.int64).sum(dim=1), xors[lo:hi])
+    # (4') EVERY item of the batch round-trips on the GPU verifier: decrypt + decode within the
+    # reference's 0.1 (device/test/ckks_tests_common.c:228), under each prime
+    ctx.set_secret_key(sk)
+    d_dec = torch.empty((batch, vlen), dtype=torch.float32, device="cuda")
+    for p in range(np_):
+        ctx.decrypt_decode_device(d_out, batch, p, vlen, d_dec)
+        assert float((d_dec - d_vals).abs().max()) < 0.1, p
     # (2),(4) oracle on the ends
     vals = d_vals.cpu().numpy()
     seeds = d_seeds.cpu().numpy()
