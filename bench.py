@@ -219,10 +219,12 @@ def run_b200_arm(args) -> None:
 
     n, np_, batch, vlen = N_DEG, N_PRIMES, args.batch, N_DEG // 2
     ctx = seb.Context(n, np_, asym=True, device=local)
+    # a real key pair: random ternary secret key, public key generated on the GPU (seb_gen_public_key =
+    # the reference's gen_pk, ckks_asym.c:159-171), so the ciphertexts of the timed steps can be decrypted
     rng = np.random.default_rng(7)
-    pk0 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes])
-    pk1 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in ctx.primes])
-    ctx.set_public_key(pk0, pk1)
+    t = rng.integers(0, 3, (n // 4, 4), dtype=np.uint8)
+    sk = ((t[:, 0] << 6) | (t[:, 1] << 4) | (t[:, 2] << 2) | t[:, 3]).astype(np.uint8)
+    ctx.gen_public_key(sk)
     ctx.reserve(batch)
     # a real (non-default) stream shared with torch, so torch.cuda.Event times the kernels' own stream
     stream = torch.cuda.Stream()
@@ -265,6 +267,14 @@ def run_b200_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * batch * args.steps / (ms_max * 1e-3)
+
+    # ---- every ciphertext of the last timed step decrypts and decodes back to its message (GPU verifier,
+    # the reference's acceptance criterion: within 0.1, device/test/ckks_tests_common.c:228)
+    d_dec = torch.empty((batch, vlen), dtype=torch.float32, device="cuda")
+    ctx.decrypt_decode_device(d_out, batch, 0, vlen, d_dec)
+    torch.cuda.synchronize()
+    verify_err = float((d_dec - d_vals).abs().max())
+    del d_dec
 
     # ---- NTT-only micro-benchmark (config E shape: same n, primes; polys >> L2), rank-local
     polys = torch.randint(0, 1 << 30, (batch, np_, n), generator=gen, device="cuda", dtype=torch.int32)
@@ -381,6 +391,8 @@ def run_b200_arm(args) -> None:
                        "l2": f"inputs+outputs per step ({(d_vals.numel() * 4 + d_out.numel() * 4) >> 20} MiB) "
                              "exceed the 126 MB L2"},
             "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+            "verify": {"what": "decrypt+decode of every ciphertext of the last timed step on the GPU verifier",
+                       "items": batch, "max_abs_err": verify_err, "tolerance": 0.1, "ok": verify_err < 0.1},
             "kernels_ms": {nm: float(v) for nm, v in zip(names, avg)},
             "roofline": roofline, "ntt_microbench": ntt_micro, "cpu_baseline": cpu}
     emit(line)

@@ -147,6 +147,11 @@ int seb_set_stream(seb_ctx *ctx, void *cuda_stream);
 int seb_set_public_key(seb_ctx *ctx, const uint32_t *pk0, const uint32_t *pk1);
 /* sk: host n/4 bytes, 2 bits per coefficient (file sk_<n>.dat, fileops.c:140-170) */
 int seb_set_secret_key(seb_ctx *ctx, const uint8_t *sk_packed);
+/* gen_pk (ckks_asym.c:159-171) on the GPU: loads sk (as seb_set_secret_key), samples ep = CBD(PRNG(ep_seed))
+ * and, per prime p, a = uniform(PRNG(a_seed_base with byte 0 := p)); writes pk0 = -(a (.) ntt(s)) + ntt(ep)
+ * and pk1 = a to host [nprimes][n] and installs them when the context is asymmetric */
+int seb_gen_public_key(seb_ctx *ctx, const uint8_t *sk_packed, const uint8_t *ep_seed, const uint8_t *a_seed_base,
+                       uint32_t *pk0, uint32_t *pk1);
 /* pre-size the per-batch scratch (otherwise grown on demand) */
 int seb_reserve(seb_ctx *ctx, size_t batch);
 

@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "seb_encrypt_asym_device", "seb_encrypt_sym_device", "seb_encode_failures", "seb_encrypt_asym_host",
     "seb_encrypt_sym_host", "seb_encode_device", "seb_sample_asym_device", "seb_sample_cbd_device",
     "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
-    "seb_intt_device", "seb_decrypt_decode_device",
+    "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
 ]
 
 
@@ -132,6 +132,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_sample_uniform_device.argtypes = [vp, vp, vp, sz, sz, vp, sz]
     L.seb_ntt_device.argtypes = [vp, vp, sz]
     L.seb_prng_blocks_device.argtypes = [vp, vp, vp, sz, vp]
+    L.seb_gen_public_key.argtypes = [vp, vp, vp, vp, vp, vp]
     L.seb_intt_device.argtypes = [vp, vp, sz]
     L.seb_decrypt_decode_device.argtypes = [vp, vp, sz, sz, sz, vp]
     L.seb_profile_begin.argtypes = [vp, i32]
@@ -222,6 +223,19 @@ class Context:
         sk = np.ascontiguousarray(sk_packed, dtype=np.uint8)
         assert sk.size == self.n // 4
         self._check(self.lib.seb_set_secret_key(self.h, _addr(sk)))
+
+    def gen_public_key(self, sk_packed: np.ndarray, ep_seed=bytes([7]) * 64, a_seed_base=bytes([9]) * 64):
+        """gen_pk on the GPU (ckks_asym.c:159-171); returns (pk0, pk1) [nprimes][n] and installs them on an
+        asymmetric context.  Default seeds = the recipe of the test key material."""
+        sk = np.ascontiguousarray(sk_packed, dtype=np.uint8)
+        assert sk.size == self.n // 4
+        es = np.frombuffer(bytes(ep_seed), np.uint8).copy()
+        as_ = np.frombuffer(bytes(a_seed_base), np.uint8).copy()
+        assert es.size == SEED_BYTES and as_.size == SEED_BYTES
+        pk0 = np.empty((self.nprimes, self.n), np.uint32)
+        pk1 = np.empty((self.nprimes, self.n), np.uint32)
+        self._check(self.lib.seb_gen_public_key(self.h, _addr(sk), _addr(es), _addr(as_), _addr(pk0), _addr(pk1)))
+        return pk0, pk1
 
     def reserve(self, batch: int) -> None:
         self._check(self.lib.seb_reserve(self.h, batch))

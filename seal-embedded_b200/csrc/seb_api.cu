@@ -500,6 +500,84 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     return 0;
 }
 
+// gen_pk (device/lib/ckks_asym.c:159-171) for every prime: a symmetric encryption of zero whose error
+// polynomial ep is CBD(PRNG(ep_seed)) (shared by all primes) and whose `a` for prime p comes from a
+// fresh PRNG seeded with a_seed_base where byte 0 is replaced by p:
+//   pk0_p = -(a_p (.) ntt(s)) + ntt(ep),  pk1_p = a_p.
+// Built from the same kernels as the symmetric path (plaintext 0).  The key is returned to the host
+// and, on an asymmetric context, installed.
+extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const uint8_t *ep_seed,
+                                  const uint8_t *a_seed_base, uint32_t *pk0, uint32_t *pk1)
+{
+    if (!c || !sk_packed || !ep_seed || !a_seed_base || !pk0 || !pk1) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    int r = seb_set_secret_key(c, sk_packed);
+    if (r) return r;
+    const size_t n = c->n, np = c->np;
+    std::vector<uint8_t> seeds((np + 1) * SEB_SEED_BYTES);
+    memcpy(seeds.data(), ep_seed, SEB_SEED_BYTES);
+    for (size_t p = 0; p < np; p++)
+    {
+        memcpy(seeds.data() + (p + 1) * SEB_SEED_BYTES, a_seed_base, SEB_SEED_BYTES);
+        seeds[(p + 1) * SEB_SEED_BYTES] = (uint8_t)p;
+    }
+    uint8_t *d_seeds = nullptr, *d_e = nullptr;
+    int64_t *d_pt = nullptr;
+    uint32_t *d_small = nullptr, *d_out = nullptr;  // d_small: mag, ctr, rej_cnt
+    uint16_t *d_rej = nullptr;
+    const uint32_t cap = c->rej_cap ? c->rej_cap : 1;
+    cudaStream_t st = c->stream;
+    auto cleanup = [&]() {
+        cudaFree(d_seeds);
+        cudaFree(d_e);
+        cudaFree(d_pt);
+        cudaFree(d_small);
+        cudaFree(d_out);
+        cudaFree(d_rej);
+    };
+#define CUK(call)                                                                          \
+    do                                                                                     \
+    {                                                                                      \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+        {                                                                                  \
+            cleanup();                                                                     \
+            return fail(SE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+        }                                                                                  \
+    } while (0)
+    CUK(cudaMalloc(&d_seeds, seeds.size()));
+    CUK(cudaMalloc(&d_e, n));
+    CUK(cudaMalloc(&d_pt, n * sizeof(int64_t)));
+    CUK(cudaMalloc(&d_small, 3 * sizeof(uint32_t)));
+    CUK(cudaMalloc(&d_out, 2 * np * n * sizeof(uint32_t)));
+    CUK(cudaMalloc(&d_rej, cap * sizeof(uint16_t)));
+    CUK(cudaMemcpyAsync(d_seeds, seeds.data(), seeds.size(), cudaMemcpyHostToDevice, st));
+    CUK(cudaMemsetAsync(d_pt, 0, n * sizeof(int64_t), st));
+    CUK(cudaMemsetAsync(d_small, 0, 3 * sizeof(uint32_t), st));
+    seb_launch_sample_cbd(d_seeds, nullptr, reinterpret_cast<int8_t *>(d_e), (int)n, 1, 1, st);
+    for (size_t p = 0; p < np; p++)
+    {
+        CUK(cudaMemsetAsync(d_small + 1, 0, sizeof(uint32_t), st));  // a fresh PRNG per prime: counter 0
+        seb_launch_uniform(d_seeds + (p + 1) * SEB_SEED_BYTES, d_small + 1, d_out + (2 * p + 1) * n, 2 * np * n, (int)n,
+                           c->mods.m[p], 1, d_rej, d_small + 2, cap, st);
+    }
+    CUK(cudaGetLastError());
+    CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots, c->d_ntt_s, c->mods,
+                               (int)np, d_out, 0, 1, st));
+    c->launches += 2 + 2 * np;
+    std::vector<uint32_t> out(2 * np * n);
+    CUK(cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUK(cudaStreamSynchronize(st));
+#undef CUK
+    cleanup();
+    for (size_t p = 0; p < np; p++)
+    {
+        memcpy(pk0 + p * n, out.data() + (2 * p) * n, n * sizeof(uint32_t));
+        memcpy(pk1 + p * n, out.data() + (2 * p + 1) * n, n * sizeof(uint32_t));
+    }
+    if (c->asym) return seb_set_public_key(c, pk0, pk1);
+    return 0;
+}
+
 extern "C" int seb_reserve(seb_ctx *c, size_t batch)
 {
     if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");

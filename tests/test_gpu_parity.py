@@ -279,6 +279,20 @@ def test_decrypt_decode(n, np_, asym, seb, torch_cuda, oracle_mod, orc, ctxs):
 
 
 @pytest.mark.parametrize("n,np_", CONFIGS)
+def test_gen_public_key(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """gen_pk (ckks_asym.c:159-171) on the GPU equals the oracle's (which equals the reference's:
+    tests/test_oracle.py::test_gen_pk_matches_reference), on asymmetric and symmetric contexts."""
+    sk = oracle_mod.make_sk(n)
+    exp0, exp1 = orc.gen_pk(n, np_, sk)
+    for asym in (True, False):
+        pk0, pk1 = ctxs(n, np_, asym).gen_public_key(sk)
+        assert np.array_equal(pk0, exp0) and np.array_equal(pk1, exp1), (n, asym)
+    e0, e1 = orc.gen_pk(n, np_, sk, ep_seed=bytes(range(64)), seed_base=bytes(range(100, 164)))
+    g0, g1 = ctxs(n, np_, True).gen_public_key(sk, ep_seed=bytes(range(64)), a_seed_base=bytes(range(100, 164)))
+    assert np.array_equal(g0, e0) and np.array_equal(g1, e1)
+
+
+@pytest.mark.parametrize("n,np_", CONFIGS)
 def test_encrypt_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """seal_embedded.c:98-215 asymmetric branch == ckks_asym.c:173-286, full ciphertext bit-exact."""
     torch = torch_cuda
