@@ -124,6 +124,10 @@ bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seed
 /* Reproduce se_encrypt's symmetric byte stream exactly, where the c1 buffer handed to the send
  * callback holds ntt(m+e) (ckks_sym.c:86-88 aliasing).  Default 0: c1 = a. */
 void se_b200_set_reference_quirk(int on);
+/* se_encrypt(print = true) prints each component with the reference's print_poly: 8 values and "... }"
+ * as in the default SE_PRINT_SMALL build (0), or the whole polynomial as in a build without it (1) —
+ * the text format the adapter's ct_string_file_load parses (adapter/fileops.cpp:492-538). */
+void se_b200_set_print_full(int on);
 /* The context behind the static SE_PARMS (for the seb_* calls below); NULL before se_setup. */
 struct seb_ctx *se_b200_context(SE_PARMS *se_parms);
 

@@ -81,7 +81,7 @@ SEND_FNCT = C.CFUNCTYPE(C.c_size_t, C.c_void_p, C.c_size_t)
 # every symbol include/seal_embedded_b200.h declares
 EXPORTED_SYMBOLS = [
     "se_setup_custom", "se_setup", "se_setup_default", "se_encrypt_seeded", "se_encrypt", "se_cleanup",
-    "se_encrypt_batch_seeded", "se_b200_set_reference_quirk", "se_b200_context",
+    "se_encrypt_batch_seeded", "se_b200_set_reference_quirk", "se_b200_set_print_full", "se_b200_context",
     "seb_last_error", "seb_create", "seb_destroy", "seb_set_stream", "seb_set_public_key", "seb_set_secret_key",
     "seb_reserve", "seb_degree", "seb_nprimes", "seb_scale", "seb_prime", "seb_launch_count",
     "seb_encrypt_asym_device", "seb_encrypt_sym_device", "seb_encode_failures", "seb_encrypt_asym_host",
@@ -153,6 +153,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.se_encrypt_batch_seeded.restype = C.c_bool
     L.se_b200_set_reference_quirk.argtypes = [i32]
     L.se_b200_set_reference_quirk.restype = None
+    L.se_b200_set_print_full.argtypes = [i32]
+    L.se_b200_set_print_full.restype = None
     L.se_b200_context.argtypes = [C.POINTER(_SeParms)]
     L.se_b200_context.restype = vp
     if path is None:
@@ -375,6 +377,9 @@ class SealEmbedded:
 
     def set_reference_quirk(self, on: bool) -> None:
         self.lib.se_b200_set_reference_quirk(int(on))
+
+    def set_print_full(self, on: bool) -> None:
+        self.lib.se_b200_set_print_full(int(on))
 
     def se_cleanup(self) -> None:
         if self.se_parms is not None:

@@ -31,6 +31,7 @@ static SE_PARMS g_se_parms;
 static seb_ctx *g_ctx   = NULL;
 static uint32_t *g_ct   = NULL; /* [nprimes][2][n] host copy of the last ciphertext */
 static int g_ref_quirk  = 0;
+static int g_print_full = 0;
 static int g_pk_loaded  = 0;
 
 /* fileops.c:60-138 read_from_image + check_ret: a missing or short key file is fatal */
@@ -207,6 +208,24 @@ SE_PARMS *se_setup_default(EncryptType encrypt_type)
 
 void se_b200_set_reference_quirk(int on) { g_ref_quirk = on != 0; }
 
+void se_b200_set_print_full(int on) { g_print_full = on != 0; }
+
+/* print_poly (device/lib/util_print.h:478-489) in the reference's two build flavours: the default
+ * SE_PRINT_SMALL build prints PRINT_LEN_SMALL = 8 values and "... }" (defines.h:47-50); without it
+ * the whole polynomial is printed, which is the text the adapter's ct_string_file_load /
+ * poly_string_file_load parse (adapter/fileops.h:221-301, adapter/fileops.cpp:492-538). */
+static void print_poly_like_reference(const char *name, const ZZ *a, size_t len)
+{
+    size_t print_len = (!g_print_full && len > 8) ? 8 : len;
+    printf("%s : { ", name);
+    for (size_t i = 0; i < print_len; i++)
+    {
+        printf("%u", a[i]);
+        printf(i < len - 1 ? ", " : " "); /* print_comma, util_print.h:86-92 */
+    }
+    printf("%s", len == print_len ? "}\n" : "... }\n"); /* print_end_string, util_print.h:99-103 */
+}
+
 seb_ctx *se_b200_context(SE_PARMS *se_parms)
 {
     return (se_parms == &g_se_parms) ? g_ctx : NULL;
@@ -293,10 +312,10 @@ bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR net
         g_parms.curr_modulus     = &g_parms.moduli[i];
         g_ptrs.c0_ptr            = g_ct + (2 * i) * n;
         g_ptrs.c1_ptr            = g_ct + (2 * i + 1) * n;
-        if (print)
+        if (print) /* seal_embedded.c:161-165 */
         {
-            printf("c0: { %u, %u, ..., %u }\n", g_ptrs.c0_ptr[0], g_ptrs.c0_ptr[1], g_ptrs.c0_ptr[n - 1]);
-            printf("c1: { %u, %u, ..., %u }\n", g_ptrs.c1_ptr[0], g_ptrs.c1_ptr[1], g_ptrs.c1_ptr[n - 1]);
+            print_poly_like_reference("c0: ", g_ptrs.c0_ptr, n);
+            print_poly_like_reference("c1: ", g_ptrs.c1_ptr, n);
         }
         if (network_send_function)
         {

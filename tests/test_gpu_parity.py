@@ -445,7 +445,7 @@ def _send_collector(chunks):
 
 
 @pytest.mark.parametrize("asym", [False, True])
-def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeypatch):
+def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeypatch, capfd):
     """The reference's own API surface: se_setup reads adapter_output_data/, se_encrypt_seeded calls
     send(c0), send(c1) per prime with n*4 bytes each (seal_embedded.c:180-204); compared with the
     oracle and, when its .so is present, with the compiled reference run on the same files."""
@@ -485,6 +485,34 @@ def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeyp
                 ref.close()
                 os.chdir(tmp_path)
             assert okr and np.array_equal(got, ctr)
+        # print = true: the reference's print_poly text (seal_embedded.c:161-165, util_print.h:478-489).
+        # Default build flavour: 8 values then "... }"; full flavour: what the adapter's
+        # ct_string_file_load / poly_string_file_load parse (adapter/fileops.h:221-301).
+        capfd.readouterr()
+        assert se.se_encrypt_seeded(sseed, seed, None, vals, print_=True)
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+        lines = [ln for ln in capfd.readouterr().out.splitlines() if ln.startswith("c")]
+        assert len(lines) == 2 * np_
+        for p_ in range(np_):
+            for k, nm in enumerate(("c0: ", "c1: ")):
+                first8 = ", ".join(str(int(x)) for x in exp[p_, k, :8])
+                assert lines[2 * p_ + k] == f"{nm} : {{ {first8}, ... }}", lines[2 * p_ + k]
+        se.set_print_full(True)
+        assert se.se_encrypt_seeded(sseed, seed, None, vals, print_=True)
+        ctypes.CDLL(None).fflush(None)
+        text = capfd.readouterr().out
+        se.set_print_full(False)
+        parsed, pos = [], 0
+        while True:  # poly_string_file_load: find '{', read whitespace-separated tokens up to '}', strip commas
+            i = text.find("{", pos)
+            if i < 0:
+                break
+            j = text.find("}", i)
+            parsed.append([int(tok.replace(",", "")) for tok in text[i + 1:j].split()])
+            pos = j + 1
+        assert len(parsed) == 2 * np_ and all(len(v) == n for v in parsed)
+        assert np.array_equal(np.array(parsed, np.uint32).reshape(np_, 2, n), exp)
         # short input keeps earlier slots only (seal_embedded.c:108-111); NULL seeds draw randomness
         chunks2 = []
         assert se.se_encrypt(_send_collector(chunks2), vals[:16])
