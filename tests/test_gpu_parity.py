@@ -341,6 +341,47 @@ def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
             assert np.abs(dec - vals[0]).max() < 0.1
 
 
+def test_encrypt_asym_27bit_primes(seb, torch_cuda, oracle_mod, orc):
+    """The reference's SE_DEFAULT_4K_27BIT parameter set (parameters.c:204-209: n = 4096 with the three
+    27-bit primes, roots ntt.c:213-225) as a run-time option: explicit primes, tabulated roots.  The
+    expected ciphertext is composed from the oracle's stage functions (ckks_asym.c:205-286)."""
+    torch = torch_cuda
+    n, primes = 4096, [134012929, 134111233, 134176769]
+    np_ = len(primes)
+    ctx = seb.Context(n, np_, True, device=0, primes=primes, scale=2.0 ** 20)
+    try:
+        assert ctx.primes == primes
+        rng = np.random.default_rng(27)
+        pk0 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in primes])
+        pk1 = np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in primes])
+        ctx.set_public_key(pk0, pk1)
+        batch, vlen = 3, n // 2
+        vals = oracle_mod.make_values(batch, vlen, seed=27)
+        vals[2] *= np.float32(1.0e6)  # coefficients far above these small primes: 64-bit reduction path
+        seeds = oracle_mod.make_seeds(batch, b"27bit")
+        d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+        ctx.encrypt_asym_device(dev(torch, vals), vlen, dev(torch, seeds), batch, d_out)
+        assert ctx.encode_failures() == 0
+        got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+        for b in range(batch):
+            ok, pt = orc.encode(n, vals[b], scale=2.0 ** 20)
+            assert ok
+            u, ctr = orc.sample_ternary_small(n, seeds[b], 0)
+            e0, ctr = orc.sample_cbd(n, seeds[b], ctr)
+            e1, ctr = orc.sample_cbd(n, seeds[b], ctr)
+            pte = pt + e0.astype(np.int64)
+            for p, q in enumerate(primes):
+                uh = orc.ntt(n, q, orc.expand_ternary(n, q, u)).astype(np.uint64)
+                e1h = orc.ntt(n, q, orc.reduce_small(n, q, e1)).astype(np.uint64)
+                mh = orc.ntt(n, q, orc.reduce_pte(n, q, pte)).astype(np.uint64)
+                c0 = (pk0[p].astype(np.uint64) * uh + mh) % np.uint64(q)
+                c1 = (pk1[p].astype(np.uint64) * uh + e1h) % np.uint64(q)
+                assert np.array_equal(got[b, p, 0], c0.astype(np.uint32)), (b, p)
+                assert np.array_equal(got[b, p, 1], c1.astype(np.uint32)), (b, p)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("n,np_,asym", [(4096, 3, True), (1024, 1, False), (8192, 4, True)])
 def test_encrypt_large_magnitudes(n, np_, asym, seb, torch_cuda, oracle_mod, orc, ctxs):
     """reduce_set_pte (ckks_common.c:224-245) over the whole int64 range: messages from tiny to ~1e11 give
