@@ -36,6 +36,7 @@ static inline uint32_t __vcmpgeu4(uint32_t a, uint32_t b)
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 using std::min;
 #define SEB_CONSTANT static const
 #else

@@ -193,6 +193,30 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
     }
 }
 
+// Coefficient index of element j = 0 of group i of thread t in pass P (element j is at | (j << LS)).
+// The single definition of "which thread touches which coefficient in which pass": the passes use it
+// for addressing and tests/test_host_logic.py uses it to prove the barrier scopes below.
+template <int LOGN, int P>
+__host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group_base(uint32_t t, uint32_t i)
+{
+    constexpr int T  = (1 << LOGN) / SEB_E;
+    constexpr int R  = NttPlan<LOGN>::R[P];
+    constexpr int LS = LOGN - NttS0<LOGN, P>::value - R;
+    const uint32_t g = t + i * T;
+    return ((g >> LS) << (LS + R)) | (g & ((1u << LS) - 1u));
+}
+
+// Barrier scope between pass P and pass P+1.  Where every coefficient a thread reads in pass P+1 was
+// written in pass P by a thread of the same warp, __syncwarp() is enough and the CTA-wide barrier
+// (all n/16 threads waiting for the slowest warp) disappears: the last boundary of n = 1024, 4096,
+// 8192 and 16384 (checked exhaustively by tests/test_host_logic.py::test_ntt_barrier_scopes).
+template <int LOGN, int P>
+struct NttWarpSync
+{
+    static constexpr bool value = (LOGN == 10 && P == 1) || (LOGN == 12 && P == 1) || (LOGN == 13 && P == 2) ||
+                                  (LOGN == 14 && P == 2);
+};
+
 // One pass P of the plan.  FIRST: inputs come from load(p, pos); otherwise from smem.  LAST:
 // outputs stay in registers (x[p][i*2^R + j] = coefficient (g_i << R) + j, lazy [0,4q)) and the
 // caller finishes; otherwise they are written back to smem (same slots this thread read).
@@ -213,10 +237,8 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
 #pragma unroll
     for (int i = 0; i < GP; i++)
     {
-        const uint32_t g    = (uint32_t)t + (uint32_t)i * T;
-        const uint32_t off  = g & ((1u << LS) - 1u);
-        const uint32_t blk  = g >> LS;
-        const uint32_t base = (blk << (LS + R)) | off;
+        const uint32_t blk  = ((uint32_t)t + (uint32_t)i * T) >> LS;
+        const uint32_t base = seb_ntt_group_base<LOGN, P>((uint32_t)t, (uint32_t)i);
         uint32_t *sp        = smem + seb_pad<LOGN>(base);  // element j lives at sp[seb_pad(j << LS)]
         if (P == 0)
         {
@@ -270,7 +292,10 @@ struct SebNttRun
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
         if (P + 1 < NttPlan<LOGN>::NPASS)
         {
-            __syncthreads();
+            if (NttWarpSync<LOGN, P>::value)
+                __syncwarp();
+            else
+                __syncthreads();
             SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
                                                                                               load);
         }

@@ -140,6 +140,38 @@ extern "C" int emul_plan(int logn, int *radices)
     return 0;
 }
 
+// coefficient index of element j of group i of thread t in pass P; -1 outside the plan
+extern "C" int64_t emul_ntt_elem(int logn, int pass, uint32_t t, uint32_t i, uint32_t j)
+{
+#define CASEP(L, P)                                                                                   \
+    if (logn == L && pass == P)                                                                       \
+    {                                                                                                 \
+        if (P >= NttPlan<L>::NPASS) return -1;                                                        \
+        constexpr int PP = P < NttPlan<L>::NPASS ? P : 0;                                             \
+        constexpr int R  = NttPlan<L>::R[PP];                                                         \
+        constexpr int LS = L - NttS0<L, PP>::value - R;                                               \
+        if (i >= (uint32_t)(SEB_E >> R) || j >= (1u << R)) return -1;                                 \
+        return (int64_t)(seb_ntt_group_base<L, PP>(t, i) | (j << LS));                                \
+    }
+#define CASEL(L) CASEP(L, 0) CASEP(L, 1) CASEP(L, 2) CASEP(L, 3)
+    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14)
+#undef CASEL
+#undef CASEP
+    return -1;
+}
+
+// 1 when the boundary after pass `pass` is synchronised per warp only
+extern "C" int emul_ntt_warp_sync(int logn, int pass)
+{
+#define CASEP(L, P) \
+    if (logn == L && pass == P) return NttWarpSync<L, P>::value ? 1 : 0;
+#define CASEL(L) CASEP(L, 0) CASEP(L, 1) CASEP(L, 2) CASEP(L, 3)
+    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14)
+#undef CASEL
+#undef CASEP
+    return 0;
+}
+
 extern "C" uint32_t emul_barrett64(uint64_t x, uint32_t q)
 {
     const uint64_t ratio = (uint64_t)(((unsigned __int128)1 << 64) / q);

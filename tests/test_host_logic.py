@@ -28,6 +28,9 @@ def E(emul):
     emul.emul_smem_words.argtypes = [C.c_int]
     emul.emul_smem_words.restype = C.c_uint32
     emul.emul_plan.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    emul.emul_ntt_elem.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    emul.emul_ntt_elem.restype = C.c_int64
+    emul.emul_ntt_warp_sync.argtypes = [C.c_int, C.c_int]
     emul.emul_barrett64.argtypes = [C.c_uint64, C.c_uint32]
     emul.emul_barrett64.restype = C.c_uint32
     emul.emul_barrett32.argtypes = [C.c_uint32, C.c_uint32]
@@ -121,6 +124,35 @@ def test_smem_layout_conflict_free(logn, E):
                             banks = pad[base | (j << LS)] % 32
                             assert len(set(banks.tolist())) == 32, (logn, pi, i, j, w0)
         s0 += R
+
+
+@pytest.mark.parametrize("logn", LOGNS)
+def test_ntt_barrier_scopes(logn, E):
+    """Each pass covers every coefficient exactly once, and wherever the kernels replace the CTA barrier
+    between two passes by __syncwarp() (NttWarpSync), every coefficient a thread reads in the later pass
+    was written in the earlier one by a thread of the same warp."""
+    n = 1 << logn
+    T = n // 16
+    plan = _plan(E, logn)
+    owner = []
+    for p, R in enumerate(plan):
+        own = np.full(n, -1, np.int64)
+        for t in range(T):
+            for i in range(16 >> R):
+                for j in range(1 << R):
+                    e = E.emul_ntt_elem(logn, p, t, i, j)
+                    assert 0 <= e < n and own[e] == -1
+                    own[e] = t
+        assert (own >= 0).all()
+        owner.append(own)
+    relaxed = 0
+    for p in range(len(plan) - 1):
+        local = bool(((owner[p] >> 5) == (owner[p + 1] >> 5)).all())
+        if E.emul_ntt_warp_sync(logn, p):
+            assert local, (logn, p)
+            relaxed += 1
+    assert relaxed == (0 if logn == 11 else 1)
+    assert not E.emul_ntt_warp_sync(logn, len(plan) - 1)
 
 
 @pytest.mark.parametrize("logn", LOGNS)
