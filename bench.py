@@ -212,11 +212,12 @@ def run_b200_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    seb = importlib.import_module("seal-embedded_b200")
+    # before any pinned allocation: run next to this rank's GPU (matters for e2e at N > 1)
+    numa = seb.bind_to_gpu_numa(local) if world > 1 else "not bound (single rank)"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    seb = importlib.import_module("seal-embedded_b200")
-
     n, np_, batch, vlen = N_DEG, N_PRIMES, args.batch, N_DEG // 2
     ctx = seb.Context(n, np_, asym=True, device=local)
     # a real key pair: random ternary secret key, public key generated on the GPU (seb_gen_public_key =
@@ -324,7 +325,7 @@ def run_b200_arm(args) -> None:
         e2e = {"value": world * eb / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "batch_per_gpu": eb, "h2d_bytes_per_step": eb * (vlen * 4 + 64),
                "d2h_bytes_per_step": eb * (np_ * 2 * n * 4 + 4), "matches_device_path": same,
-               "api": "seb_encrypt_asym_host (pinned host buffers, 2 chunks in flight)"}
+               "api": "seb_encrypt_asym_host (pinned host buffers, 2 chunks in flight)", "cpu_binding": numa}
 
     if rank != 0:
         if world > 1:

@@ -17,4 +17,4 @@ from .api import (  # noqa: F401
     build_library,
     load_library,
 )
-from .shard import Shard, all_gather_ciphertexts, owner_of, shard_range  # noqa: F401
+from .shard import Shard, all_gather_ciphertexts, bind_to_gpu_numa, owner_of, shard_range  # noqa: F401

@@ -870,7 +870,9 @@ static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym)
 static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, const uint8_t *sseeds,
                         const uint8_t *seeds, size_t batch, uint32_t *out, int quirk)
 {
-    if (!c || !values || !seeds || !out || (sym && !sseeds)) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
+    if (batch == 0) return 0;
+    if (!values || !seeds || !out || (sym && !sseeds)) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
     if (sym ? !c->have_sk : !c->have_pk) return fail(SE_ERR_NO_KEY, "key material not loaded");
     int r = check_vlen(c, vlen);
     if (r) return r;

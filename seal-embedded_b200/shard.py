@@ -77,6 +77,30 @@ def all_gather_ciphertexts(local, batch: int, group=None):
     return torch.cat([pieces[r][: shard_range(batch, r, world).count] for r in range(world)], dim=0)
 
 
+def bind_to_gpu_numa(gpu_index: int) -> str:
+    """Pin the calling process to the CPUs next to GPU `gpu_index` (NVML's ideal CPU affinity), so that the
+    pinned staging buffers it allocates afterwards are first-touched on that GPU's NUMA node and the
+    host<->device copies of eight ranks do not all cross one socket.  Returns a description; a no-op (with
+    the reason) when NVML or the affinity call is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "no usable CPUs in the GPU's affinity mask"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs ({min(cpus)}-{max(cpus)})"
+    except Exception as e:  # noqa: BLE001 - best effort
+        return f"unavailable: {type(e).__name__}"
+
+
 def encrypt_asym_sharded(ctx, values, seeds, batch: int, rank: int, world: int, out=None):
     """Encrypt this rank's shard of a global batch held in host numpy arrays `values` [batch][vlen] and
     `seeds` [batch][64] through the host-pointer C ABI.  Returns (Shard, ciphertexts of the shard)."""

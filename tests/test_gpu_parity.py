@@ -455,6 +455,47 @@ def test_encrypt_reduction_path_boundary(n, np_, seb, torch_cuda, oracle_mod, or
     assert below >= 3 and above >= 3
 
 
+def test_edge_cases_and_errors(seb, torch_cuda, oracle_mod, orc):
+    """Empty batch, empty message (vlen = 0 encrypts the zero message), and the error behaviour of the
+    seb_* layer: missing key material, vlen beyond n/2, key coefficients outside [0, q)."""
+    torch = torch_cuda
+    n, np_ = 1024, 1
+    ctx = seb.Context(n, np_, True, device=0)
+    try:
+        d_vals = torch.zeros((4, n // 2), dtype=torch.float32, device="cuda")
+        d_seeds = dev(torch, oracle_mod.make_seeds(4, b"edge"))
+        d_out = torch.full((4, np_, 2, n), -1, dtype=torch.int32, device="cuda")
+        with pytest.raises(seb.SebError, match="no public key"):
+            ctx.encrypt_asym_device(d_vals, n // 2, d_seeds, 4, d_out)
+        sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+        bad = pk0.copy()
+        bad[0, 5] = ctx.primes[0]
+        with pytest.raises(seb.SebError, match="modulus"):
+            ctx.set_public_key(bad, pk1)
+        ctx.set_public_key(pk0, pk1)
+        with pytest.raises(seb.SebError, match="exceeds"):
+            ctx.encrypt_asym_device(d_vals, n // 2 + 1, d_seeds, 4, d_out)
+        with pytest.raises(seb.SebError, match="no secret key"):
+            ctx.decrypt_decode_device(d_out, 4, 0, n // 2, d_vals)
+        ctx.encrypt_asym_device(d_vals, n // 2, d_seeds, 0, d_out)  # empty batch: nothing is written
+        torch.cuda.synchronize()
+        assert ctx.encode_failures() == 0 and int((d_out != -1).sum()) == 0
+        ctx.encrypt_asym_device(d_vals, 0, d_seeds, 4, d_out)  # vlen = 0: the zero message
+        assert ctx.encode_failures() == 0
+        got = host(d_out, np.uint32).reshape(4, np_, 2, n)
+        seeds = host(d_seeds, np.uint8).reshape(4, 64)
+        for b in range(4):
+            ok, exp = orc.encrypt_asym(n, np_, np.zeros(0, np.float32), seeds[b], pk0, pk1)
+            assert ok and np.array_equal(got[b], exp)
+        assert ctx.encrypt_asym_host(np.zeros((0, 7), np.float32), np.zeros((0, 64), np.uint8)).shape == (0, np_, 2, n)
+    finally:
+        ctx.close()
+    with pytest.raises(seb.SebError):
+        seb.Context(4096, 4, True, device=0)  # parameters.c:204-213: n = 4096 takes at most 3 primes
+    with pytest.raises(seb.SebError):
+        seb.Context(4096, 1, True, device=0, primes=[1053818881], psis=[12345])  # not a primitive 2n-th root
+
+
 def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs):
     """Host-pointer batch API: pageable and pinned buffers, more items than one chunk, ragged vlen."""
     torch = torch_cuda
