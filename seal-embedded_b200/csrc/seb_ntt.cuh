@@ -193,29 +193,71 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
     }
 }
 
+// Group index of slot i of thread t in pass P: the single definition of "which thread touches which
+// coefficient in which pass".  Group g of a pass of radix R and stride 2^LS covers the coefficients
+// ((g >> LS) << (LS + R)) | (g & (2^LS - 1)) | (j << LS), j < 2^R.  The default assignment is
+// g = t + i*T.  For n = 16384 the last two passes (radix 8, two groups per thread) use
+// g = (t/64)*128 + i*64 + t%64 instead, so that the 1024 contiguous coefficients a 64-thread group
+// produced in pass 1 are the ones it consumes in pass 2 (and each warp keeps its own 512 in pass 3):
+// lanes of a warp still own consecutive groups, so the shared-memory access pattern is unchanged.
+template <int LOGN, int P>
+__host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group(uint32_t t, uint32_t i)
+{
+    constexpr int T = (1 << LOGN) / SEB_E;
+    if (LOGN == 14 && P >= 2) return ((t >> 6) << 7) | (i << 6) | (t & 63u);
+    return t + i * T;
+}
+
 // Coefficient index of element j = 0 of group i of thread t in pass P (element j is at | (j << LS)).
-// The single definition of "which thread touches which coefficient in which pass": the passes use it
-// for addressing and tests/test_host_logic.py uses it to prove the barrier scopes below.
+// The passes use it for addressing and tests/test_host_logic.py uses it to prove the barrier scopes below.
 template <int LOGN, int P>
 __host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group_base(uint32_t t, uint32_t i)
 {
-    constexpr int T  = (1 << LOGN) / SEB_E;
     constexpr int R  = NttPlan<LOGN>::R[P];
     constexpr int LS = LOGN - NttS0<LOGN, P>::value - R;
-    const uint32_t g = t + i * T;
+    const uint32_t g = seb_ntt_group<LOGN, P>(t, i);
     return ((g >> LS) << (LS + R)) | (g & ((1u << LS) - 1u));
 }
 
-// Barrier scope between pass P and pass P+1.  Where every coefficient a thread reads in pass P+1 was
-// written in pass P by a thread of the same warp, __syncwarp() is enough and the CTA-wide barrier
-// (all n/16 threads waiting for the slowest warp) disappears: the last boundary of n = 1024, 4096,
-// 8192 and 16384 (checked exhaustively by tests/test_host_logic.py::test_ntt_barrier_scopes).
+// Barrier scope between pass P and pass P+1.  A CTA-wide barrier makes all n/16 threads wait for the
+// slowest warp; wherever every coefficient a thread reads in pass P+1 was written in pass P by a
+// thread of a smaller unit, only that unit synchronises:
+//   SEB_SYNC_WARP   : same warp -> __syncwarp()            (last boundary of n = 1024, 4096, 8192, 16384)
+//   SEB_SYNC_GROUP64: same aligned group of 64 threads -> named barrier `bar.sync t/64, 64`
+//                     (boundary 1 -> 2 of n = 8192 and 16384; at most 16 groups = the 16 hardware barriers.
+//                     Barrier 0 doubles as the __syncthreads() barrier: the two uses never overlap in time
+//                     because every thread has left the preceding CTA-wide barrier before any thread can
+//                     arrive here, and no CTA-wide barrier follows inside the transform)
+//   SEB_SYNC_CTA    : __syncthreads()
+// Checked exhaustively by tests/test_host_logic.py::test_ntt_barrier_scopes.
+#define SEB_SYNC_CTA 0
+#define SEB_SYNC_GROUP64 1
+#define SEB_SYNC_WARP 2
 template <int LOGN, int P>
-struct NttWarpSync
+struct NttSync
 {
-    static constexpr bool value = (LOGN == 10 && P == 1) || (LOGN == 12 && P == 1) || (LOGN == 13 && P == 2) ||
-                                  (LOGN == 14 && P == 2);
+    static constexpr int value = ((LOGN == 10 && P == 1) || (LOGN == 12 && P == 1) || (LOGN == 13 && P == 2) ||
+                                  (LOGN == 14 && P == 2))
+                                     ? SEB_SYNC_WARP
+                                     : ((LOGN == 13 && P == 1) || (LOGN == 14 && P == 1)) ? SEB_SYNC_GROUP64 : SEB_SYNC_CTA;
 };
+
+template <int SCOPE>
+__device__ __forceinline__ void seb_ntt_sync(const int t)
+{
+    if (SCOPE == SEB_SYNC_WARP)
+        __syncwarp();
+    else if (SCOPE == SEB_SYNC_GROUP64)
+    {
+#if defined(SEB_UBENCH_CTA_BARRIERS)  // tools/ubench A/B switch only
+        __syncthreads();
+#elif defined(__CUDACC__)
+        asm volatile("bar.sync %0, 64;" ::"r"(t >> 6) : "memory");
+#endif
+    }
+    else
+        __syncthreads();
+}
 
 // One pass P of the plan.  FIRST: inputs come from load(p, pos); otherwise from smem.  LAST:
 // outputs stay in registers (x[p][i*2^R + j] = coefficient (g_i << R) + j, lazy [0,4q)) and the
@@ -225,8 +267,6 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                              Loader &load)
 {
-    constexpr int N     = 1 << LOGN;
-    constexpr int T     = N / SEB_E;
     constexpr int R     = NttPlan<LOGN>::R[P];
     constexpr int S0    = NttS0<LOGN, P>::value;
     constexpr int LS    = LOGN - S0 - R;  // log2 stride
@@ -237,7 +277,7 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
 #pragma unroll
     for (int i = 0; i < GP; i++)
     {
-        const uint32_t blk  = ((uint32_t)t + (uint32_t)i * T) >> LS;
+        const uint32_t blk  = seb_ntt_group<LOGN, P>((uint32_t)t, (uint32_t)i) >> LS;
         const uint32_t base = seb_ntt_group_base<LOGN, P>((uint32_t)t, (uint32_t)i);
         uint32_t *sp        = smem + seb_pad<LOGN>(base);  // element j lives at sp[seb_pad(j << LS)]
         if (P == 0)
@@ -292,10 +332,7 @@ struct SebNttRun
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
         if (P + 1 < NttPlan<LOGN>::NPASS)
         {
-            if (NttWarpSync<LOGN, P>::value)
-                __syncwarp();
-            else
-                __syncthreads();
+            seb_ntt_sync<NttSync<LOGN, P>::value>(t);
             SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
                                                                                               load);
         }
@@ -349,7 +386,7 @@ struct NttOut
     static constexpr int T   = (1 << LOGN) / SEB_E;
     __host__ __device__ __forceinline__ static constexpr uint32_t pos(int t, int i)
     {
-        return ((uint32_t)t + (uint32_t)i * T) << RL;
+        return seb_ntt_group<LOGN, NttPlan<LOGN>::NPASS - 1>((uint32_t)t, (uint32_t)i) << RL;
     }
 };
 
@@ -370,7 +407,7 @@ inline void seb_build_epi(const uint2 *natural, seb_oct *out)
             for (int k = 0; k < O::RUN / 4; k++)
                 for (int c = 0; c < 4; c++)
                 {
-                    const uint2 w = natural[(((uint32_t)t + (uint32_t)i * O::T) << O::RL) + 4 * k + c];
+                    const uint2 w = natural[O::pos(t, i) + 4 * k + c];
                     seb_oct &o    = out[seb_epi_index<LOGN>(t, i, k)];
                     o.v[2 * c]     = w.x;
                     o.v[2 * c + 1] = w.y;

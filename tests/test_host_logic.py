@@ -30,7 +30,7 @@ def E(emul):
     emul.emul_plan.argtypes = [C.c_int, C.POINTER(C.c_int)]
     emul.emul_ntt_elem.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     emul.emul_ntt_elem.restype = C.c_int64
-    emul.emul_ntt_warp_sync.argtypes = [C.c_int, C.c_int]
+    emul.emul_ntt_sync_scope.argtypes = [C.c_int, C.c_int]
     emul.emul_barrett64.argtypes = [C.c_uint64, C.c_uint32]
     emul.emul_barrett64.restype = C.c_uint32
     emul.emul_barrett32.argtypes = [C.c_uint32, C.c_uint32]
@@ -108,9 +108,8 @@ def test_smem_layout_conflict_free(logn, E):
         if pi > 0 or not last:
             for i in range(GP):
                 for w0 in range(0, T, 32):
-                    g = np.arange(w0, w0 + 32) + i * T
-                    off, blk = g & ((1 << LS) - 1), g >> LS
-                    base = (blk << (LS + R)) | off
+                    # element 0 of slot i of the warp's 32 threads, from the kernels' own mapping
+                    base = np.array([E.emul_ntt_elem(logn, pi, t, i, 0) for t in range(w0, w0 + 32)], dtype=np.int64)
                     if last and pi > 0:
                         # 128-bit reads: 8 lanes per phase, each 4 consecutive words
                         for k in range((1 << R) // 4):
@@ -129,8 +128,9 @@ def test_smem_layout_conflict_free(logn, E):
 @pytest.mark.parametrize("logn", LOGNS)
 def test_ntt_barrier_scopes(logn, E):
     """Each pass covers every coefficient exactly once, and wherever the kernels replace the CTA barrier
-    between two passes by __syncwarp() (NttWarpSync), every coefficient a thread reads in the later pass
-    was written in the earlier one by a thread of the same warp."""
+    between two passes by a narrower one (NttSync: __syncwarp() or a 64-thread named barrier), every
+    coefficient a thread reads in the later pass was written in the earlier one by a thread of the same
+    warp / the same aligned 64-thread group."""
     n = 1 << logn
     T = n // 16
     plan = _plan(E, logn)
@@ -145,14 +145,18 @@ def test_ntt_barrier_scopes(logn, E):
                     own[e] = t
         assert (own >= 0).all()
         owner.append(own)
-    relaxed = 0
+    scopes = []
     for p in range(len(plan) - 1):
-        local = bool(((owner[p] >> 5) == (owner[p + 1] >> 5)).all())
-        if E.emul_ntt_warp_sync(logn, p):
-            assert local, (logn, p)
-            relaxed += 1
-    assert relaxed == (0 if logn == 11 else 1)
-    assert not E.emul_ntt_warp_sync(logn, len(plan) - 1)
+        scope = E.emul_ntt_sync_scope(logn, p)
+        shift = {0: None, 1: 6, 2: 5}[scope]
+        if shift is not None:
+            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (logn, p, scope)
+            if scope == 1:
+                assert T % 64 == 0 and T // 64 <= 16  # one hardware barrier per group
+        scopes.append(scope)
+    expect = {10: [0, 2], 11: [0, 0], 12: [0, 2], 13: [0, 1, 2], 14: [0, 1, 2]}[logn]
+    assert scopes == expect
+    assert E.emul_ntt_sync_scope(logn, len(plan) - 1) == 0
 
 
 @pytest.mark.parametrize("logn", LOGNS)
