@@ -128,6 +128,15 @@ void se_b200_set_reference_quirk(int on);
  * as in the default SE_PRINT_SMALL build (0), or the whole polynomial as in a build without it (1) —
  * the text format the adapter's ct_string_file_load parses (adapter/fileops.cpp:492-538). */
 void se_b200_set_print_full(int on);
+/* Seed-compressed symmetric ciphertexts (the reference's unfinished SE_ENABLE_SYM_SEED_CT,
+ * seal_embedded.c:184-194): with the switch on, symmetric se_encrypt* calls send, per prime, the 64-byte
+ * shareable seed and then c0 (n words) instead of (c0, c1); c1 = a is a function of the seed alone
+ * (sample.c:39-57) and the receiver rebuilds it (seb_expand_seedct_device).  Default 0. */
+void se_b200_set_sym_seed_ct(int on);
+/* Batch form: c0_out [batch][nprimes][n] words, half the bytes of se_encrypt_batch_seeded's output.
+ * shareable_seeds [batch][64] are required (they are the other half of each ciphertext); seeds may be NULL. */
+bool se_encrypt_batch_seedct(const uint8_t *shareable_seeds, const uint8_t *seeds, const flpt *v, size_t vlen,
+                             size_t batch, ZZ *c0_out, SE_PARMS *se_parms);
 /* The context behind the static SE_PARMS (for the seb_* calls below); NULL before se_setup. */
 struct seb_ctx *se_b200_context(SE_PARMS *se_parms);
 
@@ -174,6 +183,15 @@ int seb_encrypt_asym_device(seb_ctx *ctx, const float *d_values, size_t vlen, co
 int seb_encrypt_sym_device(seb_ctx *ctx, const float *d_values, size_t vlen,
                            const uint8_t *d_shareable_seeds, const uint8_t *d_seeds, size_t batch,
                            uint32_t *d_out, int ref_quirk);
+/* Seed-compressed symmetric form: d_c0_out [batch][nprimes][n] receives c0 only (a stays in scratch). */
+int seb_encrypt_sym_seedct_device(seb_ctx *ctx, const float *d_values, size_t vlen,
+                                  const uint8_t *d_shareable_seeds, const uint8_t *d_seeds, size_t batch,
+                                  uint32_t *d_c0_out);
+/* Receiver side: d_out [batch][nprimes][2][n] gets c0 from d_c0 [batch][nprimes][n] (NULL: c0 slots left
+ * untouched) and c1 = a regenerated from the shareable seeds, bit-identical to what the full-size
+ * call would have produced. */
+int seb_expand_seedct_device(seb_ctx *ctx, const uint8_t *d_shareable_seeds, const uint32_t *d_c0, size_t batch,
+                             uint32_t *d_out);
 /* synchronises the stream; returns how many items of the last *_device call failed to encode
  * (>= 0) or a negative error */
 int seb_encode_failures(seb_ctx *ctx);
@@ -191,6 +209,10 @@ int seb_encrypt_asym_host(seb_ctx *ctx, const float *values, size_t vlen, const 
 int seb_encrypt_sym_host(seb_ctx *ctx, const float *values, size_t vlen,
                          const uint8_t *shareable_seeds, const uint8_t *seeds, size_t batch,
                          uint32_t *out, int ref_quirk);
+
+int seb_encrypt_sym_seedct_host(seb_ctx *ctx, const float *values, size_t vlen,
+                                const uint8_t *shareable_seeds, const uint8_t *seeds, size_t batch,
+                                uint32_t *c0_out);
 
 /* ---- stage level (device pointers, asynchronous) ---- */
 /* ckks_encode_base: d_pt [batch][n] int64 */

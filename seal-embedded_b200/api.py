@@ -88,6 +88,8 @@ EXPORTED_SYMBOLS = [
     "seb_encrypt_sym_host", "seb_encode_device", "seb_sample_asym_device", "seb_sample_cbd_device",
     "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
     "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
+    "seb_encrypt_sym_seedct_device", "seb_encrypt_sym_seedct_host", "seb_expand_seedct_device",
+    "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct",
 ]
 
 
@@ -126,6 +128,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_encode_failures.argtypes = [vp]
     L.seb_encrypt_asym_host.argtypes = [vp, vp, sz, vp, sz, vp]
     L.seb_encrypt_sym_host.argtypes = [vp, vp, sz, vp, vp, sz, vp, i32]
+    L.seb_encrypt_sym_seedct_device.argtypes = [vp, vp, sz, vp, vp, sz, vp]
+    L.seb_encrypt_sym_seedct_host.argtypes = [vp, vp, sz, vp, vp, sz, vp]
+    L.seb_expand_seedct_device.argtypes = [vp, vp, vp, sz, vp]
     L.seb_encode_device.argtypes = [vp, vp, sz, sz, vp]
     L.seb_sample_asym_device.argtypes = [vp, vp, sz, vp, vp, vp]
     L.seb_sample_cbd_device.argtypes = [vp, vp, vp, sz, sz, vp]
@@ -155,6 +160,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.se_b200_set_reference_quirk.restype = None
     L.se_b200_set_print_full.argtypes = [i32]
     L.se_b200_set_print_full.restype = None
+    L.se_b200_set_sym_seed_ct.argtypes = [i32]
+    L.se_b200_set_sym_seed_ct.restype = None
+    L.se_encrypt_batch_seedct.argtypes = [vp, vp, vp, sz, sz, vp, C.POINTER(_SeParms)]
+    L.se_encrypt_batch_seedct.restype = C.c_bool
     L.se_b200_context.argtypes = [C.POINTER(_SeParms)]
     L.se_b200_context.restype = vp
     if path is None:
@@ -275,6 +284,23 @@ class Context:
                                                   batch, _addr(out), int(ref_quirk)))
         return out
 
+    # -- seed-compressed symmetric ciphertexts: c0 only; c1 = a is rebuilt from the shareable seed
+    def encrypt_sym_seedct_device(self, d_values, vlen: int, d_share_seeds, d_seeds, batch: int, d_c0_out) -> None:
+        self._check(self.lib.seb_encrypt_sym_seedct_device(self.h, _addr(d_values), vlen, _addr(d_share_seeds),
+                                                           _addr(d_seeds), batch, _addr(d_c0_out)))
+
+    def encrypt_sym_seedct_host(self, values: np.ndarray, share_seeds: np.ndarray, seeds: np.ndarray,
+                                out: np.ndarray | None = None) -> np.ndarray:
+        batch, vlen = values.shape
+        if out is None:
+            out = np.empty((batch, self.nprimes, self.n), np.uint32)
+        self._check(self.lib.seb_encrypt_sym_seedct_host(self.h, _addr(values), vlen, _addr(share_seeds), _addr(seeds),
+                                                         batch, _addr(out)))
+        return out
+
+    def expand_seedct_device(self, d_share_seeds, d_c0, batch: int, d_out) -> None:
+        self._check(self.lib.seb_expand_seedct_device(self.h, _addr(d_share_seeds), _addr(d_c0), batch, _addr(d_out)))
+
     PROFILE_SEGMENTS = {True: ("encode", "sample_ternary", "sample_cbd", "encrypt"),
                         False: ("encode", "sample_cbd", "sample_uniform", "encrypt")}
 
@@ -380,6 +406,19 @@ class SealEmbedded:
 
     def set_print_full(self, on: bool) -> None:
         self.lib.se_b200_set_print_full(int(on))
+
+    def set_sym_seed_ct(self, on: bool) -> None:
+        self.lib.se_b200_set_sym_seed_ct(int(on))
+
+    def se_encrypt_batch_seedct(self, shareable_seeds, seeds, v: np.ndarray, out: np.ndarray | None = None):
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        batch, vlen = v.shape
+        p = self.parms
+        if out is None:
+            out = np.empty((batch, p.nprimes, p.coeff_count), np.uint32)
+        ok = self.lib.se_encrypt_batch_seedct(_addr(shareable_seeds), _addr(seeds), _addr(v), vlen, batch, _addr(out),
+                                              self.se_parms)
+        return bool(ok), out
 
     def se_cleanup(self) -> None:
         if self.se_parms is not None:

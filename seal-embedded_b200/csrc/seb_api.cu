@@ -131,8 +131,11 @@ struct Scratch  // per in-flight chunk
     uint32_t *mag    = nullptr;  // max |plaintext coefficient| per item, clipped to 32 bits
     uint16_t *rej_idx = nullptr;  // [cap][n/8] uniform sampler: indices of rejected words (symmetric mode)
     uint32_t *rej_cnt = nullptr;  // [cap]
+    uint32_t *a_buf   = nullptr;  // [a_cap][np][n] `a` of the seed-compressed symmetric path (allocated on first use)
+    size_t a_cap      = 0;
     // host-API staging
     size_t io_cap    = 0;
+    size_t io_out_words = 0;  // words of d_out / h_out per ciphertext
     float *d_values  = nullptr;
     uint8_t *d_seeds = nullptr, *d_sseeds = nullptr;
     uint32_t *d_out  = nullptr;
@@ -232,6 +235,7 @@ static void free_scratch(Scratch &s)
     cudaFree(s.mag);
     cudaFree(s.rej_idx);
     cudaFree(s.rej_cnt);
+    cudaFree(s.a_buf);
     cudaFree(s.d_values);
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
@@ -562,7 +566,7 @@ extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const ui
     }
     CUK(cudaGetLastError());
     CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots, c->d_ntt_s, c->mods,
-                               (int)np, d_out, 0, 1, st));
+                               (int)np, d_out + n, d_out, 2 * np * n, 2 * n, 0, 1, st));
     c->launches += 2 + 2 * np;
     std::vector<uint32_t> out(2 * np * n);
     CUK(cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -721,10 +725,25 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 
 // seal_embedded.c:98-215 (symmetric branch): encode, e, then per prime sample a (the shareable
 // PRNG's counter runs on across primes, ckks_sym.c:219), then the fused c0 kernel.
+// seedct: the seed-compressed form (SE_ENABLE_SYM_SEED_CT, seal_embedded.c:184-194) — `a` goes to
+// scratch instead of the c1 slots and d_out receives c0 only, [batch][np][n]; the receiver regenerates a
+// from the 64-byte shareable seed (seb_expand_seedct_device).
 static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
-                          const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk, cudaStream_t st)
+                          const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk, bool seedct,
+                          cudaStream_t st)
 {
     const int n = (int)c->n;
+    if (seedct && s.a_cap < batch)
+    {
+        cudaFree(s.a_buf);
+        s.a_buf = nullptr;
+        s.a_cap = 0;
+        CU(cudaMalloc(&s.a_buf, batch * c->np * c->n * sizeof(uint32_t)));
+        s.a_cap = batch;
+    }
+    uint32_t *a_base       = seedct ? s.a_buf : d_out + c->n;
+    const size_t ct_stride = (seedct ? 1 : 2) * c->np * c->n;
+    const size_t p_stride  = (seedct ? 1 : 2) * c->n;
     prof_mark(c, st, 0);
     int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, s.mag, st);
     if (r) return r;
@@ -732,14 +751,13 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
     prof_mark(c, st, 2);
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
-    const size_t ct_stride = 2 * c->np * c->n;
     for (size_t p = 0; p < c->np; p++)
-        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * c->n, ct_stride, n, c->mods.m[p], (int)batch,
+        seb_launch_uniform(d_sseeds, s.ctr_a, a_base + p * p_stride, ct_stride, n, c->mods.m[p], (int)batch,
                            s.rej_idx, s.rej_cnt, c->rej_cap, st);
     CU(cudaGetLastError());
     prof_mark(c, st, 3);
-    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, d_out, quirk,
-                              (int)batch, st));
+    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
+                              ct_stride, p_stride, seedct ? 0 : quirk, (int)batch, st));
     prof_mark(c, st, 4);
     prof_next(c, st);
     c->launches += 2 + 2 * c->np;
@@ -758,16 +776,55 @@ extern "C" int seb_encrypt_asym_device(seb_ctx *c, const float *d_values, size_t
     return encrypt_asym_on(c, c->slot[0], d_values, vlen, d_seeds, batch, d_out, c->stream);
 }
 
-extern "C" int seb_encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
-                                      const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk)
+static int encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
+                              const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk, bool seedct)
 {
     if (!c || !d_values || !d_seeds || !d_sseeds || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "symmetric encryption on an asymmetric context");
     if (!c->have_sk) return fail(SE_ERR_NO_KEY, "no secret key loaded");
     int r = check_vlen(c, vlen);
     if (r) return r;
     if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
     c->last_batch = batch;
-    return encrypt_sym_on(c, c->slot[0], d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, c->stream);
+    return encrypt_sym_on(c, c->slot[0], d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, seedct, c->stream);
+}
+
+extern "C" int seb_encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
+                                      const uint8_t *d_seeds, size_t batch, uint32_t *d_out, int quirk)
+{
+    return encrypt_sym_device(c, d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, false);
+}
+
+extern "C" int seb_encrypt_sym_seedct_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
+                                             const uint8_t *d_seeds, size_t batch, uint32_t *d_c0_out)
+{
+    return encrypt_sym_device(c, d_values, vlen, d_sseeds, d_seeds, batch, d_c0_out, 0, true);
+}
+
+// Receiver side of the seed-compressed form: out[b][p][0] = c0[b][p], out[b][p][1] = a regenerated from the
+// shareable seed exactly as the sender sampled it (sample.c:39-57, counter running on across primes).
+// d_c0 == NULL leaves the c0 slots of d_out untouched.
+extern "C" int seb_expand_seedct_device(seb_ctx *c, const uint8_t *d_sseeds, const uint32_t *d_c0, size_t batch,
+                                        uint32_t *d_out)
+{
+    if (!c || !d_sseeds || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "seed-compressed ciphertexts are symmetric");
+    if (batch == 0) return 0;
+    int r;
+    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    Scratch &s      = c->slot[0];
+    cudaStream_t st = c->stream;
+    const size_t n  = c->n;
+    if (d_c0)
+        CU(cudaMemcpy2DAsync(d_out, 2 * n * sizeof(uint32_t), d_c0, n * sizeof(uint32_t), n * sizeof(uint32_t),
+                             batch * c->np, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
+    for (size_t p = 0; p < c->np; p++)
+        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * n, 2 * c->np * n, (int)n, c->mods.m[p], (int)batch,
+                           s.rej_idx, s.rej_cnt, c->rej_cap, st);
+    CU(cudaGetLastError());
+    c->launches += 2 * c->np;
+    return 0;
 }
 
 // Per-kernel timing of the next `max_steps` full-path *_device calls: CUDA events are recorded on
@@ -838,11 +895,11 @@ static size_t host_chunk(const seb_ctx *c)
     return chunk < 16 ? 16 : chunk;
 }
 
-static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym)
+static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym, size_t per_ct)
 {
     if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    if (chunk <= s.io_cap && (!sym || s.d_sseeds)) return 0;
+    if (chunk <= s.io_cap && per_ct <= s.io_out_words && (!sym || s.d_sseeds)) return 0;
     cudaFree(s.d_values);
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
@@ -853,7 +910,7 @@ static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym)
     cudaFreeHost(s.h_out);
     cudaFreeHost(s.h_fail);
     s.io_cap            = 0;
-    const size_t out_b  = chunk * 2 * c->np * c->n * sizeof(uint32_t);
+    const size_t out_b  = chunk * per_ct * sizeof(uint32_t);
     CU(cudaMalloc(&s.d_values, chunk * (c->n / 2) * sizeof(float)));
     CU(cudaMalloc(&s.d_seeds, chunk * SEB_SEED_BYTES));
     CU(cudaMalloc(&s.d_sseeds, chunk * SEB_SEED_BYTES));
@@ -863,28 +920,30 @@ static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym)
     CU(cudaMallocHost(&s.h_sseeds, chunk * SEB_SEED_BYTES));
     CU(cudaMallocHost(&s.h_out, out_b));
     CU(cudaMallocHost(&s.h_fail, chunk * sizeof(int)));
-    s.io_cap = chunk;
+    s.io_cap       = chunk;
+    s.io_out_words = per_ct;
     return 0;
 }
 
 static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, const uint8_t *sseeds,
-                        const uint8_t *seeds, size_t batch, uint32_t *out, int quirk)
+                        const uint8_t *seeds, size_t batch, uint32_t *out, int quirk, bool seedct = false)
 {
     if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
     if (batch == 0) return 0;
     if (!values || !seeds || !out || (sym && !sseeds)) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (sym == c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "encryption type does not match the context");
     if (sym ? !c->have_sk : !c->have_pk) return fail(SE_ERR_NO_KEY, "key material not loaded");
     int r = check_vlen(c, vlen);
     if (r) return r;
     CU(cudaSetDevice(c->device));
     const size_t chunk  = host_chunk(c) < batch ? host_chunk(c) : batch;
-    const size_t per_ct = 2 * c->np * c->n;
+    const size_t per_ct = (seedct ? 1 : 2) * c->np * c->n;  // words of output per ciphertext
     const bool pin_in   = is_pinned(values) && is_pinned(seeds) && (!sym || is_pinned(sseeds));
     const bool pin_out  = is_pinned(out);
     for (auto &s : c->slot)
     {
         if ((r = ensure_scratch(c, s, chunk))) return r;
-        if ((r = ensure_io(c, s, chunk, sym))) return r;
+        if ((r = ensure_io(c, s, chunk, sym, per_ct))) return r;
     }
     struct Pending
     {
@@ -924,7 +983,7 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
         CU(cudaMemcpyAsync(s.d_values, hv, count * vlen * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(s.d_seeds, hs, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
         if (sym) CU(cudaMemcpyAsync(s.d_sseeds, hss, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
-        r = sym ? encrypt_sym_on(c, s, s.d_values, vlen, s.d_sseeds, s.d_seeds, count, s.d_out, quirk, s.stream)
+        r = sym ? encrypt_sym_on(c, s, s.d_values, vlen, s.d_sseeds, s.d_seeds, count, s.d_out, quirk, seedct, s.stream)
                 : encrypt_asym_on(c, s, s.d_values, vlen, s.d_seeds, count, s.d_out, s.stream);
         if (r) return r;
         uint32_t *ho = pin_out ? out + first * per_ct : s.h_out;
@@ -951,4 +1010,11 @@ extern "C" int seb_encrypt_sym_host(seb_ctx *c, const float *values, size_t vlen
                                     const uint8_t *seeds, size_t batch, uint32_t *out, int quirk)
 {
     return encrypt_host(c, true, values, vlen, sseeds, seeds, batch, out, quirk);
+}
+
+extern "C" int seb_encrypt_sym_seedct_host(seb_ctx *c, const float *values, size_t vlen, const uint8_t *sseeds,
+                                           const uint8_t *seeds, size_t batch, uint32_t *c0_out)
+{
+    if (c && c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "seed-compressed ciphertexts are symmetric");
+    return encrypt_host(c, true, values, vlen, sseeds, seeds, batch, c0_out, 0, true);
 }

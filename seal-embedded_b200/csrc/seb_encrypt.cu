@@ -232,12 +232,15 @@ struct LoadSym
     }
 };
 
+// a / c0 are addressed as base + b*ct_stride + p*p_stride (words): the full layout has a in the c1 slot
+// of the output (a = out + n, c0 = out, strides 2*np*n and 2n); the seed-compressed layout keeps a in
+// scratch and writes c0 only ([batch][np][n], strides np*n and n).
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
     k_encrypt_sym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
                   const seb_oct *__restrict__ roots,
-                  const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, int np,
-                  uint32_t *__restrict__ out, int quirk, size_t batch)
+                  const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, uint32_t *a_base,
+                  uint32_t *c0_base, size_t ct_stride, size_t p_stride, int quirk, size_t batch)
 {
     constexpr int N = 1 << LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
     seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
 
     using O           = NttOut<LOGN>;
-    uint32_t *c0      = out + (b * np + p) * 2 * (size_t)N;
-    uint32_t *c1      = c0 + N;
+    uint32_t *c0      = c0_base + b * ct_stride + (size_t)p * p_stride;
+    uint32_t *c1      = a_base + b * ct_stride + (size_t)p * p_stride;
     const seb_oct *sk = ntt_s + (size_t)p * (N / 4);
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
@@ -395,13 +398,13 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t 
 }
 
 cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
-                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
-                                   int batch, cudaStream_t st)
+                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *a, uint32_t *c0,
+                                   size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
-#define RUN(L)                                                                                              \
-    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(pt, mag, e, roots, ntt_s, mods, \
-                                                                                      np, out, quirk, (size_t)batch)
+#define RUN(L)                                                                                                       \
+    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(                 \
+        pt, mag, e, roots, ntt_s, mods, a, c0, ct_stride, p_stride, quirk, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();

@@ -48,11 +48,13 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, cons
 cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const uint8_t *u,
                                     const seb_oct *roots, const seb_oct *pk0s, const seb_oct *pk1s,
                                     const SebModuli &mods, int np, uint32_t *out, int batch, cudaStream_t st);
-// sym: out[b][p][1] already holds a; out[b][p][0] = -(a (.) ntt(s)) + ntt(m+e);
-// quirk != 0 additionally overwrites out[b][p][1] with ntt(m+e) (reference byte stream)
+// sym: a (already sampled) and c0 live at base + b*ct_stride + p*p_stride words; c0 = -(a (.) ntt(s)) + ntt(m+e).
+// Full layout: a = out + n, c0 = out, ct_stride = 2*np*n, p_stride = 2n.  Seed-compressed layout
+// (SURVEY 8f-2): a in scratch, c0 = the [batch][np][n] output, ct_stride = np*n, p_stride = n.
+// quirk != 0 additionally overwrites a's slot with ntt(m+e) (reference byte stream)
 cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
-                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *out, int quirk,
-                                   int batch, cudaStream_t st);
+                                   const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *a, uint32_t *c0,
+                                   size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st);
 cudaError_t seb_encrypt_configure(int logn);
 
 // ---- verifier: inverse NTT, decrypt + decode (seb_verify.cu) ----

@@ -32,6 +32,7 @@ static seb_ctx *g_ctx   = NULL;
 static uint32_t *g_ct   = NULL; /* [nprimes][2][n] host copy of the last ciphertext */
 static int g_ref_quirk  = 0;
 static int g_print_full = 0;
+static int g_sym_seed_ct = 0; /* se_encrypt sends (seed, c0) per prime in symmetric mode */
 static int g_pk_loaded  = 0;
 
 /* fileops.c:60-138 read_from_image + check_ret: a missing or short key file is fatal */
@@ -210,6 +211,8 @@ void se_b200_set_reference_quirk(int on) { g_ref_quirk = on != 0; }
 
 void se_b200_set_print_full(int on) { g_print_full = on != 0; }
 
+void se_b200_set_sym_seed_ct(int on) { g_sym_seed_ct = on != 0; }
+
 /* print_poly (device/lib/util_print.h:478-489) in the reference's two build flavours: the default
  * SE_PRINT_SMALL build prints PRINT_LEN_SMALL = 8 values and "... }" (defines.h:47-50); without it
  * the whole polynomial is printed, which is the text the adapter's ct_string_file_load /
@@ -288,11 +291,47 @@ bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seed
     return true;
 }
 
+/* Seed-compressed symmetric batch: c0 only, [batch][nprimes][n] words; the receiver rebuilds c1 = a from
+ * shareable_seeds (seb_expand_seedct_device).  The shareable seeds are the caller's because they ARE
+ * the second half of each ciphertext. */
+bool se_encrypt_batch_seedct(const uint8_t *shareable_seeds, const uint8_t *seeds, const flpt *v, size_t vlen,
+                             size_t batch, ZZ *c0_out, SE_PARMS *se_parms)
+{
+    if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v || !c0_out || !shareable_seeds) return false;
+    if (g_parms.is_asymmetric) return false;
+    if (batch == 0) return true;
+    if (vlen > g_parms.coeff_count / 2) vlen = g_parms.coeff_count / 2;
+    uint8_t *sd = malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
+    if (!sd)
+    {
+        printf("Error! Allocation failed. Exiting...\n");
+        exit(1);
+    }
+    fill_seeds(sd, seeds, batch);
+    int rc = seb_encrypt_sym_seedct_host(g_ctx, v, vlen, shareable_seeds, sd, batch, c0_out);
+    free(sd);
+    if (rc == SE_ERR_ENCODE_RANGE)
+    {
+        printf("Error! Value is possibly too large.\n"); /* ckks_common.c:197 */
+        return false;
+    }
+    die_on(rc, "se_encrypt");
+    return true;
+}
+
 bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR network_send_function, void *v,
                        size_t vlen_bytes, bool print, SE_PARMS *se_parms)
 {
     if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v) return false;
     size_t n = g_parms.coeff_count, np = g_parms.nprimes;
+    /* seed-compressed mode needs the shareable seed in hand: draw it here when the caller gave none */
+    uint8_t own_sseed[SE_PRNG_SEED_BYTE_COUNT];
+    const bool seed_ct = g_sym_seed_ct && !g_parms.is_asymmetric;
+    if (seed_ct && !shareable_seed)
+    {
+        fill_seeds(own_sseed, NULL, 1);
+        shareable_seed = own_sseed;
+    }
 
     /* seal_embedded.c:108-111: at most n/2 values are taken; slots past the input keep what the
      * previous call staged there (zero after setup), as in the reference */
@@ -320,6 +359,17 @@ bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR net
         if (network_send_function)
         {
             size_t nbytes_send = n * sizeof(ZZ);
+            if (seed_ct)
+            {
+                /* the reference's unfinished SE_ENABLE_SYM_SEED_CT (seal_embedded.c:184-194) sends the
+                 * 64-byte shareable seed in place of one component; here the pair is (seed, c0), which
+                 * is what a receiver needs to rebuild (c0, c1 = a) */
+                size_t nb = network_send_function(shareable_seed, SE_PRNG_SEED_BYTE_COUNT);
+                if (nb != SE_PRNG_SEED_BYTE_COUNT) return false;
+                nb = network_send_function(g_ptrs.c0_ptr, nbytes_send);
+                if (nb != nbytes_send) return false;
+                continue;
+            }
             size_t nbytes_recv = network_send_function(g_ptrs.c0_ptr, nbytes_send);
             if (nbytes_recv != nbytes_send) return false;
             nbytes_recv = network_send_function(g_ptrs.c1_ptr, nbytes_send);

@@ -341,6 +341,54 @@ def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
             assert np.abs(dec - vals[0]).max() < 0.1
 
 
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_encrypt_sym_seed_compressed(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """SURVEY 8f-2 (the reference's unfinished SE_ENABLE_SYM_SEED_CT, seal_embedded.c:184-194): the
+    seed-compressed call emits c0 only, bit-identical to the full ciphertext's c0; expanding the shareable
+    seeds on the receiving side rebuilds c1 = a (sample.c:39-57) bit-identically; the expanded ciphertext
+    decrypts.  Device and host flavours, odd batch so the host path's last chunk is ragged."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    sk = oracle_mod.make_sk(n)
+    ctx.set_secret_key(sk)
+    batch = 5
+    vlen = n // 2
+    vals = oracle_mod.make_values(batch, vlen, seed=n + 7)
+    seeds = oracle_mod.make_seeds(batch, b"seedct-%d" % n)
+    sseeds = oracle_mod.make_seeds(batch, b"seedct-share-%d" % n)
+    exp = np.stack([orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)[1] for b in range(batch)])
+    d_c0 = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+    d_ss = dev(torch, sseeds)
+    ctx.encrypt_sym_seedct_device(dev(torch, vals), vlen, d_ss, dev(torch, seeds), batch, d_c0)
+    assert ctx.encode_failures() == 0
+    c0 = host(d_c0, np.uint32).reshape(batch, np_, n)
+    assert np.array_equal(c0, exp[:, :, 0, :])
+    d_full = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+    ctx.expand_seedct_device(d_ss, d_c0, batch, d_full)
+    torch.cuda.synchronize()
+    full = host(d_full, np.uint32).reshape(batch, np_, 2, n)
+    assert np.array_equal(full, exp)
+    dec = orc.decrypt_decode(n, np_, full[batch - 1], sk, vlen)
+    assert np.abs(dec - vals[batch - 1]).max() < 0.1
+    # c0 == NULL: only the c1 slots are written
+    d_full.fill_(-1)
+    ctx.expand_seedct_device(d_ss, None, batch, d_full)
+    torch.cuda.synchronize()
+    part = host(d_full, np.uint32).reshape(batch, np_, 2, n)
+    assert np.array_equal(part[:, :, 1, :], exp[:, :, 1, :]) and (part[:, :, 0, :] == 0xFFFFFFFF).all()
+    # host flavour (half the device-to-host bytes of encrypt_sym_host), then the full-size call again:
+    # the staging buffers are shared between the two output sizes
+    c0h = ctx.encrypt_sym_seedct_host(vals, sseeds, seeds)
+    assert np.array_equal(c0h, exp[:, :, 0, :])
+    assert np.array_equal(ctx.encrypt_sym_host(vals, sseeds, seeds), exp)
+    # an asymmetric context refuses
+    actx = ctxs(n, np_, True)
+    with pytest.raises(seb.api.SebError):
+        actx.encrypt_sym_seedct_device(dev(torch, vals), vlen, d_ss, dev(torch, seeds), batch, d_c0)
+    with pytest.raises(seb.api.SebError):
+        actx.expand_seedct_device(d_ss, d_c0, batch, d_full)
+
+
 def test_encrypt_asym_27bit_primes(seb, torch_cuda, oracle_mod, orc):
     """The reference's SE_DEFAULT_4K_27BIT parameter set (parameters.c:204-209: n = 4096 with the three
     27-bit primes, roots ntt.c:213-225) as a run-time option: explicit primes, tabulated roots.  The
@@ -613,6 +661,36 @@ def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeyp
             else:
                 _, exp = orc.encrypt_sym(n, np_, bvals[b], bshare[b], bseeds[b], sk)
             assert np.array_equal(out[b], exp)
+        if not asym:
+            # seed-compressed protocol: per prime send(seed, 64) then send(c0, 4n); batch form = c0 only
+            se.set_sym_seed_ct(True)
+            try:
+                chunks3 = []
+                assert se.se_encrypt_seeded(sseed, seed, _send_collector(chunks3), vals)
+                assert [len(c) for c in chunks3] == [64, 4 * n] * np_
+                _, full = orc.encrypt_sym(n, np_, vals, sseed, seed, sk)
+                for p_ in range(np_):
+                    assert chunks3[2 * p_] == sseed.tobytes()
+                    assert np.array_equal(np.frombuffer(chunks3[2 * p_ + 1], np.uint32), full[p_, 0])
+                # NULL shareable seed: the library draws one and sends it; the receiver can rebuild a from it
+                chunks4 = []
+                assert se.se_encrypt(_send_collector(chunks4), vals)
+                drawn = np.frombuffer(chunks4[0], np.uint8)
+                assert all(chunks4[2 * p_] == chunks4[0] for p_ in range(np_)) and chunks4[0] != sseed.tobytes()
+                a, ctr = [], 0  # the receiver's expansion: one PRNG, counter running on across primes
+                for q in primes:
+                    ap, ctr = orc.sample_uniform(n, q, drawn, ctr)
+                    a.append(ap)
+                ct = np.stack([np.stack([np.frombuffer(chunks4[2 * p_ + 1], np.uint32), a[p_]]) for p_ in range(np_)])
+                dec = orc.decrypt_decode(n, np_, ct, sk, n // 2)
+                assert np.abs(dec - vals).max() < 0.1
+                ok, c0s = se.se_encrypt_batch_seedct(bshare, bseeds, bvals)
+                assert ok
+                for b in range(3):
+                    _, exp = orc.encrypt_sym(n, np_, bvals[b], bshare[b], bseeds[b], sk)
+                    assert np.array_equal(c0s[b], exp[:, 0, :])
+            finally:
+                se.set_sym_seed_ct(False)
     finally:
         se.se_cleanup()
 
