@@ -139,9 +139,6 @@ struct Scratch  // per in-flight chunk
     float *d_values  = nullptr;
     uint8_t *d_seeds = nullptr, *d_sseeds = nullptr;
     uint32_t *d_out  = nullptr;
-    float *h_values  = nullptr;
-    uint8_t *h_seeds = nullptr, *h_sseeds = nullptr;
-    uint32_t *h_out  = nullptr;
     int *h_fail      = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done    = nullptr;
@@ -240,10 +237,6 @@ static void free_scratch(Scratch &s)
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
     cudaFree(s.d_out);
-    cudaFreeHost(s.h_values);
-    cudaFreeHost(s.h_seeds);
-    cudaFreeHost(s.h_sseeds);
-    cudaFreeHost(s.h_out);
     cudaFreeHost(s.h_fail);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -389,7 +382,9 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     cudaError_t e;
     if (device >= 0 && (e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaGetDevice(&c->device)) != cudaSuccess) return bail("cudaGetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+    // a blocking stream: it orders itself after work the caller queued on the legacy default stream
+    // (cudaMemset / cudaMemcpy / a framework's default-stream fills of the buffers handed to us)
+    if ((e = cudaStreamCreate(&c->own_stream)) != cudaSuccess)
         return bail("cudaStreamCreate", e);
     c->stream = c->own_stream;
     if ((e = seb_encode_configure(logn)) != cudaSuccess) return bail("encode kernel attributes", e);
@@ -872,9 +867,11 @@ extern "C" int seb_encode_failures(seb_ctx *c)
 }
 
 // ---------------------------------------------------------------------------------------------
-// full path, host pointers: two chunks in flight, each on its own stream, so the H2D of chunk
-// k+1 and the D2H of chunk k-1 overlap the kernels of chunk k.  Pinned caller buffers are used
-// in place; pageable ones are staged through pinned bounce buffers.
+// full path, host pointers: the batch is cut in chunks, two in flight, each on its own stream, so the
+// H2D of chunk k+1 and the D2H of chunk k-1 overlap the kernels of chunk k.  With pinned caller buffers
+// every copy is asynchronous.  Pageable buffers are handed to cudaMemcpyAsync as they are (the runtime
+// stages them and the call blocks); chunk k+1 is launched before chunk k's blocking read-back, so the
+// kernels still overlap the copies.
 // ---------------------------------------------------------------------------------------------
 static bool is_pinned(const void *p)
 {
@@ -887,12 +884,23 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-static size_t host_chunk(const seb_ctx *c)
+// Items per chunk.  Large enough to keep the copy engines busy (>= 64 MiB of ciphertext) AND to fill the
+// GPU: the asymmetric path's ternary sampler is a warp per ciphertext, and the symmetric path's uniform
+// sampler is ONE sequential sponge per ciphertext whose latency (~2 ms per prime at n = 16384) is paid
+// per chunk whatever its size — 85-item chunks made config D's host path 12x slower than its device
+// path (profiles/README.md).  Chunks are balanced so the last one is not a sliver.  SEB_HOST_CHUNK
+// overrides the item count.
+static size_t host_chunk(const seb_ctx *c, bool sym, size_t batch)
 {
-    // ~64 MiB of ciphertext per chunk keeps the copy engines busy without hoarding pinned memory
     const size_t per_ct = 2 * c->np * c->n * sizeof(uint32_t);
     size_t chunk        = (64u << 20) / per_ct;
-    return chunk < 16 ? 16 : chunk;
+    const size_t fill   = sym ? 8192 : 2048;
+    if (chunk < fill) chunk = fill;
+    if (const char *v = getenv("SEB_HOST_CHUNK"))
+        if (atol(v) > 0) chunk = (size_t)atol(v);
+    if (chunk >= batch) return batch;
+    const size_t nchunks = (batch + chunk - 1) / chunk;
+    return (batch + nchunks - 1) / nchunks;
 }
 
 static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym, size_t per_ct)
@@ -904,21 +912,18 @@ static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym, size_t per_
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
     cudaFree(s.d_out);
-    cudaFreeHost(s.h_values);
-    cudaFreeHost(s.h_seeds);
-    cudaFreeHost(s.h_sseeds);
-    cudaFreeHost(s.h_out);
     cudaFreeHost(s.h_fail);
-    s.io_cap            = 0;
-    const size_t out_b  = chunk * per_ct * sizeof(uint32_t);
+    s.d_values = nullptr;
+    s.d_seeds = s.d_sseeds = nullptr;
+    s.d_out  = nullptr;
+    s.h_fail = nullptr;
+    s.io_cap = 0;
+    if (chunk < s.io_cap) chunk = s.io_cap;
+    if (per_ct < s.io_out_words) per_ct = s.io_out_words;
     CU(cudaMalloc(&s.d_values, chunk * (c->n / 2) * sizeof(float)));
     CU(cudaMalloc(&s.d_seeds, chunk * SEB_SEED_BYTES));
     CU(cudaMalloc(&s.d_sseeds, chunk * SEB_SEED_BYTES));
-    CU(cudaMalloc(&s.d_out, out_b));
-    CU(cudaMallocHost(&s.h_values, chunk * (c->n / 2) * sizeof(float)));
-    CU(cudaMallocHost(&s.h_seeds, chunk * SEB_SEED_BYTES));
-    CU(cudaMallocHost(&s.h_sseeds, chunk * SEB_SEED_BYTES));
-    CU(cudaMallocHost(&s.h_out, out_b));
+    CU(cudaMalloc(&s.d_out, chunk * per_ct * sizeof(uint32_t)));
     CU(cudaMallocHost(&s.h_fail, chunk * sizeof(int)));
     s.io_cap       = chunk;
     s.io_out_words = per_ct;
@@ -936,14 +941,14 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     int r = check_vlen(c, vlen);
     if (r) return r;
     CU(cudaSetDevice(c->device));
-    const size_t chunk  = host_chunk(c) < batch ? host_chunk(c) : batch;
+    const size_t chunk  = host_chunk(c, sym, batch);
     const size_t per_ct = (seedct ? 1 : 2) * c->np * c->n;  // words of output per ciphertext
-    const bool pin_in   = is_pinned(values) && is_pinned(seeds) && (!sym || is_pinned(sseeds));
     const bool pin_out  = is_pinned(out);
-    for (auto &s : c->slot)
+    const size_t nslots = chunk < batch ? 2 : 1;
+    for (size_t k = 0; k < nslots; k++)
     {
-        if ((r = ensure_scratch(c, s, chunk))) return r;
-        if ((r = ensure_io(c, s, chunk, sym, per_ct))) return r;
+        if ((r = ensure_scratch(c, c->slot[k], chunk))) return r;
+        if ((r = ensure_io(c, c->slot[k], chunk, sym, per_ct))) return r;
     }
     struct Pending
     {
@@ -952,11 +957,14 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     } pend[2];
     int failures = 0;
 
+    // wait for chunk k's results to be in the caller's buffer
     auto drain = [&](int k) -> int {
         if (!pend[k].live) return 0;
         Scratch &s = c->slot[k];
+        if (!pin_out)  // blocking copy, ordered after the chunk's kernels on its stream
+            CU(cudaMemcpyAsync(out + pend[k].first * per_ct, s.d_out, pend[k].count * per_ct * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventSynchronize(s.done));
-        if (!pin_out) memcpy(out + pend[k].first * per_ct, s.h_out, pend[k].count * per_ct * sizeof(uint32_t));
         for (size_t i = 0; i < pend[k].count; i++) failures += s.h_fail[i] != 0;
         pend[k].live = false;
         return 0;
@@ -966,33 +974,25 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     for (size_t first = 0; first < batch; first += chunk, k ^= 1)
     {
         const size_t count = batch - first < chunk ? batch - first : chunk;
-        Scratch &s         = c->slot[k];
-        if ((r = drain(k))) return r;
+        Scratch &s         = c->slot[k];  // free: its previous chunk was drained one iteration ago
         const float *hv    = values + first * vlen;
         const uint8_t *hs  = seeds + first * SEB_SEED_BYTES;
         const uint8_t *hss = sym ? sseeds + first * SEB_SEED_BYTES : nullptr;
-        if (!pin_in)
-        {
-            memcpy(s.h_values, hv, count * vlen * sizeof(float));
-            memcpy(s.h_seeds, hs, count * SEB_SEED_BYTES);
-            if (sym) memcpy(s.h_sseeds, hss, count * SEB_SEED_BYTES);
-            hv  = s.h_values;
-            hs  = s.h_seeds;
-            hss = s.h_sseeds;
-        }
         CU(cudaMemcpyAsync(s.d_values, hv, count * vlen * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(s.d_seeds, hs, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
         if (sym) CU(cudaMemcpyAsync(s.d_sseeds, hss, count * SEB_SEED_BYTES, cudaMemcpyHostToDevice, s.stream));
         r = sym ? encrypt_sym_on(c, s, s.d_values, vlen, s.d_sseeds, s.d_seeds, count, s.d_out, quirk, seedct, s.stream)
                 : encrypt_asym_on(c, s, s.d_values, vlen, s.d_seeds, count, s.d_out, s.stream);
         if (r) return r;
-        uint32_t *ho = pin_out ? out + first * per_ct : s.h_out;
-        CU(cudaMemcpyAsync(ho, s.d_out, count * per_ct * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (pin_out)
+            CU(cudaMemcpyAsync(out + first * per_ct, s.d_out, count * per_ct * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               s.stream));
         CU(cudaMemcpyAsync(s.h_fail, s.fail, count * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
         pend[k].first = first;
         pend[k].count = count;
         pend[k].live  = true;
+        if ((r = drain(k ^ 1))) return r;  // the previous chunk, while this one computes
     }
     if ((r = drain(0))) return r;
     if ((r = drain(1))) return r;

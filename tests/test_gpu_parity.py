@@ -544,26 +544,43 @@ def test_edge_cases_and_errors(seb, torch_cuda, oracle_mod, orc):
         seb.Context(4096, 1, True, device=0, primes=[1053818881], psis=[12345])  # not a primitive 2n-th root
 
 
-def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs):
-    """Host-pointer batch API: pageable and pinned buffers, more items than one chunk, ragged vlen."""
+def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
+    """Host-pointer batch API: pageable and pinned buffers, several chunks in flight (SEB_HOST_CHUNK forces
+    3 balanced chunks of 500 items; the default policy would take 1500 items in one), ragged vlen, and
+    the symmetric flavours (full and seed-compressed) through the same pipeline."""
     torch = torch_cuda
     n, np_ = 4096, 3
     ctx = ctxs(n, np_, True)
     sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
     ctx.set_public_key(pk0, pk1)
-    batch = 1500  # chunk is ~682 items at 96 KiB per ciphertext
+    batch = 1500
     vlen = 100
     vals = oracle_mod.make_values(batch, vlen, seed=99)
     seeds = oracle_mod.make_seeds(batch, b"host")
-    out = ctx.encrypt_asym_host(vals, seeds)
+    one = ctx.encrypt_asym_host(vals, seeds)  # default policy: a single chunk
+    monkeypatch.setenv("SEB_HOST_CHUNK", "600")
+    out = ctx.encrypt_asym_host(vals, seeds)  # pageable buffers
+    assert np.array_equal(out, one)
     pv = torch.from_numpy(vals).pin_memory()
     ps = torch.from_numpy(seeds).pin_memory()
     po = torch.empty((batch, np_, 2, n), dtype=torch.int32).pin_memory()
     ctx.lib.seb_encrypt_asym_host(ctx.h, pv.data_ptr(), vlen, ps.data_ptr(), batch, po.data_ptr())
     assert np.array_equal(out, po.numpy().view(np.uint32))
-    for b in (0, 1, 681, 682, 683, 1364, 1499):
+    for b in (0, 1, 499, 500, 501, 999, 1000, 1499):
         ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
         assert ok and np.array_equal(out[b], exp), b
+    # symmetric: chunks of 40 out of 100 items -> 3 chunks of 34/34/32
+    sctx = ctxs(n, np_, False)
+    sctx.set_secret_key(sk)
+    monkeypatch.setenv("SEB_HOST_CHUNK", "40")
+    sb = 100
+    sseeds = oracle_mod.make_seeds(sb, b"host-share")
+    full = sctx.encrypt_sym_host(vals[:sb], sseeds, seeds[:sb])
+    c0 = sctx.encrypt_sym_seedct_host(vals[:sb], sseeds, seeds[:sb])
+    assert np.array_equal(c0, full[:, :, 0, :])
+    for b in (0, 33, 34, 67, 68, 99):
+        ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
+        assert ok and np.array_equal(full[b], exp), b
 
 
 def _send_collector(chunks):

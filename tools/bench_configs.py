@@ -98,13 +98,43 @@ def ntt_sweep(quick):
     return out
 
 
+def e2e_sym(name, n, np_, batch, reps=2):
+    """Host-pointer symmetric path with pinned buffers, full ciphertexts vs the seed-compressed form (c0 only):
+    the ciphertext D2H is the bound, so halving it should nearly double the end-to-end rate."""
+    import time
+    ctx = seb.Context(n, np_, asym=False, device=0)
+    rng = np.random.default_rng(2)
+    t = rng.integers(0, 3, (n // 4, 4), dtype=np.uint8)
+    ctx.set_secret_key(((t[:, 0] << 6) | (t[:, 1] << 4) | (t[:, 2] << 2) | t[:, 3]).astype(np.uint8))
+    vlen = n // 2
+    vals = torch.empty((batch, vlen), dtype=torch.float32).uniform_(-16, 16).pin_memory()
+    seeds = torch.randint(0, 256, (batch, 64), dtype=torch.uint8).pin_memory()
+    ss = torch.randint(0, 256, (batch, 64), dtype=torch.uint8).pin_memory()
+    res = {"config": name, "n": n, "nprimes": np_, "batch": batch}
+    for mode, words in (("full", 2 * np_ * n), ("seedct", np_ * n)):
+        out = torch.empty((batch, words), dtype=torch.int32).pin_memory()
+        fn = (lambda: ctx.encrypt_sym_host(vals.numpy(), ss.numpy(), seeds.numpy(), out.numpy().view(np.uint32))) \
+            if mode == "full" else \
+            (lambda: ctx.encrypt_sym_seedct_host(vals.numpy(), ss.numpy(), seeds.numpy(), out.numpy().view(np.uint32)))
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps
+        res[mode] = {"ms_per_step": dt * 1e3, "ciphertexts_per_s": batch / dt, "d2h_GB_per_step": batch * words * 4 / 1e9,
+                     "d2h_GBps": batch * words * 4 / 1e9 / dt}
+        del out
+    ctx.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
     torch.cuda.set_device(0)
-    res = {"hbm_peak_GBps": PEAK, "full_path": [], "ntt_only": []}
+    res = {"hbm_peak_GBps": PEAK, "full_path": [], "e2e_sym": [], "ntt_only": []}
     cfgs = [("A: n=1024 1 prime sym, batch 65536 (the reference's CPU case, batched)", 1024, 1, False, 65536),
             ("B: n=4096 3 primes asym, batch 65536", 4096, 3, True, 65536),
             ("B-sym: n=4096 3 primes sym, batch 65536", 4096, 3, False, 65536),
@@ -113,6 +143,12 @@ def main():
     for c in cfgs:
         r = full_path(*c)
         res["full_path"].append(r)
+        print(json.dumps(r), flush=True)
+    res["e2e_sym"] = []
+    for c in (("B-sym e2e: n=4096 3 primes sym, batch 16384 (host buffers)", 4096, 3, 16384),
+              ("D e2e: n=16384 6 primes sym, batch 4096 (host buffers)", 16384, 6, 4096)):
+        r = e2e_sym(*c)
+        res["e2e_sym"].append(r)
         print(json.dumps(r), flush=True)
     res["ntt_only"] = ntt_sweep(a.quick)
     for r in res["ntt_only"]:
