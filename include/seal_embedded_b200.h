@@ -148,12 +148,16 @@ typedef struct seb_ctx seb_ctx;
 const char *seb_last_error(void);
 
 /* primes == NULL: the reference's default chain for (n, nprimes) (parameters.c:129-230) with its
- * tabulated 2n-th roots (ntt.c:199-291) and default scale when scale <= 0.  With explicit primes,
- * psis[i] must be a primitive 2n-th root of unity mod primes[i].  device < 0: keep the current
- * CUDA device. */
+ * tabulated 2n-th roots (ntt.c:199-291) and default scale when scale <= 0.  With explicit primes
+ * (each < 2^30 and = 1 mod 2n), psis[i] must be a primitive 2n-th root of unity mod primes[i]; psis == NULL
+ * takes the reference's tabulated root where there is one and seb_minimal_psi otherwise.  device < 0:
+ * keep the current CUDA device. */
 seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes, const uint32_t *psis,
                     double scale, int asym, int device);
 void seb_destroy(seb_ctx *ctx);
+/* Smallest primitive 2n-th root of unity mod q, 0 if there is none (host arithmetic, no GPU needed).
+ * Equals the reference's table get_ntt_root (ntt.c:199-291) wherever that is defined. */
+uint32_t seb_minimal_psi(size_t n, uint32_t q);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own */
 int seb_set_stream(seb_ctx *ctx, void *cuda_stream);
 /* pk0, pk1: host [nprimes][n], NTT form (files pk{0,1}_ntt_<n>_<q>.dat, fileops.c:172-204) */

@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
     "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
     "seb_encrypt_sym_seedct_device", "seb_encrypt_sym_seedct_host", "seb_expand_seedct_device",
-    "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct",
+    "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct", "seb_minimal_psi",
 ]
 
 
@@ -107,6 +107,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_last_error.restype = C.c_char_p
     L.seb_create.argtypes = [sz, sz, vp, vp, C.c_double, i32, i32]
     L.seb_create.restype = vp
+    L.seb_minimal_psi.argtypes = [sz, u32]
+    L.seb_minimal_psi.restype = u32
     L.seb_destroy.argtypes = [vp]
     L.seb_destroy.restype = None
     L.seb_set_stream.argtypes = [vp, vp]
@@ -169,6 +171,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     if path is None:
         _lib = L
     return L
+
+
+def minimal_psi(n: int, q: int) -> int:
+    """Smallest primitive 2n-th root of unity mod q (host arithmetic inside the library; 0 if none)."""
+    return int(load_library().seb_minimal_psi(n, q))
 
 
 def _addr(x) -> int:

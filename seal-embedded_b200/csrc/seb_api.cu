@@ -116,6 +116,36 @@ static inline size_t bitrev(size_t x, int bits)
     return r;
 }
 
+// Smallest primitive 2n-th root of unity mod q (0 when q - 1 is not a multiple of 2n or no root is found):
+// what SEAL's try_minimal_primitive_root computes and — checked for all 27 pairs by the CPU suite — what
+// the reference tabulates per (n, q) in get_ntt_root (ntt.c:199-291).  Lets custom prime chains
+// (se_setup_custom) and the NTT sweep's "1..8 primes at every degree" work without a table.
+extern "C" uint32_t seb_minimal_psi(size_t n, uint32_t q)
+{
+    if (n == 0 || q < 3 || (q - 1) % (2 * n) != 0) return 0;
+    const uint64_t e = (q - 1) / (2 * n);
+    uint32_t r       = 0;
+    for (uint32_t g = 2; g < 1000 && g < q; g++)
+    {
+        const uint32_t c = powmod(g, e, q);
+        if (powmod(c, n, q) == q - 1)  // order exactly 2n (n is a power of two)
+        {
+            r = c;
+            break;
+        }
+    }
+    if (!r) return 0;
+    // the primitive 2n-th roots are the odd powers of r
+    const uint32_t r2 = mulmod(r, r, q);
+    uint32_t best = r, cur = r;
+    for (size_t i = 1; i < n; i++)
+    {
+        cur = mulmod(cur, r2, q);
+        if (cur < best) best = cur;
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
@@ -341,6 +371,7 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
         {
             c->primes[i] = primes[i];
             c->psis[i]   = psis ? psis[i] : default_psi(n, primes[i]);
+            if (!c->psis[i]) c->psis[i] = seb_minimal_psi(n, primes[i]);
         }
     }
     else

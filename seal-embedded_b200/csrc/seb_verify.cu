@@ -124,9 +124,14 @@ __global__ void __launch_bounds__(SEB_VERIFY_THREADS)
 
 cudaError_t seb_verify_configure(int n)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_intt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * n);
+    // The attribute belongs to the kernel, not to a context: contexts of several degrees live in one
+    // process, so it is always raised to the largest degree's need (a later, smaller context must not
+    // lower it under an earlier one's launches).
+    (void)n;
+    const int max_bytes = 4 * 16384;
+    cudaError_t e = cudaFuncSetAttribute(k_intt, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_decrypt_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * n);
+        e = cudaFuncSetAttribute(k_decrypt_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, max_bytes);
     return e;
 }
 

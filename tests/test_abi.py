@@ -77,6 +77,31 @@ def test_invalid_parameters_are_rejected(seb):
         assert b"unsupported" in lib.seb_last_error() or b"no default" in lib.seb_last_error()
 
 
+def test_minimal_psi_reproduces_the_reference_table(seb, orc):
+    """seb_minimal_psi (host arithmetic inside the library, usable without a GPU) equals get_ntt_root
+    (ntt.c:199-291) for every (n, q) the reference tabulates, is a primitive 2n-th root for the 30-bit
+    primes at degrees the reference does not tabulate them for, and refuses unfriendly moduli."""
+    from importlib import import_module
+
+    api = import_module("seal-embedded_b200.api")
+    checked = 0
+    for n, nps in ((1024, 1), (2048, 1), (4096, 3), (8192, 6), (16384, 13)):
+        for q in orc.primes(n, nps):
+            assert api.minimal_psi(n, q) == orc.ntt_root(n, q), (n, q)
+            checked += 1
+    for q in (134012929, 134111233, 134176769):  # the 27-bit 4K set (parameters.c:204-209)
+        assert api.minimal_psi(4096, q) == orc.ntt_root(4096, q)
+        checked += 1
+    assert checked == 27
+    for n in (1024, 4096):
+        for q in orc.primes(16384, 8):
+            psi = api.minimal_psi(n, q)
+            assert psi and pow(psi, n, q) == q - 1
+            assert all(pow(psi, k, q) >= psi or pow(pow(psi, k, q), n, q) != q - 1 for k in (3, 5, 7, 9))
+    assert api.minimal_psi(16384, 134012929) == 0  # q - 1 is not a multiple of 2n
+    assert api.minimal_psi(4096, 1000003) == 0
+
+
 def test_missing_library_is_an_error(seb, tmp_path):
     with pytest.raises(seb.SebError):
         seb.load_library(str(tmp_path / "nope.so"))

@@ -223,6 +223,35 @@ def test_ntt(n, np_, seb, torch_cuda, orc, ctxs):
         assert np.all(got[1, p] == 1)  # NTT(delta_0) = all ones
 
 
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_ntt_custom_prime_chain(n, seb, torch_cuda, orc):
+    """Config E asks for 1..8 primes at n = 1024 and 4096, beyond the reference's parameter sets
+    (SURVEY 0.9): a caller-supplied chain of eight 30-bit primes with the library's minimal 2n-th roots
+    (the custom-prime path the reference leaves broken, 0.8) against the oracle's ntt_inpl
+    restatement run with the same roots."""
+    torch = torch_cuda
+    primes = orc.primes(16384, 8)
+    ctx = seb.Context(n, 8, True, device=0, primes=primes)
+    try:
+        assert ctx.primes == primes
+        batch = 3
+        rng = np.random.default_rng(n)
+        x = np.stack([np.stack([rng.integers(0, q, n, dtype=np.uint32) for q in primes]) for _ in range(batch)])
+        d = dev(torch, x)
+        ctx.ntt_device(d, batch)
+        torch.cuda.synchronize()
+        got = host(d, np.uint32).reshape(batch, 8, n)
+        for b in range(batch):
+            for p, q in enumerate(primes):
+                psi = seb.api.minimal_psi(n, q)
+                assert np.array_equal(got[b, p], orc.ntt(n, q, x[b, p], psi=psi)), (n, b, p)
+        ctx.intt_device(d, batch)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d, np.uint32).reshape(batch, 8, n), x)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (8192, 6), (16384, 13)])
 def test_intt(n, np_, seb, torch_cuda, orc, ctxs):
     """Verifier INTT (inverse of ntt_inpl; reference: intt.c:226-501): equals the oracle's inverse and undoes
@@ -501,6 +530,30 @@ def test_encrypt_reduction_path_boundary(n, np_, seb, torch_cuda, oracle_mod, or
         ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
         assert ok and ok_pt and np.array_equal(got[b], exp), (n, b, mx)
     assert below >= 3 and above >= 3
+
+
+def test_contexts_of_several_degrees_coexist(seb, torch_cuda, ctxs):
+    """Kernel attributes are per kernel, not per context: creating a small-degree context after a large one
+    must not shrink what the large one may launch (regression: the verifier's dynamic shared memory limit)."""
+    torch = torch_cuda
+    big = ctxs(16384, 6, False)
+    small = seb.Context(1024, 1, True, device=0)
+    try:
+        rng = np.random.default_rng(5)
+        x = np.stack([rng.integers(0, q, 16384, dtype=np.uint32) for q in big.primes])[None]
+        d = dev(torch, x)
+        big.ntt_device(d, 1)
+        big.intt_device(d, 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d, np.uint32).reshape(1, 6, 16384), x)
+        y = rng.integers(0, small.primes[0], (2, 1, 1024), dtype=np.uint32)
+        d2 = dev(torch, y)
+        small.ntt_device(d2, 2)
+        small.intt_device(d2, 2)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d2, np.uint32).reshape(2, 1, 1024), y)
+    finally:
+        small.close()
 
 
 def test_edge_cases_and_errors(seb, torch_cuda, oracle_mod, orc):

@@ -25,6 +25,10 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
+PRIMES30 = [1053818881, 1054015489, 1054212097, 1055260673, 1056178177, 1056440321, 1058209793, 1060175873,
+            1060700161, 1060765697, 1061093377, 1062469633, 1062535169]  # device/lib/parameters.c:129-174
+
+
 def timed(fn, stream, reps):
     fn()
     torch.cuda.synchronize()
@@ -82,9 +86,11 @@ def ntt_sweep(quick):
     out = []
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    for n, nps in ((1024, (1,)), (2048, (1,)), (4096, (1, 3)), (8192, (1, 4, 6)), (16384, (1, 6, 13))):
+    # config E: n x primes x batch.  Prime counts beyond the reference's parameter sets (8 primes at n <= 8192)
+    # use the first primes of its 30-bit list with the library's minimal 2n-th roots (seb_minimal_psi).
+    for n, nps in ((1024, (1, 8)), (2048, (1,)), (4096, (1, 3, 8)), (8192, (1, 4, 8)), (16384, (1, 6, 8, 13))):
         for np_ in nps:
-            ctx = seb.Context(n, np_, asym=True, device=0)
+            ctx = seb.Context(n, np_, asym=True, device=0, primes=PRIMES30[:np_])
             ctx.set_stream(stream.cuda_stream)
             batches = [1, 64, 4096, (1 << 30) // (4 * n * np_)] if not quick else [(1 << 30) // (4 * n * np_)]
             for batch in batches:
