@@ -793,24 +793,37 @@ def test_golden_fixtures(seb, torch_cuda, oracle_mod, ctxs):
             assert np.array_equal(got[0], g[key + "_ct0"].reshape(-1))
 
 
-def test_full_size_properties(seb, torch_cuda, oracle_mod, orc, ctxs):
-    """Config B at full size (n=4096, 3 primes, batch 65536): size-independent properties —
-    (1) items are independent of batch position and grid shape (re-encrypting slices reproduces the
-    same per-item checksums), (2) first/last items equal the oracle bit for bit, (3) every residue
-    is < q, (4) decrypt+decode of sampled items returns the message within 0.1."""
+@pytest.mark.parametrize("n,np_,asym,batch", [(4096, 3, True, 65536), (8192, 4, True, 32768), (16384, 6, False, 16384),
+                                              (1024, 1, False, 65536)],
+                         ids=["B-4096x3-asym-65536", "C-8192x4-asym-32768", "D-16384x6-sym-16384", "A-1024x1-sym-65536"])
+def test_full_size_properties(n, np_, asym, batch, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """BASELINE.json's configurations at full per-GPU size (B whole; C and D as their 1/8 shards; A batched):
+    size-independent properties — (1) items are independent of batch position and grid shape (re-encrypting
+    slices reproduces the same per-item checksums), (2) first/middle/last items equal the oracle bit for
+    bit, (3) every residue is < q, (4) EVERY item decrypts and decodes to its message within the
+    reference's 0.1 on the GPU verifier."""
     torch = torch_cuda
-    n, np_ = 4096, 3
-    batch = 65536
-    ctx = ctxs(n, np_, True)
+    ctx = ctxs(n, np_, asym)
     sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
-    ctx.set_public_key(pk0, pk1)
+    if asym:
+        ctx.set_public_key(pk0, pk1)
+    ctx.set_secret_key(sk)
     vlen = n // 2
     gen = torch.Generator(device="cuda").manual_seed(1)
     d_vals = torch.rand((batch, vlen), generator=gen, device="cuda", dtype=torch.float32) * 32 - 16
     d_seeds = torch.randint(0, 256, (batch, 64), generator=gen, device="cuda", dtype=torch.uint8)
+    d_ss = torch.randint(0, 256, (batch, 64), generator=gen, device="cuda", dtype=torch.uint8)
     d_out = torch.empty((batch, np_, 2, n), dtype=torch.int32, device="cuda")
-    ctx.encrypt_asym_device(d_vals, vlen, d_seeds, batch, d_out)
-    assert ctx.encode_failures() == 0
+
+    def encrypt(lo, hi, out):
+        v, sd, ss = d_vals[lo:hi].contiguous(), d_seeds[lo:hi].contiguous(), d_ss[lo:hi].contiguous()
+        if asym:
+            ctx.encrypt_asym_device(v, vlen, sd, hi - lo, out)
+        else:
+            ctx.encrypt_sym_device(v, vlen, ss, sd, hi - lo, out, False)
+        assert ctx.encode_failures() == 0
+
+    encrypt(0, batch, d_out)
     sums = d_out.view(batch, -1).to(torch.int64).sum(dim=1)
     xors = d_out.view(batch, -1)[:, ::97].to(torch.int64).sum(dim=1)
     for p, q in enumerate(ctx.primes):
@@ -818,23 +831,28 @@ def test_full_size_properties(seb, torch_cuda, oracle_mod, orc, ctxs):
     # (1) slices with other batch sizes / offsets
     for lo, hi in ((0, 1), (5, 777), (batch - 4099, batch)):
         d_o2 = torch.empty((hi - lo, np_, 2, n), dtype=torch.int32, device="cuda")
-        ctx.encrypt_asym_device(d_vals[lo:hi].contiguous(), vlen, d_seeds[lo:hi].contiguous(), hi - lo, d_o2)
-        assert ctx.encode_failures() == 0
+        encrypt(lo, hi, d_o2)
         assert torch.equal(d_o2.view(hi - lo, -1).to(torch.int64).sum(dim=1), sums[lo:hi])
         assert torch.equal(d_o2.view(hi - lo, -1)[:, ::97].to(torch.int64).sum(dim=1), xors[lo:hi])
-    # (4') EVERY item of the batch round-trips on the GPU verifier: decrypt + decode within the
-    # reference's 0.1 (device/test/ckks_tests_common.c:228), under each prime
-    ctx.set_secret_key(sk)
+        del d_o2
+    # (4) every item of the batch round-trips on the GPU verifier (device/test/ckks_tests_common.c:228),
+    # under each prime
     d_dec = torch.empty((batch, vlen), dtype=torch.float32, device="cuda")
     for p in range(np_):
         ctx.decrypt_decode_device(d_out, batch, p, vlen, d_dec)
         assert float((d_dec - d_vals).abs().max()) < 0.1, p
-    # (2),(4) oracle on the ends
+    # (2) the oracle on the ends and the middle
     vals = d_vals.cpu().numpy()
     seeds = d_seeds.cpu().numpy()
+    sseeds = d_ss.cpu().numpy()
     for b in (0, 1, batch // 2, batch - 1):
         got = host(d_out[b], np.uint32).reshape(np_, 2, n)
-        ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        if asym:
+            ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+        else:
+            ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
         assert ok and np.array_equal(got, exp), b
         dec = orc.decrypt_decode(n, np_, got, sk, vlen)
         assert np.abs(dec - vals[b]).max() < 0.1
+    del d_out, d_dec
+    torch.cuda.empty_cache()
