@@ -32,6 +32,12 @@
 
 #define SEB_E 16  // coefficients per thread
 
+// How a twiddle oct is fetched: a 256-bit read-only global load of the L1/L2-resident table.  (tools/ubench/
+// ubench_ntt_tma.cu overrides it to measure a table staged in shared memory by cp.async.bulk.)
+#ifndef SEB_TW_LOAD
+#define SEB_TW_LOAD(p) seb_ldg256(p)
+#endif
+
 template <int LOGN>
 struct NttPlan;
 template <>
@@ -171,7 +177,7 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
 {
     seb_oct w[(1 << R) / 4];
 #pragma unroll
-    for (int k = 0; k < (1 << R) / 4; k++) w[k] = seb_ldg256(tp + (size_t)k * nb);
+    for (int k = 0; k < (1 << R) / 4; k++) w[k] = SEB_TW_LOAD(tp + (size_t)k * nb);
 #pragma unroll
     for (int r = 0; r < R; r++)
     {
@@ -222,16 +228,15 @@ __host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group_base(uint32
 // Barrier scope between pass P and pass P+1.  A CTA-wide barrier makes all n/16 threads wait for the
 // slowest warp; wherever every coefficient a thread reads in pass P+1 was written in pass P by a
 // thread of a smaller unit, only that unit synchronises:
-//   SEB_SYNC_WARP   : same warp -> __syncwarp()            (last boundary of n = 1024, 4096, 8192, 16384)
-//   SEB_SYNC_GROUP64: same aligned group of 64 threads -> named barrier `bar.sync t/64, 64`
-//                     (boundary 1 -> 2 of n = 8192 and 16384; at most 16 groups = the 16 hardware barriers.
-//                     Barrier 0 doubles as the __syncthreads() barrier: the two uses never overlap in time
-//                     because every thread has left the preceding CTA-wide barrier before any thread can
-//                     arrive here, and no CTA-wide barrier follows inside the transform)
-//   SEB_SYNC_CTA    : __syncthreads()
+//   SEB_SYNC_WARP : same warp -> __syncwarp()               (last boundary of n = 1024, 4096, 8192, 16384)
+//   SEB_SYNC_GROUP: same aligned group of NttSync::GROUP threads -> named barrier `bar.sync 1 + t/GROUP, GROUP`
+//                   (boundary 1 -> 2 of n = 8192: 8 groups of 64, and of n = 16384: the exchange is local to 64
+//                   threads too, but 16 groups would need hardware barrier 0, which belongs to __syncthreads();
+//                   8 groups of 128 keep to barriers 1..8)
+//   SEB_SYNC_CTA  : __syncthreads()
 // Checked exhaustively by tests/test_host_logic.py::test_ntt_barrier_scopes.
 #define SEB_SYNC_CTA 0
-#define SEB_SYNC_GROUP64 1
+#define SEB_SYNC_GROUP 1
 #define SEB_SYNC_WARP 2
 template <int LOGN, int P>
 struct NttSync
@@ -239,20 +244,21 @@ struct NttSync
     static constexpr int value = ((LOGN == 10 && P == 1) || (LOGN == 12 && P == 1) || (LOGN == 13 && P == 2) ||
                                   (LOGN == 14 && P == 2))
                                      ? SEB_SYNC_WARP
-                                     : ((LOGN == 13 && P == 1) || (LOGN == 14 && P == 1)) ? SEB_SYNC_GROUP64 : SEB_SYNC_CTA;
+                                     : ((LOGN == 13 && P == 1) || (LOGN == 14 && P == 1)) ? SEB_SYNC_GROUP : SEB_SYNC_CTA;
+    static constexpr int GROUP = LOGN == 14 ? 128 : 64;  // threads per named barrier (SEB_SYNC_GROUP only)
 };
 
-template <int SCOPE>
+template <int SCOPE, int GROUP>
 __device__ __forceinline__ void seb_ntt_sync(const int t)
 {
     if (SCOPE == SEB_SYNC_WARP)
         __syncwarp();
-    else if (SCOPE == SEB_SYNC_GROUP64)
+    else if (SCOPE == SEB_SYNC_GROUP)
     {
 #if defined(SEB_UBENCH_CTA_BARRIERS)  // tools/ubench A/B switch only
         __syncthreads();
 #elif defined(__CUDACC__)
-        asm volatile("bar.sync %0, 64;" ::"r"(t >> 6) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + t / GROUP), "n"(GROUP) : "memory");
 #endif
     }
     else
@@ -332,7 +338,7 @@ struct SebNttRun
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
         if (P + 1 < NttPlan<LOGN>::NPASS)
         {
-            seb_ntt_sync<NttSync<LOGN, P>::value>(t);
+            seb_ntt_sync<NttSync<LOGN, P>::value, NttSync<LOGN, P>::GROUP>(t);
             SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
                                                                                               load);
         }

@@ -160,11 +160,13 @@ extern "C" int64_t emul_ntt_elem(int logn, int pass, uint32_t t, uint32_t i, uin
     return -1;
 }
 
-// scope of the barrier after pass `pass`: SEB_SYNC_CTA (0), SEB_SYNC_GROUP64 (1), SEB_SYNC_WARP (2)
+// scope of the barrier after pass `pass`: SEB_SYNC_CTA -> 0, SEB_SYNC_WARP -> 32, SEB_SYNC_GROUP -> threads
+// per named barrier
 extern "C" int emul_ntt_sync_scope(int logn, int pass)
 {
-#define CASEP(L, P) \
-    if (logn == L && pass == P) return NttSync<L, P>::value;
+#define CASEP(L, P)                                                                                  \
+    if (logn == L && pass == P)                                                                      \
+        return NttSync<L, P>::value == SEB_SYNC_CTA ? 0 : NttSync<L, P>::value == SEB_SYNC_WARP ? 32 : NttSync<L, P>::GROUP;
 #define CASEL(L) CASEP(L, 0) CASEP(L, 1) CASEP(L, 2) CASEP(L, 3)
     CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14)
 #undef CASEL

@@ -128,9 +128,9 @@ def test_smem_layout_conflict_free(logn, E):
 @pytest.mark.parametrize("logn", LOGNS)
 def test_ntt_barrier_scopes(logn, E):
     """Each pass covers every coefficient exactly once, and wherever the kernels replace the CTA barrier
-    between two passes by a narrower one (NttSync: __syncwarp() or a 64-thread named barrier), every
-    coefficient a thread reads in the later pass was written in the earlier one by a thread of the same
-    warp / the same aligned 64-thread group."""
+    between two passes by a narrower one (NttSync: __syncwarp() or a named barrier over an aligned group of
+    64 / 128 threads), every coefficient a thread reads in the later pass was written in the earlier one by
+    a thread of the same warp / group."""
     n = 1 << logn
     T = n // 16
     plan = _plan(E, logn)
@@ -147,14 +147,16 @@ def test_ntt_barrier_scopes(logn, E):
         owner.append(own)
     scopes = []
     for p in range(len(plan) - 1):
-        scope = E.emul_ntt_sync_scope(logn, p)
-        shift = {0: None, 1: 6, 2: 5}[scope]
-        if shift is not None:
-            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (logn, p, scope)
-            if scope == 1:
-                assert T % 64 == 0 and T // 64 <= 16  # one hardware barrier per group
-        scopes.append(scope)
-    expect = {10: [0, 2], 11: [0, 0], 12: [0, 2], 13: [0, 1, 2], 14: [0, 1, 2]}[logn]
+        width = E.emul_ntt_sync_scope(logn, p)  # 0: whole CTA, 32: warp, else threads per named barrier
+        if width:
+            shift = width.bit_length() - 1
+            assert 1 << shift == width
+            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (logn, p, width)
+            if width > 32:
+                # hardware barriers 1..15 only: barrier 0 is __syncthreads()
+                assert T % width == 0 and T // width <= 15
+        scopes.append(width)
+    expect = {10: [0, 32], 11: [0, 0], 12: [0, 32], 13: [0, 64, 32], 14: [0, 128, 32]}[logn]
     assert scopes == expect
     assert E.emul_ntt_sync_scope(logn, len(plan) - 1) == 0
 
