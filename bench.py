@@ -327,6 +327,34 @@ def run_b200_arm(args) -> None:
                "d2h_bytes_per_step": eb * (np_ * 2 * n * 4 + 4), "matches_device_path": same,
                "api": "seb_encrypt_asym_host (pinned host buffers, 2 chunks in flight)", "cpu_binding": numa}
 
+    # ---- optional collation (BASELINE north_star: "a single NCCL all-gather only to collate outputs"): every
+    # rank receives every rank's ciphertexts.  Off the throughput path; timed on a bounded slice so that the
+    # gathered tensor stays small (world x 4096 items x 96 KiB = 3 GiB at N = 8).
+    collate = None
+    if world > 1 and not args.no_collate:
+        cb = min(batch, 4096)
+        local_ct = d_out[:cb].contiguous()
+        g = seb.all_gather_ciphertexts(local_ct, cb * world)  # warm-up (NCCL channel setup)
+        ok = bool(torch.equal(g[rank * cb:(rank + 1) * cb], local_ct))
+        del g
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(3):
+            g = seb.all_gather_ciphertexts(local_ct, cb * world)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        t3 = torch.tensor([c0.elapsed_time(c1) / 3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        cms = float(t3.item())
+        recv = (world - 1) * cb * np_ * 2 * n * 4
+        collate = {"what": "one NCCL all-gather of finished ciphertexts to every rank (off the throughput path)",
+                   "items_per_gpu": cb, "ms": cms, "received_GB_per_gpu": recv / 1e9,
+                   "receive_GBps_per_gpu": recv / 1e9 / (cms * 1e-3), "own_shard_intact": ok,
+                   "ciphertexts_per_s_if_collated": world * cb / (cms * 1e-3)}
+        del g
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -396,6 +424,8 @@ def run_b200_arm(args) -> None:
                        "items": batch, "max_abs_err": verify_err, "tolerance": 0.1, "ok": verify_err < 0.1},
             "kernels_ms": {nm: float(v) for nm, v in zip(names, avg)},
             "roofline": roofline, "ntt_microbench": ntt_micro, "cpu_baseline": cpu}
+    if collate is not None:
+        line["collate"] = collate
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -426,6 +456,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=0, help="ciphertexts per GPU per e2e step (default: --batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-collate", action="store_true", help="skip the N>1 all-gather collation measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

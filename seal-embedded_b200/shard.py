@@ -65,16 +65,25 @@ def all_gather_ciphertexts(local, batch: int, group=None):
     mine = shard_range(batch, rank, world)
     if local.shape[0] != mine.count:
         raise ValueError(f"rank {rank} holds {local.shape[0]} items, shard_range says {mine.count}")
-    cap = max(shard_range(batch, r, world).count for r in range(world))
+    counts = [shard_range(batch, r, world).count for r in range(world)]
+    cap = max(counts)
     if cap == 0:
         return local.new_empty((0,) + tuple(local.shape[1:]))
+    if min(counts) == cap:
+        # equal shards (the usual case): one collective straight into the result, no padding, no concatenation
+        out = local.new_empty((batch,) + tuple(local.shape[1:]))
+        try:
+            dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+            return out
+        except (RuntimeError, NotImplementedError):  # a backend without the flat variant
+            del out
     padded = local
     if mine.count < cap:
         padded = local.new_zeros((cap,) + tuple(local.shape[1:]))
         padded[: mine.count] = local
     pieces = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(pieces, padded.contiguous(), group=group)
-    return torch.cat([pieces[r][: shard_range(batch, r, world).count] for r in range(world)], dim=0)
+    return torch.cat([pieces[r][: counts[r]] for r in range(world)], dim=0)
 
 
 def bind_to_gpu_numa(gpu_index: int) -> str:
