@@ -188,7 +188,7 @@ struct seb_ctx
     uint32_t rej_cap = 0;  // capacity of the uniform sampler's per-ciphertext reject lists (n/8)
     // resident tables
     seb_oct *d_roots    = nullptr;  // [np][seb_table_octs]: per-pass twiddle tables
-    double2 *d_tw       = nullptr;  // [n]
+    double2 *d_tw       = nullptr;  // [n] natural order + [7][n/8] pass-0 copies (seb_encode.cuh)
     uint16_t *d_src_map = nullptr;  // [n]
     seb_oct *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n/4] Shoup pairs, epilogue order
     seb_oct *d_ntt_s = nullptr;                  // [np][n/4] Shoup pairs, epilogue order
@@ -318,7 +318,7 @@ static int build_tables(seb_ctx *c)
     }
 
     // IFFT twiddles from the host libm, same expression as fft.c:27-45 (+ conj at fft.c:129)
-    std::vector<double2> tw(n);
+    std::vector<double2> tw(seb_enc_tw_entries(n));
     const size_t m = 2 * n;
     tw[0]          = make_double2(1.0, 0.0);
     for (size_t i = 1; i < n; i++)
@@ -327,8 +327,9 @@ static int build_tables(seb_ctx *c)
         const double angle = 2 * M_PI * (double)k / (double)m;
         tw[i]              = make_double2(cos(angle), -sin(angle));
     }
-    CU(cudaMalloc(&c->d_tw, n * sizeof(double2)));
-    CU(cudaMemcpy(c->d_tw, tw.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+    seb_host_build_enc_tw0(n, tw.data());  // pass-0 roots again, in the order the encode kernel's lanes read them
+    CU(cudaMalloc(&c->d_tw, tw.size() * sizeof(double2)));
+    CU(cudaMemcpy(c->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
 
     // index map (ckks_common.c:32-68) inverted: position -> slot
     std::vector<uint16_t> src(n), fwd(n);

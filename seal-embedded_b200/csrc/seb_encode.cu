@@ -44,7 +44,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
     extern __shared__ double esm[];
     double *sre   = esm;
     double *sim   = esm + NL;
-    float *svals  = reinterpret_cast<float *>(esm + 2 * NL);  // n/2 floats: the message, zero padded
+    float *svals  = reinterpret_cast<float *>(esm + 2 * NL);  // the message, zero padded, skewed (enc_vskew)
 
     const int t            = threadIdx.x;
     const size_t b         = blockIdx.x / CL;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
 #pragma unroll
         for (int k = 0; k < PER; k++) v[k] = (t + k * T) < vlen ? __ldg(vals + t + k * T) : 0.0f;
 #pragma unroll
-        for (int k = 0; k < PER; k++) svals[t + k * T] = v[k];
+        for (int k = 0; k < PER; k++) svals[enc_vskew<LOGN>((uint32_t)(t + k * T))] = v[k];
     }
     __syncthreads();
 
@@ -126,11 +126,14 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+size_t seb_enc_tw_entries(size_t n) { return enc_tw_entries(n); }
+void seb_host_build_enc_tw0(size_t n, double2 *tw) { enc_build_tw0(n, tw); }
+
 template <int LOGN, int CL>
 static cudaError_t encode_cfg()
 {
     return cudaFuncSetAttribute(k_encode<LOGN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * ((1 << LOGN) / 2)));
+                                (int)(sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * EncVals<LOGN>::WORDS));
 }
 
 cudaError_t seb_encode_configure(int logn)
@@ -154,7 +157,7 @@ static cudaError_t encode_launch(const float *values, size_t v_stride, int vlen,
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = dim3((unsigned)batch * CL);
     cfg.blockDim           = dim3((1 << LOGN) / CL / ENC_E);
-    cfg.dynamicSmemBytes   = sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * ((1 << LOGN) / 2);
+    cfg.dynamicSmemBytes   = sizeof(double) * 2 * ((1 << LOGN) / CL) + sizeof(float) * EncVals<LOGN>::WORDS;
     cfg.stream             = st;
     cudaLaunchAttribute attr[1];
     attr[0].id               = cudaLaunchAttributeClusterDimension;

@@ -23,10 +23,48 @@ __device__ __forceinline__ uint32_t enc_swz(uint32_t i)
     return i ^ ((i >> 4) & 7u) ^ (((i >> 6) & 1u) << 3);
 }
 
+// Layout of the staged message in shared memory.  Pass 0 gathers values[src_map[pos]] for 8 consecutive
+// positions per thread; the slots a warp asks for in one instruction are far from random (the index map is
+// 3^i mod 2n, bit-reversed): in a linear layout they collide 2- (n = 1024) to 32-way (n = 16384) on the 32
+// banks.  Skewing slot s to s + (s >> (log2 n - 9)) makes every gather instruction of every warp conflict
+// free at every degree (exhaustive check: tests/test_host_logic.py::test_encode_gather_conflict_free).
+template <int LOGN>
+__host__ __device__ __forceinline__ constexpr uint32_t enc_vskew(uint32_t s)
+{
+    return s + (s >> (LOGN - 9));
+}
+// floats of shared memory the staged message occupies
+template <int LOGN>
+struct EncVals
+{
+    static constexpr uint32_t WORDS = (enc_vskew<LOGN>((1u << (LOGN - 1)) - 1u) + 4u) & ~3u;
+};
+
+// Pass-0 twiddles.  Stage r of pass 0 (butterfly distance 2^r) gives the thread that owns positions
+// 8g .. 8g+7 the roots tw[(n >> (r+1)) + (g << (2-r)) + m], m < 2^(2-r): seven per thread, all distinct
+// across threads, at a lane stride of 64 / 32 / 16 bytes in the natural table — up to 16 cache lines per
+// 128-bit load instruction.  They are therefore stored a second time behind the natural table
+// (tw[n + slot*(n/8) + g], slot = 0..3 for r = 0, 4..5 for r = 1, 6 for r = 2) so that the lanes of a warp read
+// consecutive 16-byte entries.  Later passes share each root between >= 8 consecutive threads and use
+// the natural table.
+#define ENC_TW0_SLOTS 7
+__host__ __device__ __forceinline__ constexpr int enc_tw0_slot(int r, int m) { return r == 0 ? m : r == 1 ? 4 + m : 6; }
+// entries of the whole table: n natural + 7 * n/8 pass-0 copies
+__host__ __device__ __forceinline__ constexpr size_t enc_tw_entries(size_t n) { return n + ENC_TW0_SLOTS * (n / 8); }
+template <class D2>
+inline void enc_build_tw0(size_t n, D2 *tw)  // tw[0..n) filled; appends the pass-0 copies
+{
+    const size_t G = n / 8;
+    for (size_t g = 0; g < G; g++)
+        for (int r = 0; r < 3; r++)
+            for (int m = 0; m < (1 << (2 - r)); m++)
+                tw[n + (size_t)enc_tw0_slot(r, m) * G + g] = tw[(n >> (r + 1)) + (g << (2 - r)) + m];
+}
+
 // one pass = R fused Gentleman-Sande stages starting at butterfly distance S = 2^LS
 // (fft.c:119-143: vec[k] = u + v; vec[k+tt] = (u - v) * s)
-// svals: the message of this ciphertext zero-padded to n/2 floats (staged in shared memory by the
-// kernel: the scatter of ckks_common.c:139-153 is done as a gather from it)
+// svals: the message of this ciphertext zero-padded to n/2 floats, value i at svals[enc_vskew(i)] (staged
+// in shared memory by the kernel: the scatter of ckks_common.c:139-153 is done as a gather from it)
 template <int LOGN, int LOGNL, int P>
 __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E], double *sre, double *sim,
                                          const int t, const uint32_t cta_pos0, const float *svals,
@@ -57,7 +95,7 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
             for (int j = 0; j < 8; j++)
             {
                 const uint32_t slot = (mw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                xr[i * 8 + j]       = (double)svals[slot];
+                xr[i * 8 + j]       = (double)svals[enc_vskew<LOGN>(slot)];
                 xi[i * 8 + j]       = 0.0;
             }
         }
@@ -80,7 +118,10 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
 #pragma unroll
             for (int m = 0; m < (1 << (R - r - 1)); m++)
             {
-                const double2 s = __ldg(tw + h + jbase + m);
+                // pass 0: this thread's own roots, from the lane-contiguous copy behind the natural table
+                const double2 s = (P == 0) ? __ldg(tw + (1u << LOGN) + (uint32_t)enc_tw0_slot(r, m) * ((1u << LOGN) / 8) +
+                                                   (cta_pos0 >> 3) + g)
+                                           : __ldg(tw + h + jbase + m);
 #pragma unroll
                 for (int k = 0; k < (1 << r); k++)
                 {

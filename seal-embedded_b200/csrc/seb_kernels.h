@@ -27,13 +27,16 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
 
 // ---- encode (seb_encode.cu) ----
 // values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);
-// src_map[pos] = slot whose value lands on position pos; tw[i] = IFFT twiddle (re, im), i in [1,n)
+// src_map[pos] = slot whose value lands on position pos; tw[i] = IFFT twiddle (re, im), i in [1,n), followed by
+// the pass-0 copies seb_host_build_enc_tw0 appends (seb_enc_tw_entries(n) entries in all)
 // fail[b] is set when item b overflows int64; mag[b] (may be NULL; zeroed by the caller) receives
 // max |coefficient| of item b clipped to 2^32 - 1
 cudaError_t seb_launch_encode(int logn, const float *values, size_t v_stride, int vlen, const uint16_t *src_map,
                               const double2 *tw, double n_inv, int64_t *pt, int *fail, uint32_t *mag, int batch,
                               cudaStream_t st);
 cudaError_t seb_encode_configure(int logn);
+size_t seb_enc_tw_entries(size_t n);
+void seb_host_build_enc_tw0(size_t n, double2 *tw);  // tw[0..n) filled on entry
 
 // ---- NTT + encrypt (seb_encrypt.cu) ----
 // roots: per prime, the per-pass twiddle tables of seb_build_tw (seb_table_octs(logn) octs each);

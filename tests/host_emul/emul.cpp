@@ -224,8 +224,8 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
     int bad             = 0;
     g_emul_mag          = 0;
     std::vector<double> sre[2], sim[2];
-    std::vector<float> svals(N / 2, 0.0f);  // the kernel's staged, zero-padded message
-    for (int i = 0; i < vlen && i < N / 2; i++) svals[i] = vals[i];
+    std::vector<float> svals(EncVals<LOGN>::WORDS, 0.0f);  // the kernel's staged, zero-padded, skewed message
+    for (int i = 0; i < vlen && i < N / 2; i++) svals[enc_vskew<LOGN>((uint32_t)i)] = vals[i];
     for (int rank = 0; rank < CL; rank++)
     {
         sre[rank].assign(NL, 1e300);
@@ -267,7 +267,11 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
 extern "C" int emul_encode(int logn, const float *vals, int vlen, const uint16_t *src_map, const double *tw,
                            double n_inv, int64_t *out)
 {
-    const double2 *t2 = reinterpret_cast<const double2 *>(tw);
+    const size_t n = (size_t)1 << logn;
+    std::vector<double2> ext(enc_tw_entries(n));  // natural table + the pass-0 copies the kernel reads
+    memcpy(ext.data(), tw, n * sizeof(double2));
+    enc_build_tw0(n, ext.data());
+    const double2 *t2 = ext.data();
     switch (logn)
     {
         case 10: return enc_emul<10, 1>(vals, vlen, src_map, t2, n_inv, out);
@@ -277,6 +281,32 @@ extern "C" int emul_encode(int logn, const float *vals, int vlen, const uint16_t
         case 14: return enc_emul<14, 2>(vals, vlen, src_map, t2, n_inv, out);
     }
     return -1;
+}
+
+// physical word of message slot s in the staged (skewed) layout, and the size of that buffer
+extern "C" uint32_t emul_enc_vskew(int logn, uint32_t slot)
+{
+    switch (logn)
+    {
+        case 10: return enc_vskew<10>(slot);
+        case 11: return enc_vskew<11>(slot);
+        case 12: return enc_vskew<12>(slot);
+        case 13: return enc_vskew<13>(slot);
+        case 14: return enc_vskew<14>(slot);
+    }
+    return 0;
+}
+extern "C" uint32_t emul_enc_vwords(int logn)
+{
+    switch (logn)
+    {
+        case 10: return EncVals<10>::WORDS;
+        case 11: return EncVals<11>::WORDS;
+        case 12: return EncVals<12>::WORDS;
+        case 13: return EncVals<13>::WORDS;
+        case 14: return EncVals<14>::WORDS;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

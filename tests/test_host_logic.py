@@ -40,6 +40,10 @@ def E(emul):
     emul.emul_encode.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_double),
                                  C.c_double, C.POINTER(C.c_int64)]
     emul.emul_encode_mag.restype = C.c_uint32
+    emul.emul_enc_vskew.argtypes = [C.c_int, C.c_uint32]
+    emul.emul_enc_vskew.restype = C.c_uint32
+    emul.emul_enc_vwords.argtypes = [C.c_int]
+    emul.emul_enc_vwords.restype = C.c_uint32
     emul.emul_keccak.argtypes = [C.POINTER(C.c_uint64)]
     emul.emul_prng_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64)]
     emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
@@ -204,6 +208,31 @@ def _src_map(orc, n):
     src[im[: n // 2]] = np.arange(n // 2, dtype=np.uint16)
     src[im[n // 2:]] = np.arange(n // 2, dtype=np.uint16)
     return src
+
+
+@pytest.mark.parametrize("logn", LOGNS)
+def test_encode_gather_conflict_free(logn, E, orc):
+    """Pass 0 of the encode gathers values[src_map[pos]] for 8 consecutive positions per thread from the
+    message staged in shared memory.  enc_vskew is injective, stays inside EncVals::WORDS, and makes the 32
+    lanes of every warp hit 32 distinct banks in every gather instruction (a linear layout collides up to
+    32-way at n = 16384); the staging stores stay at most 2-way."""
+    n = 1 << logn
+    src = _src_map(orc, n).astype(np.int64)
+    phys = np.array([E.emul_enc_vskew(logn, s) for s in range(n // 2)], dtype=np.int64)
+    assert len(set(phys.tolist())) == n // 2 and phys.max() < E.emul_enc_vwords(logn)
+    nl = n // 2 if logn == 14 else n  # positions per CTA (n = 16384 runs as a 2-CTA cluster)
+    T = nl // 8
+    worst_linear = 0
+    for cta0 in range(0, n, nl):
+        for w0 in range(0, T, 32):
+            g = np.arange(w0, min(w0 + 32, T))
+            for j in range(8):
+                slots = src[cta0 + 8 * g + j]
+                assert np.bincount(phys[slots] % 32, minlength=32).max() == 1, (logn, cta0, w0, j)
+                worst_linear = max(worst_linear, int(np.bincount(slots % 32, minlength=32).max()))
+    assert worst_linear == {10: 2, 11: 4, 12: 8, 13: 16, 14: 32}[logn]
+    for i0 in range(0, n // 2, 32):  # staging: 32 consecutive slots per store instruction
+        assert np.bincount(phys[i0:i0 + 32] % 32, minlength=32).max() <= 2
 
 
 @pytest.mark.parametrize("logn", LOGNS)
