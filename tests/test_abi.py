@@ -134,3 +134,23 @@ def test_header_compiles_as_c_and_cxx(tmp_path):
                    check=True)
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-x", "c++", "-I", inc, "-c", str(src), "-o",
                     str(tmp_path / "t2.o")], check=True)
+
+
+def _build_demo(tmp_path):
+    exe = str(tmp_path / "se_encrypt_demo")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", "se_encrypt_demo.c"),
+                    "-I", os.path.join(ROOT, "include"), "-L", PKG, "-lseal_embedded_b200", f"-Wl,-rpath,{PKG}", "-o", exe],
+                   check=True)
+    return exe
+
+
+def test_c_application_links_against_the_library(seb, tmp_path):
+    """examples/se_encrypt_demo.c is a plain C11 program written against the reference's API names; it must
+    compile warning-free against include/ and link against the shared library (running it needs a GPU:
+    tests/test_gpu_parity.py::test_c_application_dropin)."""
+    seb.build_library()
+    exe = _build_demo(tmp_path)
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True, check=True).stdout
+    assert "libseal_embedded_b200.so" in out
+    r = subprocess.run([exe], capture_output=True, text=True)  # no arguments: usage, exit code 2, no CUDA call
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -765,6 +765,47 @@ def test_se_api_dropin(asym, seb, torch_cuda, oracle_mod, orc, tmp_path, monkeyp
         se.se_cleanup()
 
 
+@pytest.mark.parametrize("mode,n,np_", [("asym", 4096, 3), ("sym", 1024, 1), ("sym", 8192, 4)])
+def test_c_application_dropin(mode, n, np_, seb, torch_cuda, oracle_mod, orc, tmp_path):
+    """The drop-in claim end to end, from C: examples/se_encrypt_demo.c (plain C11 against the reference's
+    API names, key files in ./adapter_output_data like fileops.c:140-204) is compiled with gcc, linked against
+    the library and run as its own process; the bytes its send callback received and the batch extension's
+    output equal the oracle's ciphertexts."""
+    import subprocess
+    from test_abi import _build_demo
+
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    primes = orc.primes(n, np_)
+    oracle_mod.write_key_files(str(tmp_path), n, primes, sk, pk0, pk1)
+    exe = _build_demo(tmp_path)
+    out_file = tmp_path / "ct.bin"
+    r = subprocess.run([exe, mode, str(n), str(np_), str(out_file)], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+    got = np.fromfile(out_file, dtype=np.uint32)
+    assert got.size == 4 * np_ * 2 * n
+    got = got.reshape(4, np_, 2, n)
+    vlen = n // 2
+    i = np.arange(vlen)
+    msgs = [(((i + b) % 17) - 8).astype(np.float32) + (i.astype(np.float32) / np.float32(1024.0)) for b in range(3)]
+    seed = np.full(64, 0x5A, np.uint8)
+    share = np.full(64, 0xA5, np.uint8)
+
+    def expect(v, sd, ss):
+        if mode == "asym":
+            ok, ct = orc.encrypt_asym(n, np_, v, sd, pk0, pk1)
+        else:
+            ok, ct = orc.encrypt_sym(n, np_, v, ss, sd, sk)
+        assert ok
+        return ct
+
+    assert np.array_equal(got[0], expect(msgs[0], seed, share))
+    for b in range(3):
+        sd, ss = seed.copy(), share.copy()
+        sd[0], ss[0] = b, b + 100
+        assert np.array_equal(got[1 + b], expect(msgs[b], sd, ss)), b
+
+
 def test_golden_fixtures(seb, torch_cuda, oracle_mod, ctxs):
     """Committed vectors generated from the compiled reference (tests/golden/make_golden.py)."""
     torch = torch_cuda
