@@ -175,6 +175,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pcie_link(gpu_index: int) -> dict | None:
+    """Current / maximum PCIe link of the GPU (the e2e number is bound by it; boxes of one pool differ)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        return {"gen": pynvml.nvmlDeviceGetCurrPcieLinkGeneration(h), "width": pynvml.nvmlDeviceGetCurrPcieLinkWidth(h),
+                "max_gen": pynvml.nvmlDeviceGetMaxPcieLinkGeneration(h), "max_width": pynvml.nvmlDeviceGetMaxPcieLinkWidth(h)}
+    except Exception:  # noqa: BLE001 - informational only
+        return None
+
+
 def hbm_peak() -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,6 +338,8 @@ def run_b200_arm(args) -> None:
         e2e = {"value": world * eb / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "batch_per_gpu": eb, "h2d_bytes_per_step": eb * (vlen * 4 + 64),
                "d2h_bytes_per_step": eb * (np_ * 2 * n * 4 + 4), "matches_device_path": same,
+               "d2h_GBps": eb * (np_ * 2 * n * 4 + 4) * world / (e2e_ms * 1e-3) / 1e9 / world,
+               "pcie": pcie_link(local),
                "api": "seb_encrypt_asym_host (pinned host buffers, 2 chunks in flight)", "cpu_binding": numa}
 
     # ---- optional collation (BASELINE north_star: "a single NCCL all-gather only to collate outputs"): every
