@@ -426,6 +426,21 @@ def run_b200_arm(args) -> None:
         arm.close()
         cpu = arm.describe(arm.cores * arm.items * len(secs) / sum(secs))
 
+    # NTT-only CPU baseline: the reference's ntt_inpl, one host core, roots prebuilt
+    if cpu is not None:
+        try:
+            from oracle import oracle as O
+
+            if O.have_reference():
+                ref = O.ReferenceLib()
+                reps = 2000
+                ref.ntt_loop_seconds(n, np_, 0, 50)
+                secs_ntt = ref.ntt_loop_seconds(n, np_, 0, reps)
+                ntt_micro["cpu_reference"] = {"ntt_per_sec": reps / secs_ntt, "cores": 1, "kind": "reference",
+                                              "sample": f"{reps} x ntt_inpl n={n} on one core, root table built once"}
+        except Exception as e:  # noqa: BLE001 - a reported baseline, never fatal
+            ntt_micro["cpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",

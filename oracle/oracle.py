@@ -356,6 +356,9 @@ class ReferenceLib:
         L.ref_sample_uniform.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, _u8p, C.c_uint64, _u32p]
         L.ref_sample_uniform.restype = C.c_uint64
         L.ref_ntt.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, _u32p]
+        if hasattr(L, "ref_ntt_loop"):
+            L.ref_ntt_loop.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, _u32p, C.c_size_t]
+            L.ref_ntt_loop.restype = C.c_double
         L.ref_reduce_pte.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, _i64p, _u32p]
         L.ref_encrypt_sym_c1a.argtypes = [C.c_size_t, C.c_size_t, _u8p, _u8p, _u8p, _f32p, C.c_size_t, _u32p]
         L.ref_encrypt_sym_c1a.restype = C.c_int
@@ -455,6 +458,11 @@ class ReferenceLib:
         v = np.array(vec, dtype=np.uint32, copy=True)
         self.lib.ref_ntt(n, np_, prime_idx, _ptr(v, _u32p))
         return v
+
+    def ntt_loop_seconds(self, n: int, np_: int, prime_idx: int, reps: int) -> float:
+        """Seconds for `reps` calls of the reference's ntt_inpl on one core (roots built once, outside)."""
+        v = np.arange(n, dtype=np.uint32)
+        return float(self.lib.ref_ntt_loop(n, np_, prime_idx, _ptr(v, _u32p), reps))
 
     def reduce_pte(self, n: int, np_: int, prime_idx: int, pte: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(pte, dtype=np.int64)

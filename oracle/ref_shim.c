@@ -219,6 +219,24 @@ void ref_ntt(size_t n, size_t np, size_t prime_idx, uint32_t *vec)
     delete_parameters(&parms);
 }
 
+/* timing loop for the NTT-only CPU baseline (SURVEY 8d "(ii) NTT-only loop"): the root table is built once,
+ * then ntt_inpl (ntt.c:168-189) runs `reps` times on the same buffer; seconds returned */
+double ref_ntt_loop(size_t n, size_t np, size_t prime_idx, uint32_t *vec, size_t reps)
+{
+    Parms parms;
+    local_parms(n, np, 0, &parms);
+    for (size_t i = 0; i < prime_idx; i++) next_modulus(&parms);
+    ZZ *roots = calloc(2 * n, sizeof *roots);
+    ntt_roots_initialize(&parms, roots);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (size_t r = 0; r < reps; r++) ntt_inpl(&parms, roots, vec);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(roots);
+    delete_parameters(&parms);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 void ref_reduce_pte(size_t n, size_t np, size_t prime_idx, const int64_t *pte, uint32_t *out)
 {
     Parms parms;
