@@ -556,6 +556,39 @@ def test_contexts_of_several_degrees_coexist(seb, torch_cuda, ctxs):
         small.close()
 
 
+def test_context_lifecycle_does_not_leak(seb, torch_cuda, oracle_mod, orc):
+    """seb_create / work / seb_destroy twenty times over (both encryption types, device and host-pointer
+    calls, the seed-compressed scratch, the verifier): free device memory returns to where it started."""
+    torch = torch_cuda
+    n, np_ = 2048, 1
+    sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+    vals = oracle_mod.make_values(64, n // 2, seed=5)
+    seeds = oracle_mod.make_seeds(64, b"leak")
+    sseeds = oracle_mod.make_seeds(64, b"leak-share")
+
+    def cycle():
+        for asym in (True, False):
+            ctx = seb.Context(n, np_, asym, device=0)
+            ctx.set_secret_key(sk)
+            if asym:
+                ctx.set_public_key(pk0, pk1)
+                ctx.encrypt_asym_host(vals, seeds)
+            else:
+                ctx.encrypt_sym_host(vals, sseeds, seeds)
+                ctx.encrypt_sym_seedct_host(vals, sseeds, seeds)
+            ctx.close()
+
+    cycle()  # first use pays for lazily created CUDA state (module load, constant banks)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(20):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), f"{(free0 - free1) >> 20} MiB of device memory not returned"
+
+
 def test_edge_cases_and_errors(seb, torch_cuda, oracle_mod, orc):
     """Empty batch, empty message (vlen = 0 encrypts the zero message), and the error behaviour of the
     seb_* layer: missing key material, vlen beyond n/2, key coefficients outside [0, q)."""
