@@ -148,3 +148,35 @@ __device__ __forceinline__ void seb_stg_stream(uint4 *p, const uint4 &v)
                  : "memory");
 }
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// named barrier over an aligned group of W threads of a CTA of T threads: hardware barrier 1 + t/W.
+// Hardware barriers are an occupancy resource and ptxas reserves all 16 for a kernel whose barrier number is a
+// register.  IMM = true selects the number with a switch over immediates, so exactly T/W + 1 are reserved (the
+// encode at n = 1024 runs 8 CTAs per SM and lost 13 % with 16 reserved); IMM = false keeps the register form,
+// which is 2 % faster where occupancy is not at stake (the NTT at n >= 8192, 2-4 CTAs per SM).
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <int W, int T, bool IMM>
+__device__ __forceinline__ void seb_group_barrier(const int t)
+{
+    static_assert(T % W == 0 && T / W >= 1 && T / W <= 15, "named barriers 1..15");
+    if constexpr (!IMM)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + t / W), "n"(W) : "memory");
+    else
+    {
+#define SEB_BAR_CASE(G)                                                                          \
+    case G:                                                                                      \
+        if (G < T / W) asm volatile("bar.sync %0, %1;" ::"n"(G + 1), "n"(W) : "memory");          \
+        break;
+        switch (t / W)
+        {
+            SEB_BAR_CASE(0) SEB_BAR_CASE(1) SEB_BAR_CASE(2) SEB_BAR_CASE(3) SEB_BAR_CASE(4) SEB_BAR_CASE(5)
+            SEB_BAR_CASE(6) SEB_BAR_CASE(7) SEB_BAR_CASE(8) SEB_BAR_CASE(9) SEB_BAR_CASE(10) SEB_BAR_CASE(11)
+            SEB_BAR_CASE(12) SEB_BAR_CASE(13) SEB_BAR_CASE(14)
+            default: break;
+        }
+#undef SEB_BAR_CASE
+    }
+}
+#endif

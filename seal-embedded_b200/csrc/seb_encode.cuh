@@ -149,6 +149,32 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
     }
 }
 
+// Barrier scope between pass P and pass P+1 (thread t owns group t in the radix-8 passes).  Pass 1 reads, for
+// block t/8, what the eight threads 8*(t/8) .. +7 wrote in pass 0: warp-local.  Pass 2 reads, for block t/64,
+// what threads 64*(t/64) .. +63 wrote in pass 1: local to an aligned group of 64 threads, synchronised with a
+// named barrier (1 + group; CTAs of 1024 threads use groups of 128 to stay within hardware barriers 1..15).
+// Later boundaries span 512 threads or the CTA.  Returns 0 for a CTA-wide barrier, else the unit's width.
+// Checked exhaustively by tests/test_host_logic.py::test_encode_barrier_scopes.
+__host__ __device__ __forceinline__ constexpr int enc_sync_width(int lognl, int p)
+{
+    return p == 0 ? 32 : p == 1 ? (((1 << lognl) / ENC_E) > 960 ? 128 : 64) : 0;
+}
+template <int LOGNL, int P>
+__device__ __forceinline__ void enc_sync(const int t)
+{
+    constexpr int W = enc_sync_width(LOGNL, P);
+    if constexpr (W == 32)
+        __syncwarp();
+    else if constexpr (W > 32)
+    {
+#if defined(__CUDACC__)
+        seb_group_barrier<W, (1 << LOGNL) / ENC_E, true>(t);
+#endif
+    }
+    else
+        __syncthreads();
+}
+
 template <int LOGN, int LOGNL, int P>
 struct EncRun
 {
@@ -159,7 +185,7 @@ struct EncRun
         enc_pass<LOGN, LOGNL, P>(xr, xi, sre, sim, t, cta_pos0, svals, src_map, tw);
         if (P + 1 < enc_npass(LOGNL))
         {
-            __syncthreads();
+            enc_sync<LOGNL, P>(t);
             EncRun<LOGN, LOGNL, (P + 1 < enc_npass(LOGNL) ? P + 1 : P)>::run(xr, xi, sre, sim, t, cta_pos0, svals,
                                                                              src_map, tw);
         }

@@ -248,7 +248,7 @@ struct NttSync
     static constexpr int GROUP = LOGN == 14 ? 128 : 64;  // threads per named barrier (SEB_SYNC_GROUP only)
 };
 
-template <int SCOPE, int GROUP>
+template <int SCOPE, int GROUP, int T>
 __device__ __forceinline__ void seb_ntt_sync(const int t)
 {
     if (SCOPE == SEB_SYNC_WARP)
@@ -258,7 +258,7 @@ __device__ __forceinline__ void seb_ntt_sync(const int t)
 #if defined(SEB_UBENCH_CTA_BARRIERS)  // tools/ubench A/B switch only
         __syncthreads();
 #elif defined(__CUDACC__)
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + t / GROUP), "n"(GROUP) : "memory");
+        seb_group_barrier<GROUP, T, false>(t);
 #endif
     }
     else
@@ -338,7 +338,7 @@ struct SebNttRun
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
         if (P + 1 < NttPlan<LOGN>::NPASS)
         {
-            seb_ntt_sync<NttSync<LOGN, P>::value, NttSync<LOGN, P>::GROUP>(t);
+            seb_ntt_sync<NttSync<LOGN, P>::value, NttSync<LOGN, P>::GROUP, (1 << LOGN) / SEB_E>(t);
             SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
                                                                                               load);
         }

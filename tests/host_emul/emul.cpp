@@ -283,6 +283,19 @@ extern "C" int emul_encode(int logn, const float *vals, int vlen, const uint16_t
     return -1;
 }
 
+// local position of element j of slot i of thread t in encode pass `pass` (-1 outside the plan); lognl = log2 of
+// the positions one CTA holds.  Mirrors enc_pass's addressing (g = t + i*T).
+extern "C" int64_t emul_enc_pos(int lognl, int pass, uint32_t t, uint32_t i, uint32_t j)
+{
+    if (pass >= enc_npass(lognl)) return -1;
+    const int R = enc_r(lognl, pass), LS = 3 * pass;
+    const uint32_t T = (1u << lognl) / ENC_E;
+    if (i >= (uint32_t)(ENC_E >> R) || j >= (1u << R) || t >= T) return -1;
+    const uint32_t g = t + i * T, off = g & ((1u << LS) - 1u), blk = g >> LS;
+    return (int64_t)(((blk << (LS + R)) | off) | (j << LS));
+}
+extern "C" int emul_enc_sync_width(int lognl, int pass) { return enc_sync_width(lognl, pass); }
+
 // physical word of message slot s in the staged (skewed) layout, and the size of that buffer
 extern "C" uint32_t emul_enc_vskew(int logn, uint32_t slot)
 {

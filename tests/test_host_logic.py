@@ -44,6 +44,9 @@ def E(emul):
     emul.emul_enc_vskew.restype = C.c_uint32
     emul.emul_enc_vwords.argtypes = [C.c_int]
     emul.emul_enc_vwords.restype = C.c_uint32
+    emul.emul_enc_pos.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    emul.emul_enc_pos.restype = C.c_int64
+    emul.emul_enc_sync_width.argtypes = [C.c_int, C.c_int]
     emul.emul_keccak.argtypes = [C.POINTER(C.c_uint64)]
     emul.emul_prng_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint64)]
     emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
@@ -208,6 +211,40 @@ def _src_map(orc, n):
     src[im[: n // 2]] = np.arange(n // 2, dtype=np.uint16)
     src[im[n // 2:]] = np.arange(n // 2, dtype=np.uint16)
     return src
+
+
+@pytest.mark.parametrize("lognl", [10, 11, 12, 13])
+def test_encode_barrier_scopes(lognl, E):
+    """Every encode pass touches every position of the CTA exactly once, and wherever the kernel synchronises
+    less than the CTA between two passes (enc_sync_width: a warp after pass 0, a named barrier over 64 or 128
+    threads after pass 1), every position a thread reads in the later pass was written in the earlier one by
+    a thread of the same unit.  Named barriers stay within hardware barriers 1..15."""
+    nl = 1 << lognl
+    T = nl // 8
+    npass = (lognl + 2) // 3
+    owner = []
+    for p in range(npass):
+        R = 3 if lognl - 3 * p >= 3 else lognl - 3 * p
+        own = np.full(nl, -1, np.int64)
+        for t in range(T):
+            for i in range(8 >> R):
+                for j in range(1 << R):
+                    pos = E.emul_enc_pos(lognl, p, t, i, j)
+                    assert 0 <= pos < nl and own[pos] == -1
+                    own[pos] = t
+        assert (own >= 0).all()
+        owner.append(own)
+    widths = []
+    for p in range(npass - 1):
+        w = E.emul_enc_sync_width(lognl, p)
+        if w:
+            shift = w.bit_length() - 1
+            assert 1 << shift == w
+            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (lognl, p, w)
+            if w > 32:
+                assert T % w == 0 and T // w <= 15
+        widths.append(w)
+    assert widths[:2] == [32, 128 if T > 960 else 64] and all(w == 0 for w in widths[2:])
 
 
 @pytest.mark.parametrize("logn", LOGNS)
