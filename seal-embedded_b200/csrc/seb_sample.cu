@@ -8,8 +8,16 @@
 // PRNG consumption order is the reference's: every prng_fill_buffer call is
 // a fresh SHAKE256(seed || LE64(counter)) and bumps the counter, including the data-dependent
 // single-value redraws of the rejection samplers.
+#include <stdlib.h>
+
 #include "seb_kernels.h"
 #include "seb_sample.cuh"
+
+// batches up to this size take the warp-cooperative bulk sampler: measured 1.4x faster at 2048 items and 0.9x at
+// 4096, at n = 1024, 4096 and 16384 alike (profiles/r01_ab_uniform_coop.txt)
+#ifndef SEB_UNIFORM_COOP_MAX_BATCH
+#define SEB_UNIFORM_COOP_MAX_BATCH 3072
+#endif
 
 __device__ __forceinline__ void load_seed(const uint8_t *seeds, size_t b, uint64_t (&s)[8])
 {
@@ -216,6 +224,145 @@ __global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__
     rej_cnt[b] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// the same bulk squeeze for SMALL batches: one WARP per ciphertext, the Keccak state spread over 25 lanes
+// ---------------------------------------------------------------------------------------------
+// A 4n-byte squeeze is 4n/136 DEPENDENT permutations (121 at n = 4096, 482 at n = 16384, times the primes: the
+// counter is chained).  One thread runs a permutation in ~6.9 us, so a lone symmetric se_encrypt call spent
+// 2.4 ms here against 1.2 ms for the whole call on a CPU core (profiles/r01_latency_single_call.txt).  With
+// lane 5y+x holding A[x][y] a round is 16 ALU operations and 18 shuffles instead of 180 ALU operations issued in
+// order by one thread: 2.4x lower latency per permutation (2.9 us) at several times the issue slots per permutation,
+// so it wins whenever the batch leaves the machine under-filled (seb_launch_uniform picks by batch size).
+// Output, reject lists and counters are exactly those of k_uniform_bulk (sample.c:39-57).
+struct SebCoopLane
+{
+    int col[4];      // the other four lanes of this lane's column
+    int xm1, xp1;    // lanes (x-1, y) and (x+1, y)
+    int s0, s1, s2;  // pre-pi source lanes of B[x][y], B[x+1][y], B[x+2][y]
+    uint32_t rot;    // rho offset of the word this lane holds
+};
+
+__device__ __forceinline__ SebCoopLane seb_coop_setup(const int lane)
+{
+    // rho offsets indexed by lane = 5y + x (the SRC/ROT columns of seb_keccak.cuh's round macro)
+    const uint32_t rho[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    SebCoopLane c;
+    const int l = lane < 25 ? lane : 0;  // lanes 25..31 shadow lane 0 (their results are never used)
+    const int x = l % 5, y = l / 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) c.col[k] = (l + 5 * (k + 1)) % 25;
+    c.xm1 = 5 * y + (x + 4) % 5;
+    c.xp1 = 5 * y + (x + 1) % 5;
+    // B[X][Y] = rotl(A[x][y]) with X = y, Y = (2x + 3y) % 5  =>  y = X, x = (3Y + X) % 5: source lane 5X + (3Y + X) % 5
+    auto src = [](int X, int Y) { return 5 * X + (3 * Y + X) % 5; };
+    c.s0  = src(x, y);
+    c.s1  = src((x + 1) % 5, y);
+    c.s2  = src((x + 2) % 5, y);
+    c.rot = 0;
+#pragma unroll
+    for (int i = 0; i < 25; i++)
+        if (i == l) c.rot = rho[i];
+    return c;
+}
+
+// One Keccak-f[1600] on the state held as (lo, hi) of lane 5y + x: 18 shuffles in three dependent levels and 16
+// ALU operations per round.  (Exchanging through shared memory instead — one 64-bit store, __syncwarp(), 10 + 3
+// independent 64-bit loads per round — measured 13 % slower: profiles/README.md.)
+//   theta : C = xor of the column (4 shuffles per half), D = C[x-1] ^ rotl(C[x+1], 1) (2 shuffles per half)
+//   rho   : every lane rotates its own word by its own offset
+//   pi+chi: lane (x,y) fetches B[x][y], B[x+1][y], B[x+2][y] straight from the lanes that hold them before pi
+//           (3 shuffles per half)
+__device__ __forceinline__ void seb_keccak_coop(uint32_t &lo, uint32_t &hi, const SebCoopLane &c, const int lane)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int round = 0; round < 24; round++)
+    {
+        // theta
+        const uint32_t a1l = __shfl_sync(FULL, lo, c.col[0]), a1h = __shfl_sync(FULL, hi, c.col[0]);
+        const uint32_t a2l = __shfl_sync(FULL, lo, c.col[1]), a2h = __shfl_sync(FULL, hi, c.col[1]);
+        const uint32_t a3l = __shfl_sync(FULL, lo, c.col[2]), a3h = __shfl_sync(FULL, hi, c.col[2]);
+        const uint32_t a4l = __shfl_sync(FULL, lo, c.col[3]), a4h = __shfl_sync(FULL, hi, c.col[3]);
+        const uint32_t cl  = seb_xor3(seb_xor3(lo, a1l, a2l), a3l, a4l);
+        const uint32_t ch  = seb_xor3(seb_xor3(hi, a1h, a2h), a3h, a4h);
+        const uint32_t cml = __shfl_sync(FULL, cl, c.xm1), cmh = __shfl_sync(FULL, ch, c.xm1);
+        const uint32_t cpl = __shfl_sync(FULL, cl, c.xp1), cph = __shfl_sync(FULL, ch, c.xp1);
+        const uint32_t tl  = seb_xor3(lo, cml, __funnelshift_l(cph, cpl, 1));
+        const uint32_t th  = seb_xor3(hi, cmh, __funnelshift_l(cpl, cph, 1));
+        // rho: rotl64 by this lane's offset (swap the halves for offsets >= 32, then funnel by offset % 32)
+        const bool sw      = c.rot >= 32;
+        const uint32_t ul  = sw ? th : tl, uh = sw ? tl : th;
+        const uint32_t bl  = __funnelshift_l(uh, ul, c.rot);  // shift counts are taken modulo 32
+        const uint32_t bh  = __funnelshift_l(ul, uh, c.rot);
+        // pi + chi
+        const uint32_t b0l = __shfl_sync(FULL, bl, c.s0), b0h = __shfl_sync(FULL, bh, c.s0);
+        const uint32_t b1l = __shfl_sync(FULL, bl, c.s1), b1h = __shfl_sync(FULL, bh, c.s1);
+        const uint32_t b2l = __shfl_sync(FULL, bl, c.s2), b2h = __shfl_sync(FULL, bh, c.s2);
+        lo = seb_chi(b0l, b1l, b2l);
+        hi = seb_chi(b0h, b1h, b2h);
+        // iota
+        if (lane == 0)
+        {
+            lo ^= c_keccak_rc_lo[round];
+            hi ^= c_keccak_rc_hi[round];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__restrict__ seeds,
+                                                           const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
+                                                           size_t ct_stride, int n, SebModulus mod, uint32_t max_multiple,
+                                                           int batch, uint16_t *__restrict__ rej_idx,
+                                                           uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const SebCoopLane c = seb_coop_setup(lane);
+    // absorb seed || LE64(counter), pad (seb_prng_init): lanes 0..7 seed, 8 counter, 9 0x1F, 16 the final bit
+    uint32_t lo = 0, hi = 0;
+    if (lane < 8)
+    {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(seeds + (size_t)b * SEB_SEED_BYTES) + lane);
+        lo = w.x;
+        hi = w.y;
+    }
+    else if (lane == 8)
+        lo = ctr[b];
+    else if (lane == 9)
+        lo = 0x1Fu;
+    else if (lane == 16)
+        hi = 0x80000000u;
+    uint32_t *row  = out + (size_t)b * ct_stride;
+    uint16_t *list = rej_idx + (size_t)b * cap;
+    uint32_t cnt   = 0;
+    const uint32_t below = (1u << lane) - 1u;
+    for (int word = 0; word < n; word += 34)
+    {
+        seb_keccak_coop(lo, hi, c, lane);
+        // lanes 0..16 hold the 136-byte rate block: words word + 2*lane, + 1
+        const int w0     = word + 2 * lane;
+        const bool valid = lane < 17 && w0 < n;  // n is even: the pair is valid or not as a whole
+        const bool rl    = valid && lo >= max_multiple, rh = valid && hi >= max_multiple;
+        const uint32_t ml = __ballot_sync(0xFFFFFFFFu, rl), mh = __ballot_sync(0xFFFFFFFFu, rh);
+        if (valid)
+        {
+            // ascending word order = (lane 0 lo, lane 0 hi, lane 1 lo, ...)
+            uint32_t pos = cnt + (uint32_t)__popc(ml & below) + (uint32_t)__popc(mh & below);
+            if (rl)
+            {
+                if (pos < cap) list[pos] = (uint16_t)w0;
+                pos++;
+            }
+            if (rh && pos < cap) list[pos] = (uint16_t)(w0 + 1);
+            const uint32_t vl = rl ? lo : seb_barrett32(lo, mod), vh = rh ? hi : seb_barrett32(hi, mod);
+            *reinterpret_cast<uint2 *>(row + w0) = make_uint2(vl, vh);
+        }
+        cnt += (uint32_t)__popc(ml) + (uint32_t)__popc(mh);
+    }
+    if (lane == 0) rej_cnt[b] = cnt;
+}
+
 // Warp per ciphertext: the k-th rejected index (ascending) receives the k-th accepted
 // candidate LE32(X(seed, c0+1+t, 4)), t = 0,1,...; the counter ends one past the last candidate
 // consumed (sample.c:49-56).  Candidates are generated 32 counters at a time; with the reject list
@@ -329,10 +476,18 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     if (batch <= 0) return;
     // max_multiple = 0xFFFFFFFF - (0xFFFFFFFF mod q) - 1 (sample.c:45-46)
     const uint32_t max_multiple = 0xFFFFFFFFu - (0xFFFFFFFFu % mod.q) - 1u;
-    // one sequential sponge per thread: single-warp CTAs spread a small batch over all SM sub-partitions
-    // (131072-item config D leaves 16384 items = 512 warps per GPU for 592 sub-partitions)
-    k_uniform_bulk<<<(batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
-                                                     rej_idx, rej_cnt, rej_cap);
+    // Small batches: a warp per ciphertext with the sponge spread over its lanes (latency of the dependent
+    // permutations / 4); otherwise one sequential sponge per thread, in single-warp CTAs that spread the batch over
+    // all SM sub-partitions (131072-item config D leaves 16384 items = 512 warps per GPU for 592 sub-partitions).
+    // SEB_UNIFORM_COOP=0/1 forces either (tests, A/B measurements).
+    const char *e   = getenv("SEB_UNIFORM_COOP");
+    const bool coop = (e && *e) ? atoi(e) != 0 : batch <= SEB_UNIFORM_COOP_MAX_BATCH;
+    if (coop)
+        k_uniform_bulk_coop<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
+                                                             rej_idx, rej_cnt, rej_cap);
+    else
+        k_uniform_bulk<<<(batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
+                                                         rej_idx, rej_cnt, rej_cap);
     k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
                                                    rej_cnt, rej_cap);
 }

@@ -136,6 +136,34 @@ def test_samplers_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert np.array_equal(e[b, 0], e0) and np.array_equal(e[b, 1], e1), (n, b)
 
 
+@pytest.mark.parametrize("coop", ["0", "1"])
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_sampler_uniform_both_kernels(n, np_, coop, seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
+    """sample_poly_uniform (sample.c:39-57) through each of the two bulk kernels — one sequential sponge per thread
+    (large batches) and the warp-cooperative sponge spread over 25 lanes (small batches) — forced with
+    SEB_UNIFORM_COOP: same polynomials, same counters as the oracle, for a batch that is not a multiple of
+    the warps per CTA."""
+    torch = torch_cuda
+    monkeypatch.setenv("SEB_UNIFORM_COOP", coop)
+    ctx = ctxs(n, np_, False)
+    batch = 9
+    seeds = oracle_mod.make_seeds(batch, b"uniform-k-%d" % n)
+    d_seeds = dev(torch, seeds)
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+    for p in range(np_):
+        ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+    torch.cuda.synchronize()
+    out = host(d_out, np.uint32).reshape(batch, np_, n)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        c = 0
+        for p, q in enumerate(ctx.primes):
+            exp, c = orc.sample_uniform(n, q, seeds[b], c)
+            assert np.array_equal(out[b, p], exp), (n, coop, b, p)
+        assert ctr[b] == c
+
+
 @pytest.mark.parametrize("n,np_", CONFIGS)
 def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """sample.c:39-57: bulk draw, ordered redraws, counter running on across primes (ckks_sym.c:219)."""
