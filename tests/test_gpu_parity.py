@@ -901,8 +901,8 @@ def test_golden_fixtures(seb, torch_cuda, oracle_mod, ctxs):
 def test_full_size_properties(n, np_, asym, batch, seb, torch_cuda, oracle_mod, orc, ctxs):
     """BASELINE.json's configurations at full per-GPU size (B whole; C and D as their 1/8 shards; A batched):
     size-independent properties — (1) items are independent of batch position and grid shape (re-encrypting
-    slices reproduces the same per-item checksums), (2) first/middle/last items equal the oracle bit for
-    bit, (3) every residue is < q, (4) EVERY item decrypts and decodes to its message within the
+    slices reproduces the same per-item checksums), (2) the first 32, the middle and the last 32 items equal
+    the oracle bit for bit, (3) every residue is < q, (4) EVERY item decrypts and decodes to its message within the
     reference's 0.1 on the GPU verifier."""
     torch = torch_cuda
     ctx = ctxs(n, np_, asym)
@@ -947,14 +947,17 @@ def test_full_size_properties(n, np_, asym, batch, seb, torch_cuda, oracle_mod, 
     vals = d_vals.cpu().numpy()
     seeds = d_seeds.cpu().numpy()
     sseeds = d_ss.cpu().numpy()
-    for b in (0, 1, batch // 2, batch - 1):
+    # the first and last items of the batch byte for byte (32 + 32 here), plus the middle
+    picks = list(range(32)) + [batch // 2] + list(range(batch - 32, batch))
+    for b in picks:
         got = host(d_out[b], np.uint32).reshape(np_, 2, n)
         if asym:
             ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
         else:
             ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
         assert ok and np.array_equal(got, exp), b
-        dec = orc.decrypt_decode(n, np_, got, sk, vlen)
-        assert np.abs(dec - vals[b]).max() < 0.1
+        if b in (0, batch // 2, batch - 1):
+            dec = orc.decrypt_decode(n, np_, got, sk, vlen)
+            assert np.abs(dec - vals[b]).max() < 0.1
     del d_out, d_dec
     torch.cuda.empty_cache()
