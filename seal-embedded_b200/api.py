@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "seb_sample_uniform_device", "seb_ntt_device", "seb_prng_blocks_device", "seb_profile_begin", "seb_profile_end",
     "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
     "seb_encrypt_sym_seedct_device", "seb_encrypt_sym_seedct_host", "seb_expand_seedct_device",
-    "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct", "seb_minimal_psi",
+    "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct", "seb_minimal_psi", "seb_uniform_spec_misses",
 ]
 
 
@@ -128,6 +128,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_encrypt_asym_device.argtypes = [vp, vp, sz, vp, sz, vp]
     L.seb_encrypt_sym_device.argtypes = [vp, vp, sz, vp, vp, sz, vp, i32]
     L.seb_encode_failures.argtypes = [vp]
+    L.seb_uniform_spec_misses.argtypes = [vp]
+    L.seb_uniform_spec_misses.restype = C.c_long
     L.seb_encrypt_asym_host.argtypes = [vp, vp, sz, vp, sz, vp]
     L.seb_encrypt_sym_host.argtypes = [vp, vp, sz, vp, vp, sz, vp, i32]
     L.seb_encrypt_sym_seedct_device.argtypes = [vp, vp, sz, vp, vp, sz, vp]
@@ -271,6 +273,9 @@ class Context:
                            ref_quirk: bool = False) -> None:
         self._check(self.lib.seb_encrypt_sym_device(self.h, _addr(d_values), vlen, _addr(d_share_seeds),
                                                     _addr(d_seeds), batch, _addr(d_out), int(ref_quirk)))
+
+    def uniform_spec_misses(self) -> int:
+        return self._check(int(self.lib.seb_uniform_spec_misses(self.h)))
 
     def encode_failures(self) -> int:
         return self._check(self.lib.seb_encode_failures(self.h))

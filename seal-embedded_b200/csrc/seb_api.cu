@@ -163,6 +163,11 @@ struct Scratch  // per in-flight chunk
     uint32_t *rej_cnt = nullptr;  // [cap]
     uint32_t *a_buf   = nullptr;  // [a_cap][np][n] `a` of the seed-compressed symmetric path (allocated on first use)
     size_t a_cap      = 0;
+    // lone-call speculation (seb_launch_uniform_chain_spec), allocated on first use for SEB_SPEC_MAX_BATCH items
+    uint32_t *cand_rows = nullptr;
+    uint16_t *cand_list = nullptr;
+    uint32_t *cand_cnt  = nullptr;
+    size_t cand_cap     = 0;  // ciphertexts the candidate buffers hold
     // host-API staging
     size_t io_cap    = 0;
     size_t io_out_words = 0;  // words of d_out / h_out per ciphertext
@@ -200,6 +205,8 @@ struct seb_ctx
     double2 *d_work       = nullptr;  // [verify_ctas][n] FFT scratch
     int sms = 0, verify_ctas = 0;
     bool have_pk = false, have_sk = false;
+    SebSpecPlan spec_plan;            // counter windows for the lone-call uniform chain (symmetric, np >= 2)
+    uint32_t *d_spec_misses = nullptr;  // how often a true counter fell outside its window (diagnostic)
     Scratch slot[2];
     size_t last_batch = 0;
     uint64_t launches = 0;
@@ -263,6 +270,9 @@ static void free_scratch(Scratch &s)
     cudaFree(s.rej_idx);
     cudaFree(s.rej_cnt);
     cudaFree(s.a_buf);
+    cudaFree(s.cand_rows);
+    cudaFree(s.cand_list);
+    cudaFree(s.cand_cnt);
     cudaFree(s.d_values);
     cudaFree(s.d_seeds);
     cudaFree(s.d_sseeds);
@@ -406,6 +416,15 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     if (const char *v = getenv("SEB_UNIFORM_LIST_CAP"))
         if (*v && (uint32_t)atoi(v) < c->rej_cap) c->rej_cap = (uint32_t)atoi(v);
 
+    memset(&c->spec_plan, 0, sizeof c->spec_plan);
+    if (!c->asym && nprimes >= 2)
+    {
+        double sigmas = 6.0;  // SEB_UNIFORM_SPEC_SIGMAS narrows the windows so that tests can force the fallback
+        if (const char *v = getenv("SEB_UNIFORM_SPEC_SIGMAS"))
+            if (*v) sigmas = atof(v);
+        seb_uniform_spec_plan((int)n, c->mods, (int)nprimes, sigmas, &c->spec_plan);
+    }
+
     auto bail = [&](const char *what, cudaError_t e) -> seb_ctx * {
         fail(SE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
         seb_destroy(c);
@@ -442,6 +461,7 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaFree(c->d_roots);
     cudaFree(c->d_tw);
     cudaFree(c->d_src_map);
+    cudaFree(c->d_spec_misses);
     cudaFree(c->d_pk0);
     cudaFree(c->d_pk1);
     cudaFree(c->d_ntt_s);
@@ -453,6 +473,18 @@ extern "C" void seb_destroy(seb_ctx *c)
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+// How many (ciphertext, prime) squeezes of the lone-call path found their true counter outside the speculated
+// window and were redone on the spot (diagnostic; synchronises the stream).  Negative on error.
+extern "C" long seb_uniform_spec_misses(seb_ctx *c)
+{
+    if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
+    if (!c->d_spec_misses) return 0;
+    uint32_t v = 0;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(&v, c->d_spec_misses, sizeof v, cudaMemcpyDeviceToHost));
+    return (long)v;
 }
 
 extern "C" int seb_set_stream(seb_ctx *c, void *cuda_stream)
@@ -752,6 +784,58 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 
 // seal_embedded.c:98-215 (symmetric branch): encode, e, then per prime sample a (the shareable
 // PRNG's counter runs on across primes, ckks_sym.c:219), then the fused c0 kernel.
+// Batches this small run every prime's squeeze at once on speculated counters (seb_sample.cu); SEB_UNIFORM_SPEC=0/1
+// forces the choice (tests, A/B measurements).
+#define SEB_SPEC_MAX_BATCH 4
+
+// sample_poly_uniform for every prime of `batch` ciphertexts (the shareable PRNG's counter runs on across the
+// primes, ckks_sym.c:219): a_p0 = row of (item 0, prime 0), prime p is p_stride words further, item b ct_stride.
+static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, size_t batch, uint32_t *a_p0, size_t ct_stride,
+                             size_t p_stride, cudaStream_t st)
+{
+    const int n = (int)c->n;
+    CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
+    const char *e   = getenv("SEB_UNIFORM_SPEC");
+    const bool spec = c->spec_plan.total > 0 && ((e && *e) ? (atoi(e) != 0 && batch <= 64) : batch <= SEB_SPEC_MAX_BATCH);
+    if (spec)
+    {
+        if (s.cand_cap < batch)
+        {
+            cudaFree(s.cand_rows);
+            cudaFree(s.cand_list);
+            cudaFree(s.cand_cnt);
+            s.cand_rows = nullptr;
+            s.cand_list = nullptr;
+            s.cand_cnt  = nullptr;
+            s.cand_cap  = 0;
+            const size_t items = batch > SEB_SPEC_MAX_BATCH ? batch : SEB_SPEC_MAX_BATCH;
+            const size_t slots = items * c->spec_plan.total;
+            CU(cudaMalloc(&s.cand_rows, slots * c->n * sizeof(uint32_t)));
+            CU(cudaMalloc(&s.cand_list, slots * (size_t)(c->rej_cap ? c->rej_cap : 1) * sizeof(uint16_t)));
+            CU(cudaMalloc(&s.cand_cnt, slots * sizeof(uint32_t)));
+            s.cand_cap = items;
+        }
+        if (!c->d_spec_misses)
+        {
+            CU(cudaMalloc(&c->d_spec_misses, sizeof(uint32_t)));
+            CU(cudaMemsetAsync(c->d_spec_misses, 0, sizeof(uint32_t), st));
+        }
+        seb_launch_uniform_chain_spec(d_sseeds, s.ctr_a, a_p0, ct_stride, p_stride, n, c->mods, (int)c->np, c->spec_plan,
+                                      (int)batch, s.cand_rows, s.cand_list, s.cand_cnt, s.rej_idx, s.rej_cnt, c->rej_cap,
+                                      c->d_spec_misses, st);
+        c->launches += 2 * c->np;  // one squeeze launch, a select per later prime, a fix-up per prime
+    }
+    else
+    {
+        for (size_t p = 0; p < c->np; p++)
+            seb_launch_uniform(d_sseeds, s.ctr_a, a_p0 + p * p_stride, ct_stride, n, c->mods.m[p], (int)batch, s.rej_idx,
+                               s.rej_cnt, c->rej_cap, st);
+        c->launches += 2 * c->np;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // seedct: the seed-compressed form (SE_ENABLE_SYM_SEED_CT, seal_embedded.c:184-194) — `a` goes to
 // scratch instead of the c1 slots and d_out receives c0 only, [batch][np][n]; the receiver regenerates a
 // from the 64-byte shareable seed (seb_expand_seedct_device).
@@ -777,11 +861,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     prof_mark(c, st, 1);
     seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
     prof_mark(c, st, 2);
-    CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
-    for (size_t p = 0; p < c->np; p++)
-        seb_launch_uniform(d_sseeds, s.ctr_a, a_base + p * p_stride, ct_stride, n, c->mods.m[p], (int)batch,
-                           s.rej_idx, s.rej_cnt, c->rej_cap, st);
-    CU(cudaGetLastError());
+    if ((r = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, st))) return r;
     prof_mark(c, st, 3);
     CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
                               ct_stride, p_stride, seedct ? 0 : quirk, (int)batch, st));
@@ -845,13 +925,7 @@ extern "C" int seb_expand_seedct_device(seb_ctx *c, const uint8_t *d_sseeds, con
     if (d_c0)
         CU(cudaMemcpy2DAsync(d_out, 2 * n * sizeof(uint32_t), d_c0, n * sizeof(uint32_t), n * sizeof(uint32_t),
                              batch * c->np, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
-    for (size_t p = 0; p < c->np; p++)
-        seb_launch_uniform(d_sseeds, s.ctr_a, d_out + (2 * p + 1) * n, 2 * c->np * n, (int)n, c->mods.m[p], (int)batch,
-                           s.rej_idx, s.rej_cnt, c->rej_cap, st);
-    CU(cudaGetLastError());
-    c->launches += 2 * c->np;
-    return 0;
+    return run_uniform_chain(c, s, d_sseeds, batch, d_out + n, 2 * c->np * n, 2 * n, st);
 }
 
 // Per-kernel timing of the next `max_steps` full-path *_device calls: CUDA events are recorded on

@@ -25,6 +25,22 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
                         const SebModulus &mod, int batch, uint16_t *rej_idx, uint32_t *rej_cnt, uint32_t rej_cap,
                         cudaStream_t st);
 
+// Lone calls: all primes' squeezes at once, speculating on the chained counters (seb_sample.cu).
+struct SebSpecPrime
+{
+    uint32_t lo, width, first;
+};
+struct SebSpecPlan
+{
+    SebSpecPrime p[SEB_MAX_PRIMES];
+    uint32_t total;
+};
+void seb_uniform_spec_plan(int n, const SebModuli &mods, int np, double sigmas, SebSpecPlan *plan);
+void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t *out_p0, size_t ct_stride, size_t p_stride,
+                                   int n, const SebModuli &mods, int np, const SebSpecPlan &plan, int batch,
+                                   uint32_t *cand_rows, uint16_t *cand_list, uint32_t *cand_cnt, uint16_t *rej_idx,
+                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, cudaStream_t st);
+
 // ---- encode (seb_encode.cu) ----
 // values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);
 // src_map[pos] = slot whose value lands on position pos; tw[i] = IFFT twiddle (re, im), i in [1,n), followed by

@@ -8,7 +8,9 @@
 // PRNG consumption order is the reference's: every prng_fill_buffer call is
 // a fresh SHAKE256(seed || LE64(counter)) and bumps the counter, including the data-dependent
 // single-value redraws of the rejection samplers.
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "seb_kernels.h"
 #include "seb_sample.cuh"
@@ -309,33 +311,28 @@ __device__ __forceinline__ void seb_keccak_coop(uint32_t &lo, uint32_t &hi, cons
     }
 }
 
-__global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__restrict__ seeds,
-                                                           const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
-                                                           size_t ct_stride, int n, SebModulus mod, uint32_t max_multiple,
-                                                           int batch, uint16_t *__restrict__ rej_idx,
-                                                           uint32_t *__restrict__ rej_cnt, uint32_t cap)
+// the 4n-byte squeeze of SHAKE256(seed || LE64(counter)) by one warp: accepted words reduced into `row`, rejected
+// ones raw, their indices (ascending) in `list`; returns how many were rejected
+__device__ __forceinline__ uint32_t seb_coop_bulk_row(const uint8_t *__restrict__ seed, uint32_t counter,
+                                                      uint32_t *__restrict__ row, uint16_t *__restrict__ list, int n,
+                                                      const SebModulus &mod, uint32_t max_multiple, uint32_t cap,
+                                                      const SebCoopLane &c, const int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= batch) return;
-    const SebCoopLane c = seb_coop_setup(lane);
     // absorb seed || LE64(counter), pad (seb_prng_init): lanes 0..7 seed, 8 counter, 9 0x1F, 16 the final bit
     uint32_t lo = 0, hi = 0;
     if (lane < 8)
     {
-        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(seeds + (size_t)b * SEB_SEED_BYTES) + lane);
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(seed) + lane);
         lo = w.x;
         hi = w.y;
     }
     else if (lane == 8)
-        lo = ctr[b];
+        lo = counter;
     else if (lane == 9)
         lo = 0x1Fu;
     else if (lane == 16)
         hi = 0x80000000u;
-    uint32_t *row  = out + (size_t)b * ct_stride;
-    uint16_t *list = rej_idx + (size_t)b * cap;
-    uint32_t cnt   = 0;
+    uint32_t cnt         = 0;
     const uint32_t below = (1u << lane) - 1u;
     for (int word = 0; word < n; word += 34)
     {
@@ -360,7 +357,110 @@ __global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__rest
         }
         cnt += (uint32_t)__popc(ml) + (uint32_t)__popc(mh);
     }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__restrict__ seeds,
+                                                           const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
+                                                           size_t ct_stride, int n, SebModulus mod, uint32_t max_multiple,
+                                                           int batch, uint16_t *__restrict__ rej_idx,
+                                                           uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const SebCoopLane c = seb_coop_setup(lane);
+    const uint32_t cnt  = seb_coop_bulk_row(seeds + (size_t)b * SEB_SEED_BYTES, ctr[b], out + (size_t)b * ct_stride,
+                                            rej_idx + (size_t)b * cap, n, mod, max_multiple, cap, c, lane);
     if (lane == 0) rej_cnt[b] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lone calls (a handful of ciphertexts): the primes' squeezes in PARALLEL, speculating on the counters
+// ---------------------------------------------------------------------------------------------
+// The squeeze of prime p starts at counter c_p = p + (redraw calls of primes < p), which is only known once those
+// primes are done — but it is sharply distributed: the redraw calls of prime i have mean n r_i / (1 - r_i) and
+// variance n r_i / (1 - r_i)^2, r_i = the word rejection rate under q_i (1-2 %).  For a few ciphertexts the machine
+// is empty, so EVERY counter within +-6 sigma of the mean is squeezed at once (105 candidates for prime 1 at
+// n = 4096, 1760 over the five later primes at n = 16384), one warp each, beside prime 0; afterwards the chain is
+// resolved prime by prime: k_uniform_select copies the candidate the true counter points at into the output (or,
+// outside the window, squeezes it on the spot) and the usual fix-up follows.  Same bytes, same counters; the
+// dependent work shrinks from all primes' squeezes to one.
+// (SebSpecPrime / SebSpecPlan: seb_kernels.h — per prime p >= 1 the first speculated counter `lo`, how many
+// counters `width`, and `first`, the index of its first candidate among the `total` candidates of a ciphertext)
+
+// grid: warp (b, k), k = 0: prime 0 at counter 0 into the output row; k >= 1: candidate k - 1
+__global__ void __launch_bounds__(128)
+    k_uniform_spec_bulk(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ out, size_t ct_stride, size_t p_stride,
+                        int n, const __grid_constant__ SebModuli mods, int np, const __grid_constant__ SebSpecPlan plan,
+                        int batch, uint32_t *__restrict__ cand_rows, uint16_t *__restrict__ cand_list,
+                        uint32_t *__restrict__ cand_cnt, uint16_t *__restrict__ rej_idx, uint32_t *__restrict__ rej_cnt,
+                        uint32_t cap)
+{
+    const int lane       = threadIdx.x & 31;
+    const size_t warp    = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t per_ct  = (size_t)plan.total + 1;
+    if (warp >= per_ct * (size_t)batch) return;
+    const size_t b       = warp / per_ct;
+    const uint32_t k     = (uint32_t)(warp % per_ct);
+    const SebCoopLane c  = seb_coop_setup(lane);
+    const uint8_t *seed  = seeds + b * SEB_SEED_BYTES;
+    if (k == 0)
+    {
+        const SebModulus m  = mods.m[0];
+        const uint32_t maxm = 0xFFFFFFFFu - (0xFFFFFFFFu % m.q) - 1u;
+        const uint32_t cnt  = seb_coop_bulk_row(seed, 0u, out + b * ct_stride, rej_idx + b * cap, n, m, maxm, cap, c, lane);
+        if (lane == 0) rej_cnt[b] = cnt;
+        return;
+    }
+    int p = 1;
+    while (p + 1 < np && k - 1 >= plan.p[p + 1].first) p++;
+    const uint32_t j    = k - 1 - plan.p[p].first;
+    const SebModulus m  = mods.m[p];
+    const uint32_t maxm = 0xFFFFFFFFu - (0xFFFFFFFFu % m.q) - 1u;
+    const size_t slot   = b * plan.total + (k - 1);
+    const uint32_t cnt  = seb_coop_bulk_row(seed, plan.p[p].lo + j, cand_rows + slot * (size_t)n, cand_list + slot * cap, n, m,
+                                            maxm, cap, c, lane);
+    if (lane == 0) cand_cnt[slot] = cnt;
+}
+
+// warp per ciphertext, before the fix-up of prime p >= 1: bring the squeeze that starts at the TRUE counter
+// ctr[b] into the output row and the fix-up's reject list
+__global__ void __launch_bounds__(128)
+    k_uniform_select(const uint8_t *__restrict__ seeds, const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out_p,
+                     size_t ct_stride, int n, SebModulus mod, uint32_t max_multiple, SebSpecPrime sp, uint32_t total,
+                     int batch, const uint32_t *__restrict__ cand_rows, const uint16_t *__restrict__ cand_list,
+                     const uint32_t *__restrict__ cand_cnt, uint16_t *__restrict__ rej_idx, uint32_t *__restrict__ rej_cnt,
+                     uint32_t cap, uint32_t *__restrict__ misses)
+{
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const uint32_t c0 = ctr[b];
+    uint32_t *row     = out_p + (size_t)b * ct_stride;
+    uint16_t *list    = rej_idx + (size_t)b * cap;
+    if (c0 >= sp.lo && c0 - sp.lo < sp.width)
+    {
+        const size_t slot   = (size_t)b * total + sp.first + (c0 - sp.lo);
+        const uint4 *src    = reinterpret_cast<const uint4 *>(cand_rows + slot * (size_t)n);
+        uint4 *dst          = reinterpret_cast<uint4 *>(row);
+        for (int i = lane; i < n / 4; i += 32) dst[i] = src[i];
+        const uint32_t cnt  = cand_cnt[slot];
+        const uint32_t keep = cnt < cap ? cnt : cap;
+        for (uint32_t i = lane; i < keep; i += 32) list[i] = cand_list[slot * cap + i];
+        if (lane == 0) rej_cnt[b] = cnt;
+    }
+    else
+    {
+        // outside the speculated window (probability ~1e-9 per prime): squeeze it now
+        const SebCoopLane c = seb_coop_setup(lane);
+        const uint32_t cnt  = seb_coop_bulk_row(seeds + (size_t)b * SEB_SEED_BYTES, c0, row, list, n, mod, max_multiple, cap, c, lane);
+        if (lane == 0)
+        {
+            rej_cnt[b] = cnt;
+            if (misses) atomicAdd(misses, 1u);
+        }
+    }
 }
 
 // Warp per ciphertext: the k-th rejected index (ascending) receives the k-th accepted
@@ -467,6 +567,55 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
     if (batch <= 0) return;
     const size_t total = (size_t)batch * npoly * (n / 16);
     k_sample_cbd<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(seeds, ctr_base, e_out, n, npoly, batch);
+}
+
+// Speculation windows for a parameter set (host, once per context).  sigmas: half-width in standard deviations.
+void seb_uniform_spec_plan(int n, const SebModuli &mods, int np, double sigmas, SebSpecPlan *plan)
+{
+    double mean = 0.0, var = 0.0;
+    uint32_t first = 0;
+    memset(plan, 0, sizeof *plan);
+    for (int p = 1; p < np; p++)
+    {
+        const uint32_t q    = mods.m[p - 1].q;
+        const uint32_t maxm = 0xFFFFFFFFu - (0xFFFFFFFFu % q) - 1u;
+        const double r      = (4294967296.0 - (double)maxm) / 4294967296.0;  // word rejection rate under prime p-1
+        mean += 1.0 + (double)n * r / (1.0 - r);                               // its squeeze + its redraw calls
+        var += (double)n * r / ((1.0 - r) * (1.0 - r));
+        const double half = sigmas * sqrt(var) + 2.0;
+        const double lo   = mean - half;
+        plan->p[p].lo     = lo < (double)p ? (uint32_t)p : (uint32_t)lo;
+        plan->p[p].width  = (uint32_t)(mean + half) - plan->p[p].lo + 1u;
+        plan->p[p].first  = first;
+        first += plan->p[p].width;
+    }
+    plan->total = first;
+}
+
+// The whole chain for a handful of ciphertexts: every prime's squeeze in one launch (prime 0 and the speculated
+// counters of the others), then select + fix-up per prime.  out_p0 = row of (item 0, prime 0); prime p's rows are
+// p_stride words further.  cand_* = scratch for batch * plan.total candidates.  Leaves ctr[b] = the final counter.
+void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t *out_p0, size_t ct_stride, size_t p_stride,
+                                   int n, const SebModuli &mods, int np, const SebSpecPlan &plan, int batch,
+                                   uint32_t *cand_rows, uint16_t *cand_list, uint32_t *cand_cnt, uint16_t *rej_idx,
+                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, cudaStream_t st)
+{
+    if (batch <= 0) return;
+    const size_t warps = ((size_t)plan.total + 1) * (size_t)batch;
+    k_uniform_spec_bulk<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(seeds, out_p0, ct_stride, p_stride, n, mods, np, plan, batch,
+                                                                    cand_rows, cand_list, cand_cnt, rej_idx, rej_cnt, rej_cap);
+    for (int p = 0; p < np; p++)
+    {
+        const SebModulus &mod       = mods.m[p];
+        const uint32_t max_multiple = 0xFFFFFFFFu - (0xFFFFFFFFu % mod.q) - 1u;
+        uint32_t *out_p             = out_p0 + (size_t)p * p_stride;
+        if (p > 0)
+            k_uniform_select<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, plan.p[p],
+                                                              plan.total, batch, cand_rows, cand_list, cand_cnt, rej_idx,
+                                                              rej_cnt, rej_cap, misses);
+        k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                       rej_cnt, rej_cap);
+    }
 }
 
 void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,

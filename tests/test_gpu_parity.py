@@ -398,6 +398,45 @@ def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
             assert np.abs(dec - vals[0]).max() < 0.1
 
 
+@pytest.mark.parametrize("mode", ["serial", "speculative", "speculative-narrow"])
+@pytest.mark.parametrize("n,np_", [(4096, 3), (8192, 4), (16384, 6)])
+def test_encrypt_sym_lone_call_paths(n, np_, mode, seb, torch_cuda, oracle_mod, orc, monkeypatch):
+    """Lone symmetric calls run every prime's uniform squeeze at once on speculated PRNG counters
+    (seb_launch_uniform_chain_spec).  Ciphertexts must equal the oracle's whichever way the chain is walked:
+    prime after prime (SEB_UNIFORM_SPEC=0), speculatively with the 6-sigma windows (no miss expected), and
+    speculatively with windows narrowed to +-2 counters so that most true counters miss and are re-squeezed on
+    the spot (the fallback)."""
+    torch = torch_cuda
+    monkeypatch.setenv("SEB_UNIFORM_SPEC", "0" if mode == "serial" else "1")
+    if mode == "speculative-narrow":
+        monkeypatch.setenv("SEB_UNIFORM_SPEC_SIGMAS", "0")
+    ctx = seb.Context(n, np_, False, device=0)
+    try:
+        sk = oracle_mod.make_sk(n)
+        ctx.set_secret_key(sk)
+        vlen = n // 2
+        for batch in (1, 3, 6):
+            vals = oracle_mod.make_values(batch, vlen, seed=n + batch)
+            seeds = oracle_mod.make_seeds(batch, b"lone-%d-%d" % (n, batch))
+            sseeds = oracle_mod.make_seeds(batch, b"lone-share-%d-%d" % (n, batch))
+            d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+            ctx.encrypt_sym_device(dev(torch, vals), vlen, dev(torch, sseeds), dev(torch, seeds), batch, d_out, False)
+            assert ctx.encode_failures() == 0
+            got = host(d_out, np.uint32).reshape(batch, np_, 2, n)
+            for b in range(batch):
+                ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
+                assert ok and np.array_equal(got[b], exp), (n, mode, batch, b)
+        misses = ctx.uniform_spec_misses()
+        if mode == "speculative":
+            assert misses == 0
+        elif mode == "speculative-narrow":
+            assert misses > 0  # +-2 counters around the mean against a standard deviation of 9..40
+        else:
+            assert misses == 0
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("n,np_", CONFIGS)
 def test_encrypt_sym_seed_compressed(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """SURVEY 8f-2 (the reference's unfinished SE_ENABLE_SYM_SEED_CT, seal_embedded.c:184-194): the
