@@ -784,9 +784,13 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 
 // seal_embedded.c:98-215 (symmetric branch): encode, e, then per prime sample a (the shareable
 // PRNG's counter runs on across primes, ckks_sym.c:219), then the fused c0 kernel.
-// Batches this small run every prime's squeeze at once on speculated counters (seb_sample.cu); SEB_UNIFORM_SPEC=0/1
-// forces the choice (tests, A/B measurements).
-#define SEB_SPEC_MAX_BATCH 4
+// Calls this small run every prime's squeeze at once on speculated counters (seb_sample.cu): as long as all the
+// candidate sponges of the call, one warp each, stay within what the machine runs at the warp-cooperative
+// kernel handles well: measured a win up to 8192 warps (profiles/r01_ab_sym_small_batches.txt), i.e. 4 ciphertexts
+// at n = 16384 x 6 primes (~1800 candidates each), 16 at n = 4096 x 3 primes (255 each).
+// SEB_UNIFORM_SPEC=0/1 forces the choice for up to 64 ciphertexts (tests, A/B measurements).
+#define SEB_SPEC_MAX_BATCH 64
+#define SEB_SPEC_MAX_WARPS 8192
 
 // sample_poly_uniform for every prime of `batch` ciphertexts (the shareable PRNG's counter runs on across the
 // primes, ckks_sym.c:219): a_p0 = row of (item 0, prime 0), prime p is p_stride words further, item b ct_stride.
@@ -796,7 +800,8 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
     const int n = (int)c->n;
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
     const char *e   = getenv("SEB_UNIFORM_SPEC");
-    const bool spec = c->spec_plan.total > 0 && ((e && *e) ? (atoi(e) != 0 && batch <= 64) : batch <= SEB_SPEC_MAX_BATCH);
+    const bool fits = batch <= SEB_SPEC_MAX_BATCH && batch * ((size_t)c->spec_plan.total + 1) <= SEB_SPEC_MAX_WARPS;
+    const bool spec = c->spec_plan.total > 0 && ((e && *e) ? (atoi(e) != 0 && batch <= SEB_SPEC_MAX_BATCH) : fits);
     if (spec)
     {
         if (s.cand_cap < batch)
@@ -808,7 +813,7 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
             s.cand_list = nullptr;
             s.cand_cnt  = nullptr;
             s.cand_cap  = 0;
-            const size_t items = batch > SEB_SPEC_MAX_BATCH ? batch : SEB_SPEC_MAX_BATCH;
+            const size_t items = batch;
             const size_t slots = items * c->spec_plan.total;
             CU(cudaMalloc(&s.cand_rows, slots * c->n * sizeof(uint32_t)));
             CU(cudaMalloc(&s.cand_list, slots * (size_t)(c->rej_cap ? c->rej_cap : 1) * sizeof(uint16_t)));
