@@ -197,7 +197,7 @@ int seb_encrypt_sym_seedct_device(seb_ctx *ctx, const float *d_values, size_t vl
 int seb_expand_seedct_device(seb_ctx *ctx, const uint8_t *d_shareable_seeds, const uint32_t *d_c0, size_t batch,
                              uint32_t *d_out);
 /* Small symmetric calls (up to 4 ciphertexts at n = 16384 x 6 primes, 16 at n = 4096 x 3) run every prime's uniform squeeze at once on speculated PRNG counters
- * (the counter of prime p depends on the redraws of the primes before it; all counters within 6 sigma of the mean
+ * (the counter of prime p depends on the redraws of the primes before it; all counters within 5 sigma of the mean
  * are squeezed in parallel and the right one is selected afterwards — same bytes, a third to a sixth of the
  * dependent work).  Returns how many squeezes fell outside their window and were redone on the spot
  * (diagnostic; synchronises the stream). */

@@ -419,7 +419,10 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     memset(&c->spec_plan, 0, sizeof c->spec_plan);
     if (!c->asym && nprimes >= 2)
     {
-        double sigmas = 6.0;  // SEB_UNIFORM_SPEC_SIGMAS narrows the windows so that tests can force the fallback
+        // 5 sigma: a true counter falls outside with probability 6e-7 per prime (and is then squeezed on the spot);
+        // 6 sigma measured 13 % slower at n = 16384, 4 sigma no faster.  SEB_UNIFORM_SPEC_SIGMAS overrides (tests force
+        // the fallback with 0).
+        double sigmas = 5.0;
         if (const char *v = getenv("SEB_UNIFORM_SPEC_SIGMAS"))
             if (*v) sigmas = atof(v);
         seb_uniform_spec_plan((int)n, c->mods, (int)nprimes, sigmas, &c->spec_plan);
@@ -784,13 +787,15 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 
 // seal_embedded.c:98-215 (symmetric branch): encode, e, then per prime sample a (the shareable
 // PRNG's counter runs on across primes, ckks_sym.c:219), then the fused c0 kernel.
-// Calls this small run every prime's squeeze at once on speculated counters (seb_sample.cu): as long as all the
-// candidate sponges of the call, one warp each, stay within what the machine runs at the warp-cooperative
-// kernel handles well: measured a win up to 8192 warps (profiles/r01_ab_sym_small_batches.txt), i.e. 4 ciphertexts
-// at n = 16384 x 6 primes (~1800 candidates each), 16 at n = 4096 x 3 primes (255 each).
+// Calls this small run every prime's squeeze at once on speculated counters (seb_sample.cu).  All candidate sponges
+// of the call run concurrently, one warp each, and the warp-cooperative permutation slows down as the machine
+// fills (2.9 us up to ~256 warps, 4.8 us at 2048, 7.9 us at 4096: profiles/r01_ab_uniform_coop.txt), while walking
+// the chain serially costs np squeezes at 2.9 us: speculation pays while the candidates number less than about
+// 1400 x np warps — 16-20 ciphertexts at n = 4096 x 3 primes (~215 candidates each), 4-5 at n = 16384 x 6 (~1500
+// each); measured in profiles/r01_ab_sym_small_batches.txt.
 // SEB_UNIFORM_SPEC=0/1 forces the choice for up to 64 ciphertexts (tests, A/B measurements).
 #define SEB_SPEC_MAX_BATCH 64
-#define SEB_SPEC_MAX_WARPS 8192
+#define SEB_SPEC_WARPS_PER_PRIME 1400
 
 // sample_poly_uniform for every prime of `batch` ciphertexts (the shareable PRNG's counter runs on across the
 // primes, ckks_sym.c:219): a_p0 = row of (item 0, prime 0), prime p is p_stride words further, item b ct_stride.
@@ -800,7 +805,8 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
     const int n = (int)c->n;
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
     const char *e   = getenv("SEB_UNIFORM_SPEC");
-    const bool fits = batch <= SEB_SPEC_MAX_BATCH && batch * ((size_t)c->spec_plan.total + 1) <= SEB_SPEC_MAX_WARPS;
+    const bool fits = batch <= SEB_SPEC_MAX_BATCH &&
+                      batch * ((size_t)c->spec_plan.total + 1) <= (size_t)SEB_SPEC_WARPS_PER_PRIME * c->np;
     const bool spec = c->spec_plan.total > 0 && ((e && *e) ? (atoi(e) != 0 && batch <= SEB_SPEC_MAX_BATCH) : fits);
     if (spec)
     {

@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__rest
 // The squeeze of prime p starts at counter c_p = p + (redraw calls of primes < p), which is only known once those
 // primes are done — but it is sharply distributed: the redraw calls of prime i have mean n r_i / (1 - r_i) and
 // variance n r_i / (1 - r_i)^2, r_i = the word rejection rate under q_i (1-2 %).  For a few ciphertexts the machine
-// is empty, so EVERY counter within +-6 sigma of the mean is squeezed at once (105 candidates for prime 1 at
-// n = 4096, 1760 over the five later primes at n = 16384), one warp each, beside prime 0; afterwards the chain is
+// is empty, so EVERY counter within +-5 sigma of the mean is squeezed at once (~90 candidates for prime 1 at
+// n = 4096, ~1500 over the five later primes at n = 16384), one warp each, beside prime 0; afterwards the chain is
 // resolved prime by prime: k_uniform_select copies the candidate the true counter points at into the output (or,
 // outside the window, squeezes it on the spot) and the usual fix-up follows.  Same bytes, same counters; the
 // dependent work shrinks from all primes' squeezes to one.
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128)
     }
     else
     {
-        // outside the speculated window (probability ~1e-9 per prime): squeeze it now
+        // outside the speculated window (probability ~6e-7 per prime at 5 sigma): squeeze it now
         const SebCoopLane c = seb_coop_setup(lane);
         const uint32_t cnt  = seb_coop_bulk_row(seeds + (size_t)b * SEB_SEED_BYTES, c0, row, list, n, mod, max_multiple, cap, c, lane);
         if (lane == 0)

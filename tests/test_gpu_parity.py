@@ -403,7 +403,7 @@ def test_encrypt_sym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
 def test_encrypt_sym_lone_call_paths(n, np_, mode, seb, torch_cuda, oracle_mod, orc, monkeypatch):
     """Lone symmetric calls run every prime's uniform squeeze at once on speculated PRNG counters
     (seb_launch_uniform_chain_spec).  Ciphertexts must equal the oracle's whichever way the chain is walked:
-    prime after prime (SEB_UNIFORM_SPEC=0), speculatively with the 6-sigma windows (no miss expected), and
+    prime after prime (SEB_UNIFORM_SPEC=0), speculatively with the 5-sigma windows (no miss expected), and
     speculatively with windows narrowed to +-2 counters so that most true counters miss and are re-squeezed on
     the spot (the fallback)."""
     torch = torch_cuda
