@@ -469,15 +469,13 @@ __global__ void __launch_bounds__(128)
 // of the bulk kernel every accepted candidate of a wave is placed in parallel (its rank among the
 // accepted candidates so far selects the list entry).  A list that overflowed its capacity (never
 // with SHAKE output and cap = n/8, but it must stay correct) falls back to scanning the row.
-__global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
-                                                     uint32_t *__restrict__ out, size_t ct_stride, int n,
-                                                     SebModulus mod, uint32_t max_multiple, int batch,
+// the fix-up of ciphertext b by one warp
+__device__ __forceinline__ void seb_uniform_fix_warp(const int b, const int lane, const uint8_t *__restrict__ seeds,
+                                                     uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
+                                                     size_t ct_stride, int n, const SebModulus &mod, uint32_t max_multiple,
                                                      const uint16_t *__restrict__ rej_idx,
                                                      const uint32_t *__restrict__ rej_cnt, uint32_t cap)
 {
-    const int lane = threadIdx.x & 31;
-    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= batch) return;
     uint32_t *row = out + (size_t)b * ct_stride;
     uint64_t s[8];
     load_seed(seeds, (size_t)b, s);
@@ -542,6 +540,77 @@ __global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__
     if (lane == 0) ctr[b] = (uint32_t)(last_used + 1);
 }
 
+__global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
+                                                     uint32_t *__restrict__ out, size_t ct_stride, int n,
+                                                     SebModulus mod, uint32_t max_multiple, int batch,
+                                                     const uint16_t *__restrict__ rej_idx,
+                                                     const uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int b    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    seb_uniform_fix_warp(b, lane, seeds, ctr, out, ct_stride, n, mod, max_multiple, rej_idx, rej_cnt, cap);
+}
+
+// The fix-up for a handful of ciphertexts: one CTA per ciphertext, every thread one candidate, so that the ~n/50
+// candidates a polynomial needs come out of ONE round of permutations instead of n/1600 dependent 32-candidate
+// waves (10 at n = 16384: 69 us of a lone call's 85 us per prime).  Ranks are counted across the CTA (ballot per
+// warp, prefix over the warps); a second round only if the first did not yield enough accepted candidates.
+// Ciphertexts whose reject list overflowed take the one-warp scanning path.
+__global__ void __launch_bounds__(512) k_uniform_fix_wide(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
+                                                          uint32_t *__restrict__ out, size_t ct_stride, int n,
+                                                          SebModulus mod, uint32_t max_multiple, int batch,
+                                                          const uint16_t *__restrict__ rej_idx,
+                                                          const uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    __shared__ uint32_t s_count[16];
+    __shared__ uint32_t s_last;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (b >= batch) return;
+    const uint32_t cnt = rej_cnt[b];
+    if (cnt > cap)  // CTA-uniform
+    {
+        if (warp == 0) seb_uniform_fix_warp(b, lane, seeds, ctr, out, ct_stride, n, mod, max_multiple, rej_idx, rej_cnt, cap);
+        return;
+    }
+    uint32_t *row        = out + (size_t)b * ct_stride;
+    const uint16_t *list = rej_idx + (size_t)b * cap;
+    uint64_t s[8];
+    load_seed(seeds, (size_t)b, s);
+    const uint32_t c0  = ctr[b];
+    uint32_t wave_base = c0 + 1;  // counter of thread 0's candidate in the next round
+    uint32_t done      = 0;
+    if (tid == 0) s_last = c0;
+    __syncthreads();  // ctr[b] is read by everybody before thread 0 overwrites it at the end
+    while (done < cnt)
+    {
+        uint64_t a[25];
+        seb_prng_init(a, s, (uint64_t)wave_base + (uint64_t)tid);
+        seb_keccak_f1600<12>(a);  // 4 bytes per call
+        const uint32_t cand  = (uint32_t)a[0];
+        const bool ok        = cand < max_multiple;
+        const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == 0) s_count[warp] = (uint32_t)__popc(avail);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < nwarps; w++)
+        {
+            const uint32_t cw = s_count[w];
+            before += w < warp ? cw : 0u;
+            total += cw;
+        }
+        const uint32_t rank = done + before + (uint32_t)__popc(avail & ((1u << lane) - 1u));  // this candidate's turn
+        const bool used     = ok && rank < cnt;
+        if (used) row[list[rank]] = seb_barrett32(cand, mod);
+        const uint32_t um = __ballot_sync(0xFFFFFFFFu, used);
+        if (um && lane == 0) atomicMax(&s_last, wave_base + (uint32_t)(warp * 32 + 31 - __clz(um)));
+        done += total < cnt - done ? total : cnt - done;
+        wave_base += blockDim.x;
+        __syncthreads();  // s_count is rewritten by the next round; s_last is complete
+    }
+    if (tid == 0) ctr[b] = s_last + 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -567,6 +636,28 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
     if (batch <= 0) return;
     const size_t total = (size_t)batch * npoly * (n / 16);
     k_sample_cbd<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(seeds, ctr_base, e_out, n, npoly, batch);
+}
+
+// fix-up launch: a CTA per ciphertext with one round of ~n/50 + 32 candidates for a handful of ciphertexts (latency),
+// a warp per ciphertext with 32-candidate waves otherwise (throughput).  SEB_UNIFORM_FIX_WIDE=0/1 forces the choice.
+#define SEB_FIX_WIDE_MAX_BATCH 64
+static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
+                                   const SebModulus &mod, uint32_t max_multiple, int batch, uint16_t *rej_idx,
+                                   uint32_t *rej_cnt, uint32_t rej_cap, cudaStream_t st)
+{
+    const char *e   = getenv("SEB_UNIFORM_FIX_WIDE");
+    const bool wide = (e && *e) ? atoi(e) != 0 : batch <= SEB_FIX_WIDE_MAX_BATCH;
+    if (wide)
+    {
+        // expected rejections: 2 % of n at most (30-bit primes), plus head-room for the candidates' own rejections
+        int threads = ((n / 50 + 32 + 31) / 32) * 32;
+        if (threads > 512) threads = 512;
+        k_uniform_fix_wide<<<batch, threads, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt,
+                                                      rej_cap);
+    }
+    else
+        k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                       rej_cnt, rej_cap);
 }
 
 // Speculation windows for a parameter set (host, once per context).  sigmas: half-width in standard deviations.
@@ -613,8 +704,7 @@ void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t
             k_uniform_select<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, plan.p[p],
                                                               plan.total, batch, cand_rows, cand_list, cand_cnt, rej_idx,
                                                               rej_cnt, rej_cap, misses);
-        k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, batch, rej_idx,
-                                                       rej_cnt, rej_cap);
+        seb_launch_uniform_fix(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, st);
     }
 }
 
@@ -637,6 +727,5 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     else
         k_uniform_bulk<<<(batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
                                                          rej_idx, rej_cnt, rej_cap);
-    k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
-                                                   rej_cnt, rej_cap);
+    seb_launch_uniform_fix(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, st);
 }

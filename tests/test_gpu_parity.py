@@ -136,15 +136,18 @@ def test_samplers_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert np.array_equal(e[b, 0], e0) and np.array_equal(e[b, 1], e1), (n, b)
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("coop", ["0", "1"])
 @pytest.mark.parametrize("n,np_", CONFIGS)
-def test_sampler_uniform_both_kernels(n, np_, coop, seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
+def test_sampler_uniform_both_kernels(n, np_, coop, wide, seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
     """sample_poly_uniform (sample.c:39-57) through each of the two bulk kernels — one sequential sponge per thread
-    (large batches) and the warp-cooperative sponge spread over 25 lanes (small batches) — forced with
-    SEB_UNIFORM_COOP: same polynomials, same counters as the oracle, for a batch that is not a multiple of
-    the warps per CTA."""
+    (large batches) and the warp-cooperative sponge spread over 25 lanes (small batches), forced with
+    SEB_UNIFORM_COOP — and each of the two fix-up kernels — a warp per ciphertext with 32-candidate waves and a CTA
+    per ciphertext with one round of candidates, forced with SEB_UNIFORM_FIX_WIDE: same polynomials, same
+    counters as the oracle, for a batch that is not a multiple of the warps per CTA."""
     torch = torch_cuda
     monkeypatch.setenv("SEB_UNIFORM_COOP", coop)
+    monkeypatch.setenv("SEB_UNIFORM_FIX_WIDE", wide)
     ctx = ctxs(n, np_, False)
     batch = 9
     seeds = oracle_mod.make_seeds(batch, b"uniform-k-%d" % n)
@@ -160,7 +163,7 @@ def test_sampler_uniform_both_kernels(n, np_, coop, seb, torch_cuda, oracle_mod,
         c = 0
         for p, q in enumerate(ctx.primes):
             exp, c = orc.sample_uniform(n, q, seeds[b], c)
-            assert np.array_equal(out[b, p], exp), (n, coop, b, p)
+            assert np.array_equal(out[b, p], exp), (n, coop, wide, b, p)
         assert ctr[b] == c
 
 
@@ -187,13 +190,15 @@ def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert ctr[b] == c
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("cap", ["0", "3", "70"])
-def test_sampler_uniform_list_overflow(cap, seb, torch_cuda, oracle_mod, orc, monkeypatch):
+def test_sampler_uniform_list_overflow(cap, wide, seb, torch_cuda, oracle_mod, orc, monkeypatch):
     """The uniform sampler's reject lists have a fixed capacity; ciphertexts that overflow it take the
     scanning fix-up.  Forced here with tiny capacities (none / most / some ciphertexts overflow at
     n = 4096, where ~76 of 4096 words are rejected per prime) and through the full symmetric path."""
     torch = torch_cuda
     monkeypatch.setenv("SEB_UNIFORM_LIST_CAP", cap)
+    monkeypatch.setenv("SEB_UNIFORM_FIX_WIDE", wide)
     n, np_, batch = 4096, 3, 7
     ctx = seb.Context(n, np_, False, device=0)
     try:
