@@ -408,6 +408,15 @@ def run_b200_arm(args) -> None:
         roofline["issue_bound"] = {"pipe": "fma", "achieved": rate, "peak": BUTTERFLY_PEAK_PER_S, "unit": "butterflies/s",
                                    "frac": rate / BUTTERFLY_PEAK_PER_S,
                                    "peak_source": "tools/ubench_bfly register-only butterflies (profiles/)"}
+    # every kernel of the step against the HBM peak (algorithmic bytes / measured duration), beside the dominant one above
+    sym_of = {"encode": "k_encode", "sample_ternary": "k_sample_ternary", "sample_cbd": "k_sample_cbd", "encrypt": "k_encrypt_asym"}
+    per_kernel = {}
+    for nm, ms_k in zip(names, avg):
+        if ms_k > 0:
+            gbs = alg_bytes[nm] * batch / (ms_k * 1e-3) / 1e9
+            per_kernel[sym_of[nm]] = {"ms": float(ms_k), "share_of_step": float(ms_k / max(avg.sum(), 1e-9)),
+                                      "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+    roofline["all_kernels"] = per_kernel
     ntt_gbs = 8 * n * np_ * batch / (ntt_ms * 1e-3) / 1e9
     ntt_micro = {"kernel": "k_ntt_forward", "bound": "hbm", "achieved": ntt_gbs, "peak": peak, "unit": "GB/s",
                  "frac": ntt_gbs / peak, "traffic": ncu_traffic("k_ntt_forward", batch), "ms_per_launch": ntt_ms,
