@@ -137,6 +137,12 @@ void se_b200_set_sym_seed_ct(int on);
  * shareable_seeds [batch][64] are required (they are the other half of each ciphertext); seeds may be NULL. */
 bool se_encrypt_batch_seedct(const uint8_t *shareable_seeds, const uint8_t *seeds, const flpt *v, size_t vlen,
                              size_t batch, ZZ *c0_out, SE_PARMS *se_parms);
+/* SEAL-side ciphertext layout (adapter/fileops.cpp:518-527): the stream above is [nprimes][2][n] 32-bit words per
+ * ciphertext; a seal::Ciphertext of size 2 holds [2][nprimes][n] 64-bit coefficients (c0 of every prime, then c1 of
+ * every prime).  Host-side conversions for `batch` ciphertexts, both directions; `from` fails with
+ * SE_ERR_INVALD_ARGUMENT when a coefficient does not fit 32 bits. */
+int seb_ct_to_seal_layout(const ZZ *ct, size_t batch, size_t nprimes, size_t n, uint64_t *seal);
+int seb_ct_from_seal_layout(const uint64_t *seal, size_t batch, size_t nprimes, size_t n, ZZ *ct);
 /* The context behind the static SE_PARMS (for the seb_* calls below); NULL before se_setup. */
 struct seb_ctx *se_b200_context(SE_PARMS *se_parms);
 
@@ -149,21 +155,30 @@ const char *seb_last_error(void);
 
 /* primes == NULL: the reference's default chain for (n, nprimes) (parameters.c:129-230) with its
  * tabulated 2n-th roots (ntt.c:199-291) and default scale when scale <= 0.  With explicit primes
- * (each < 2^30 and = 1 mod 2n), psis[i] must be a primitive 2n-th root of unity mod primes[i]; psis == NULL
- * takes the reference's tabulated root where there is one and seb_minimal_psi otherwise.  device < 0:
- * keep the current CUDA device. */
+ * (distinct, each a PRIME < 2^30 and = 1 mod 2n: checked, deterministic Miller-Rabin), psis[i] must be a
+ * primitive 2n-th root of unity mod primes[i]; psis == NULL takes the reference's tabulated root where there is
+ * one and seb_minimal_psi otherwise.  device < 0: keep the current CUDA device.
+ * Test / A-B switches are read from the environment here, once (SEB_UNIFORM_COOP, SEB_UNIFORM_FIX_WIDE,
+ * SEB_UNIFORM_SPEC, SEB_UNIFORM_PAIR, SEB_HOST_CHUNK, SEB_UNIFORM_LIST_CAP, SEB_UNIFORM_SPEC_SIGMAS); afterwards
+ * seb_set_option changes them. */
 seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes, const uint32_t *psis,
                     double scale, int asym, int device);
 void seb_destroy(seb_ctx *ctx);
 /* Smallest primitive 2n-th root of unity mod q, 0 if there is none (host arithmetic, no GPU needed).
  * Equals the reference's table get_ntt_root (ntt.c:199-291) wherever that is defined. */
 uint32_t seb_minimal_psi(size_t n, uint32_t q);
+/* name in {"uniform_coop", "uniform_fix_wide", "uniform_spec", "uniform_pair"}: 0 / 1 force a code path, a negative
+ * value restores the automatic choice; "host_chunk": items per chunk of the host-pointer pipeline (<= 0: automatic). */
+int seb_set_option(seb_ctx *ctx, const char *name, long value);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own */
 int seb_set_stream(seb_ctx *ctx, void *cuda_stream);
 /* pk0, pk1: host [nprimes][n], NTT form (files pk{0,1}_ntt_<n>_<q>.dat, fileops.c:172-204) */
 int seb_set_public_key(seb_ctx *ctx, const uint32_t *pk0, const uint32_t *pk1);
 /* sk: host n/4 bytes, 2 bits per coefficient (file sk_<n>.dat, fileops.c:140-170) */
 int seb_set_secret_key(seb_ctx *ctx, const uint8_t *sk_packed);
+/* ckks_setup_s with sample_s (ckks_sym.c:162-173): s = sample_small_poly_ternary_prng_96(PRNG(seed), counter 0)
+ * (sample.c:218-242) on the GPU; sk_out receives the n/4 packed bytes (sk_<n>.dat format) and the key is installed */
+int seb_gen_secret_key(seb_ctx *ctx, const uint8_t *seed, uint8_t *sk_out);
 /* gen_pk (ckks_asym.c:159-171) on the GPU: loads sk (as seb_set_secret_key), samples ep = CBD(PRNG(ep_seed))
  * and, per prime p, a = uniform(PRNG(a_seed_base with byte 0 := p)); writes pk0 = -(a (.) ntt(s)) + ntt(ep)
  * and pk1 = a to host [nprimes][n] and installs them when the context is asymmetric */
@@ -248,6 +263,10 @@ int seb_intt_device(seb_ctx *ctx, uint32_t *d_polys, size_t batch);
  * an asymmetric context).  Symmetric ciphertexts must carry c1 = a (ref_quirk off). */
 int seb_decrypt_decode_device(seb_ctx *ctx, const uint32_t *d_ct, size_t batch, size_t prime_idx, size_t vlen,
                               float *d_values_out);
+/* per-item digest of d_words [items][words_per_item] (words_per_item % 4 == 0):
+ * d_digests[b] = sum_i mix64((i << 32) | word_i) mod 2^64 with the splitmix64 finaliser — 8 bytes per ciphertext
+ * to compare a full-size batch with the reference run on the host (tests/, oracle/ref_shim.c: ref_encrypt_digests) */
+int seb_digest_device(seb_ctx *ctx, const uint32_t *d_words, size_t words_per_item, size_t items, uint64_t *d_digests);
 /* first 136-byte block of SHAKE256(seed_i || LE64(counter_i)): d_out [count][17] u64 */
 int seb_prng_blocks_device(seb_ctx *ctx, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
                            uint64_t *d_out);

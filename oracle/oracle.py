@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libseref.so")
 REFERENCE_SRC = "/root/reference/device/lib"
+REF_DEMO = os.path.join(HERE, "_ref", "se_reference_api_demo")  # built by `make refdemo` (reference headers)
 
 SEED_BYTES = 64
 
@@ -40,6 +41,9 @@ def build(ref: bool | None = None) -> None:
         ref = os.path.isdir(REFERENCE_SRC)
     if ref:
         targets.append("ref")
+        # the reference-header build of the reference-API-only demo, linked against the product library
+        if os.path.exists(os.path.join(HERE, "..", "seal-embedded_b200", "libseal_embedded_b200.so")):
+            targets.append("refdemo")
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 
@@ -57,11 +61,11 @@ def _seed(seed) -> np.ndarray:
 # --------------------------------------------------------------------------------------------
 # deterministic synthetic inputs shared by tests, fixtures and the bench
 # --------------------------------------------------------------------------------------------
-def make_seeds(batch: int, tag: bytes = b"se-b200") -> np.ndarray:
-    """seed[b] = SHAKE256(tag || LE64(b))[0:64]"""
+def make_seeds(batch: int, tag: bytes = b"se-b200", start: int = 0) -> np.ndarray:
+    """seed[b] = SHAKE256(tag || LE64(start + b))[0:64]"""
     out = np.empty((batch, SEED_BYTES), dtype=np.uint8)
     for b in range(batch):
-        out[b] = np.frombuffer(hashlib.shake_256(tag + struct.pack("<Q", b)).digest(SEED_BYTES), dtype=np.uint8)
+        out[b] = np.frombuffer(hashlib.shake_256(tag + struct.pack("<Q", start + b)).digest(SEED_BYTES), dtype=np.uint8)
     return out
 
 
@@ -127,6 +131,15 @@ class Oracle:
         L.orc_encrypt_asym_batch.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, _f32p, C.c_size_t, _u8p, _u32p,
                                              _u32p, _u32p]
         L.orc_encrypt_asym_batch.restype = C.c_int
+        L.orc_encrypt_asym_ex.argtypes = [C.c_size_t, C.c_size_t, _u32p, _u32p, C.c_double, _f32p, C.c_size_t, _u8p,
+                                          _u32p, _u32p, _u32p]
+        L.orc_encrypt_asym_ex.restype = C.c_int
+        L.orc_encrypt_sym_ex.argtypes = [C.c_size_t, C.c_size_t, _u32p, _u32p, C.c_double, _f32p, C.c_size_t, _u8p,
+                                         _u8p, _u8p, C.c_int, _u32p]
+        L.orc_encrypt_sym_ex.restype = C.c_int
+        L.orc_gen_pk_prime_ex.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, _u8p, _u8p, _i8p, _u32p, _u32p]
+        L.orc_decrypt_ntt_ex.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, _u32p, _u32p, _u8p, _u32p]
+        L.orc_ntt_psi.argtypes = [C.c_size_t, C.c_uint32, C.c_uint32, _u32p]
 
     # -- hashing / prng
     def shake256(self, data: bytes, outlen: int) -> bytes:
@@ -287,6 +300,51 @@ class Oracle:
                                       _ptr(pk0[p], _u32p), _ptr(pk1[p], _u32p))
         return pk0, pk1
 
+    # -- the same with an explicit chain (custom primes: "parity unpinned" against the reference, se_oracle.h)
+    def encrypt_asym_ex(self, n, primes, psis, scale, values, seed, pk0, pk1):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        pr = np.ascontiguousarray(primes, dtype=np.uint32)
+        ps = np.ascontiguousarray(psis, dtype=np.uint32)
+        pk0 = np.ascontiguousarray(pk0, dtype=np.uint32)
+        pk1 = np.ascontiguousarray(pk1, dtype=np.uint32)
+        out = np.zeros((len(pr), 2, n), np.uint32)
+        ok = self.lib.orc_encrypt_asym_ex(n, len(pr), _ptr(pr, _u32p), _ptr(ps, _u32p), float(scale), _ptr(v, _f32p),
+                                          v.size, _ptr(_seed(seed), _u8p), _ptr(pk0, _u32p), _ptr(pk1, _u32p),
+                                          _ptr(out, _u32p))
+        return bool(ok), out
+
+    def encrypt_sym_ex(self, n, primes, psis, scale, values, share_seed, seed, sk, ref_quirk=False):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        pr = np.ascontiguousarray(primes, dtype=np.uint32)
+        ps = np.ascontiguousarray(psis, dtype=np.uint32)
+        sk = np.ascontiguousarray(sk, dtype=np.uint8)
+        out = np.zeros((len(pr), 2, n), np.uint32)
+        ok = self.lib.orc_encrypt_sym_ex(n, len(pr), _ptr(pr, _u32p), _ptr(ps, _u32p), float(scale), _ptr(v, _f32p),
+                                         v.size, _ptr(_seed(share_seed), _u8p), _ptr(_seed(seed), _u8p), _ptr(sk, _u8p),
+                                         int(ref_quirk), _ptr(out, _u32p))
+        return bool(ok), out
+
+    def gen_pk_ex(self, n, primes, psis, sk, ep_seed=bytes([7]) * 64, seed_base=bytes([9]) * 64):
+        sk = np.ascontiguousarray(sk, dtype=np.uint8)
+        ep, _ = self.sample_cbd(n, ep_seed)
+        pk0 = np.zeros((len(primes), n), np.uint32)
+        pk1 = np.zeros((len(primes), n), np.uint32)
+        for p, (q, psi) in enumerate(zip(primes, psis)):
+            sd = bytearray(seed_base)
+            sd[0] = p
+            self.lib.orc_gen_pk_prime_ex(n, int(q), int(psi), _ptr(_seed(sd), _u8p), _ptr(sk, _u8p), _ptr(ep, _i8p),
+                                         _ptr(pk0[p], _u32p), _ptr(pk1[p], _u32p))
+        return pk0, pk1
+
+    def decrypt_decode_ex(self, n, primes, psis, scale, ct, sk, vlen, prime_idx=0):
+        q, psi = int(primes[prime_idx]), int(psis[prime_idx])
+        c0 = np.ascontiguousarray(ct[prime_idx, 0], dtype=np.uint32)
+        c1 = np.ascontiguousarray(ct[prime_idx, 1], dtype=np.uint32)
+        sk = np.ascontiguousarray(sk, dtype=np.uint8)
+        ptn = np.empty(n, np.uint32)
+        self.lib.orc_decrypt_ntt_ex(n, q, psi, _ptr(c0, _u32p), _ptr(c1, _u32p), _ptr(sk, _u8p), _ptr(ptn, _u32p))
+        return self.decode(n, q, self.intt(n, q, ptn, psi), vlen, scale)
+
     def decrypt_ntt(self, n: int, q: int, c0, c1, sk) -> np.ndarray:
         c0 = np.ascontiguousarray(c0, dtype=np.uint32)
         c1 = np.ascontiguousarray(c1, dtype=np.uint32)
@@ -300,6 +358,19 @@ class Oracle:
         q = self.primes(n, np_)[prime_idx]
         ptn = self.decrypt_ntt(n, q, ct[prime_idx, 0], ct[prime_idx, 1], sk)
         return self.decode(n, q, self.intt(n, q, ptn), vlen)
+
+
+def digest_words(words: np.ndarray) -> np.ndarray:
+    """Per-row digest of a [items][W] u32 array: sum_i mix64((i << 32) | w_i) mod 2^64 (splitmix64 finaliser) — the
+    function of seb_digest_device (csrc/seb_verify.cu) and ref_encrypt_digests (ref_shim.c), in numpy."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    w = w.reshape(w.shape[0], -1)
+    with np.errstate(over="ignore"):
+        z = (np.arange(w.shape[1], dtype=np.uint64) << np.uint64(32))[None, :] | w.astype(np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return z.sum(axis=1, dtype=np.uint64)
 
 
 def write_key_files(workdir: str, n: int, primes: list[int], sk: np.ndarray | None, pk0=None, pk1=None) -> str:
@@ -343,6 +414,12 @@ class ReferenceLib:
         L.ref_encrypt_seeded.restype = C.c_int
         L.ref_encrypt_loop.argtypes = [C.c_size_t, _u8p, _u8p, _f32p, C.c_size_t, _u32p]
         L.ref_encrypt_loop.restype = C.c_double
+        if hasattr(L, "ref_encrypt_digests"):
+            L.ref_encrypt_digests.argtypes = [C.c_size_t, _u8p, _u8p, _f32p, C.c_size_t, C.c_size_t, _u32p,
+                                              C.POINTER(C.c_uint64)]
+            L.ref_encrypt_digests.restype = C.c_size_t
+            L.ref_digest_words.argtypes = [_u32p, C.c_size_t]
+            L.ref_digest_words.restype = C.c_uint64
         L.ref_index_map.argtypes = [C.c_size_t, _u16p]
         L.ref_encode.argtypes = [C.c_size_t, _f32p, C.c_size_t, _i64p]
         L.ref_encode.restype = C.c_int
@@ -414,6 +491,23 @@ class ReferenceLib:
         out = np.zeros((self.np_, 2, self.n), np.uint32)
         return float(self.lib.ref_encrypt_loop(v.shape[0], ss, _ptr(s, _u8p), _ptr(v, _f32p), v.shape[1],
                                                _ptr(out, _u32p)))
+
+    def encrypt_digests(self, share_seeds, seeds: np.ndarray, values: np.ndarray) -> np.ndarray:
+        """se_encrypt_seeded over consecutive items; returns the per-item 64-bit digest of each byte stream
+        (the function seb_digest_device computes on the GPU)."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        s = np.ascontiguousarray(seeds, dtype=np.uint8)
+        ss = None
+        if share_seeds is not None:
+            share_seeds = np.ascontiguousarray(share_seeds, dtype=np.uint8)
+            ss = _ptr(share_seeds, _u8p)
+        words = 2 * self.np_ * self.n
+        scratch = np.zeros(words, np.uint32)
+        out = np.zeros(v.shape[0], np.uint64)
+        bad = self.lib.ref_encrypt_digests(v.shape[0], ss, _ptr(s, _u8p), _ptr(v, _f32p), v.shape[1], words,
+                                           _ptr(scratch, _u32p), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        assert bad == 0, f"{bad} reference calls failed"
+        return out
 
     # -- stage level
     def index_map(self, n: int) -> np.ndarray:

@@ -110,6 +110,39 @@ double ref_encrypt_loop(size_t count, const uint8_t *share_seeds, const uint8_t 
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* The per-item digest of seb_digest_device (seal-embedded_b200/csrc/seb_verify.cu: k_digest):
+ * sum_i mix64((i << 32) | word_i) mod 2^64, mix64 = the splitmix64 finaliser. */
+static uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+uint64_t ref_digest_words(const uint32_t *w, size_t count)
+{
+    uint64_t acc = 0;
+    for (size_t i = 0; i < count; i++) acc += mix64(((uint64_t)i << 32) | w[i]);
+    return acc;
+}
+
+/* `count` consecutive items through se_encrypt_seeded (the reference's own API, byte stream captured from the
+ * send callback); digests[b] = digest of item b's [nprimes][2][n] words.  Returns how many calls returned false. */
+size_t ref_encrypt_digests(size_t count, const uint8_t *share_seeds, const uint8_t *seeds, const float *v,
+                           size_t vlen, size_t words_per_item, uint32_t *scratch, uint64_t *digests)
+{
+    size_t bad = 0;
+    for (size_t b = 0; b < count; b++)
+    {
+        g_sink    = (uint8_t *)scratch;
+        g_sinkpos = 0;
+        bool ok = se_encrypt_seeded(share_seeds ? (uint8_t *)share_seeds + 64 * b : NULL, (uint8_t *)seeds + 64 * b,
+                                    capture_send, (void *)(v + b * vlen), vlen * sizeof(float), false, g_se);
+        bad += !ok || g_sinkpos != words_per_item * sizeof(uint32_t);
+        digests[b] = ref_digest_words(scratch, words_per_item);
+    }
+    return bad;
+}
+
 /* ---- stage-level entry points (own scratch, independent of the API's static state) ---- */
 
 static void local_parms(size_t n, size_t np, int asym, Parms *parms)

@@ -526,12 +526,17 @@ void orc_ntt(size_t n, uint32_t q, const uint32_t *roots, uint32_t *vec)
     }
 }
 
-void orc_ntt_default(size_t n, uint32_t q, uint32_t *vec)
+void orc_ntt_psi(size_t n, uint32_t q, uint32_t psi, uint32_t *vec)
 {
     uint32_t *roots = malloc(n * sizeof *roots);
-    orc_ntt_roots(n, q, orc_ntt_root(n, q), roots);
+    orc_ntt_roots(n, q, psi, roots);
     orc_ntt(n, q, roots, vec);
     free(roots);
+}
+
+void orc_ntt_default(size_t n, uint32_t q, uint32_t *vec)
+{
+    orc_ntt_psi(n, q, orc_ntt_root(n, q), vec);
 }
 
 /* Inverse of orc_ntt (test helper): undo the stages last to first, then scale by n^-1. */
@@ -585,18 +590,19 @@ static void pointwise_add(size_t n, uint32_t q, uint32_t *a, const uint32_t *b) 
 }
 
 /* seal_embedded.c:98-215 (asymmetric branch), ckks_asym.c:173-203 and :205-286 */
-int orc_encrypt_asym(size_t n, size_t np, const float *values, size_t vlen, const uint8_t *seed,
-                     const uint32_t *pk0, const uint32_t *pk1, uint32_t *out)
+/* The chain is explicit (primes, the 2n-th roots psis and the scale): the default entry point below passes the
+ * reference's tables; a caller chain (set_custom_parms_ckks, parameters.c:232-249) passes its own. */
+int orc_encrypt_asym_ex(size_t n, size_t np, const uint32_t *primes, const uint32_t *psis, double scale,
+                        const float *values, size_t vlen, const uint8_t *seed, const uint32_t *pk0,
+                        const uint32_t *pk1, uint32_t *out)
 {
-    uint32_t primes[16];
-    if (!orc_default_primes(n, np, primes)) return 0;
     int64_t *pt  = malloc(n * sizeof *pt);
     uint8_t *u   = malloc(n / 4);
     int8_t *e    = malloc(n);
     int8_t *e1   = malloc(n);
     uint32_t *t  = malloc(n * sizeof *t);
     uint32_t *nu = malloc(n * sizeof *nu);
-    int ok       = orc_encode(n, orc_default_scale(n), values, vlen, pt);
+    int ok       = orc_encode(n, scale, values, vlen, pt);
     if (ok)
     {
         uint64_t ctr = 0;
@@ -607,19 +613,20 @@ int orc_encrypt_asym(size_t n, size_t np, const float *values, size_t vlen, cons
         for (size_t p = 0; p < np; p++)
         {
             uint32_t q   = primes[p];
+            uint32_t psi = psis[p];
             uint32_t *c0 = out + (2 * p) * n;
             uint32_t *c1 = out + (2 * p + 1) * n;
             orc_expand_ternary(n, q, u, nu);
-            orc_ntt_default(n, q, nu);
+            orc_ntt_psi(n, q, psi, nu);
             memcpy(c1, pk1 + p * n, n * sizeof *c1);
             memcpy(c0, pk0 + p * n, n * sizeof *c0);
             pointwise_mul(n, q, c1, nu);
             pointwise_mul(n, q, c0, nu);
             orc_reduce_small(n, q, e1, t);
-            orc_ntt_default(n, q, t);
+            orc_ntt_psi(n, q, psi, t);
             pointwise_add(n, q, c1, t);
             orc_reduce_pte(n, q, pt, t);
-            orc_ntt_default(n, q, t);
+            orc_ntt_psi(n, q, psi, t);
             pointwise_add(n, q, c0, t);
         }
     }
@@ -632,35 +639,48 @@ int orc_encrypt_asym(size_t n, size_t np, const float *values, size_t vlen, cons
     return ok;
 }
 
+static int default_chain(size_t n, size_t np, uint32_t *primes, uint32_t *psis)
+{
+    if (!orc_default_primes(n, np, primes)) return 0;
+    for (size_t p = 0; p < np; p++) psis[p] = orc_ntt_root(n, primes[p]);
+    return 1;
+}
+
+int orc_encrypt_asym(size_t n, size_t np, const float *values, size_t vlen, const uint8_t *seed,
+                     const uint32_t *pk0, const uint32_t *pk1, uint32_t *out)
+{
+    uint32_t primes[16], psis[16];
+    if (!default_chain(n, np, primes, psis)) return 0;
+    return orc_encrypt_asym_ex(n, np, primes, psis, orc_default_scale(n), values, vlen, seed, pk0, pk1, out);
+}
+
 /* one prime of ckks_sym.c:199-301; a is left in c1, ntt(m+e) in ntt_pte */
-static void sym_core(size_t n, uint32_t q, const uint8_t *share_seed, uint64_t *ctr_a,
+static void sym_core(size_t n, uint32_t q, uint32_t psi, const uint8_t *share_seed, uint64_t *ctr_a,
                      const uint8_t *sk_packed, const int64_t *pt, const int8_t *ep, uint32_t *c0,
                      uint32_t *c1, uint32_t *ntt_pte)
 {
     orc_sample_uniform(n, q, share_seed, ctr_a, c1);
     orc_expand_ternary(n, q, sk_packed, c0);
-    orc_ntt_default(n, q, c0);
+    orc_ntt_psi(n, q, psi, c0);
     pointwise_mul(n, q, c0, c1);
     for (size_t i = 0; i < n; i++) c0[i] = orc_neg_mod(c0[i], q);
     if (ep)
         orc_reduce_small(n, q, ep, ntt_pte);
     else
         orc_reduce_pte(n, q, pt, ntt_pte);
-    orc_ntt_default(n, q, ntt_pte);
+    orc_ntt_psi(n, q, psi, ntt_pte);
     pointwise_add(n, q, c0, ntt_pte);
 }
 
 /* seal_embedded.c:98-215 (symmetric branch), ckks_sym.c:181-197 and :199-301 */
-int orc_encrypt_sym(size_t n, size_t np, const float *values, size_t vlen,
-                    const uint8_t *share_seed, const uint8_t *seed, const uint8_t *sk_packed,
-                    int ref_quirk, uint32_t *out)
+int orc_encrypt_sym_ex(size_t n, size_t np, const uint32_t *primes, const uint32_t *psis, double scale,
+                       const float *values, size_t vlen, const uint8_t *share_seed, const uint8_t *seed,
+                       const uint8_t *sk_packed, int ref_quirk, uint32_t *out)
 {
-    uint32_t primes[16];
-    if (!orc_default_primes(n, np, primes)) return 0;
     int64_t *pt = malloc(n * sizeof *pt);
     int8_t *e   = malloc(n);
     uint32_t *t = malloc(n * sizeof *t);
-    int ok      = orc_encode(n, orc_default_scale(n), values, vlen, pt);
+    int ok      = orc_encode(n, scale, values, vlen, pt);
     if (ok)
     {
         uint64_t ctr_e = 0, ctr_a = 0;
@@ -670,7 +690,7 @@ int orc_encrypt_sym(size_t n, size_t np, const float *values, size_t vlen,
         {
             uint32_t *c0 = out + (2 * p) * n;
             uint32_t *c1 = out + (2 * p + 1) * n;
-            sym_core(n, primes[p], share_seed, &ctr_a, sk_packed, pt, NULL, c0, c1, t);
+            sym_core(n, primes[p], psis[p], share_seed, &ctr_a, sk_packed, pt, NULL, c0, c1, t);
             if (ref_quirk) memcpy(c1, t, n * sizeof *c1);
         }
     }
@@ -680,13 +700,40 @@ int orc_encrypt_sym(size_t n, size_t np, const float *values, size_t vlen,
     return ok;
 }
 
-void orc_gen_pk_prime(size_t n, uint32_t q, const uint8_t *seed, const uint8_t *sk_packed,
-                      const int8_t *ep, uint32_t *pk0, uint32_t *pk1)
+int orc_encrypt_sym(size_t n, size_t np, const float *values, size_t vlen,
+                    const uint8_t *share_seed, const uint8_t *seed, const uint8_t *sk_packed,
+                    int ref_quirk, uint32_t *out)
+{
+    uint32_t primes[16], psis[16];
+    if (!default_chain(n, np, primes, psis)) return 0;
+    return orc_encrypt_sym_ex(n, np, primes, psis, orc_default_scale(n), values, vlen, share_seed, seed, sk_packed,
+                              ref_quirk, out);
+}
+
+void orc_gen_pk_prime_ex(size_t n, uint32_t q, uint32_t psi, const uint8_t *seed, const uint8_t *sk_packed,
+                         const int8_t *ep, uint32_t *pk0, uint32_t *pk1)
 {
     uint64_t ctr = 0;
     uint32_t *t  = malloc(n * sizeof *t);
-    sym_core(n, q, seed, &ctr, sk_packed, NULL, ep, pk0, pk1, t);
+    sym_core(n, q, psi, seed, &ctr, sk_packed, NULL, ep, pk0, pk1, t);
     free(t);
+}
+
+void orc_gen_pk_prime(size_t n, uint32_t q, const uint8_t *seed, const uint8_t *sk_packed,
+                      const int8_t *ep, uint32_t *pk0, uint32_t *pk1)
+{
+    orc_gen_pk_prime_ex(n, q, orc_ntt_root(n, q), seed, sk_packed, ep, pk0, pk1);
+}
+
+void orc_decrypt_ntt_ex(size_t n, uint32_t q, uint32_t psi, const uint32_t *c0, const uint32_t *c1,
+                        const uint8_t *sk_packed, uint32_t *pt_ntt)
+{
+    uint32_t *s = malloc(n * sizeof *s);
+    orc_expand_ternary(n, q, sk_packed, s);
+    orc_ntt_psi(n, q, psi, s);
+    for (size_t i = 0; i < n; i++)
+        pt_ntt[i] = orc_add_mod(orc_mul_mod(c1[i], s[i], q), c0[i], q);
+    free(s);
 }
 
 void orc_decrypt_ntt(size_t n, uint32_t q, const uint32_t *c0, const uint32_t *c1,

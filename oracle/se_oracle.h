@@ -75,6 +75,7 @@ void orc_ntt_roots(size_t n, uint32_t q, uint32_t psi, uint32_t *roots);
 void orc_ntt(size_t n, uint32_t q, const uint32_t *roots, uint32_t *vec);
 void orc_intt(size_t n, uint32_t q, uint32_t psi, uint32_t *vec); /* test helper */
 void orc_ntt_default(size_t n, uint32_t q, uint32_t *vec);        /* roots from orc_ntt_root */
+void orc_ntt_psi(size_t n, uint32_t q, uint32_t psi, uint32_t *vec); /* roots from an explicit psi */
 /* O(n^2) negacyclic product, test helper (polymodmult.c:37-101) */
 void orc_negacyclic_mul(size_t n, uint32_t q, const uint32_t *a, const uint32_t *b, uint32_t *c);
 
@@ -98,6 +99,20 @@ void orc_decrypt_ntt(size_t n, uint32_t q, const uint32_t *c0, const uint32_t *c
                      const uint8_t *sk_packed, uint32_t *pt_ntt);
 
 /* batch helpers used as the CPU baseline ("port" kind): sequential loop over items */
+/* The same with an explicit chain: primes[np], their primitive 2n-th roots psis[np] and the scale (a caller
+ * chain as se_setup_custom / set_custom_parms_ckks would install, parameters.c:232-249).  The reference's own
+ * custom path does not terminate, so these are "parity unpinned" against the reference beyond
+ * the default chains, where they coincide with the functions above. */
+int orc_encrypt_asym_ex(size_t n, size_t np, const uint32_t *primes, const uint32_t *psis, double scale,
+                        const float *values, size_t vlen, const uint8_t *seed, const uint32_t *pk0,
+                        const uint32_t *pk1, uint32_t *out);
+int orc_encrypt_sym_ex(size_t n, size_t np, const uint32_t *primes, const uint32_t *psis, double scale,
+                       const float *values, size_t vlen, const uint8_t *share_seed, const uint8_t *seed,
+                       const uint8_t *sk_packed, int ref_quirk, uint32_t *out);
+void orc_gen_pk_prime_ex(size_t n, uint32_t q, uint32_t psi, const uint8_t *seed, const uint8_t *sk_packed,
+                         const int8_t *ep, uint32_t *pk0, uint32_t *pk1);
+void orc_decrypt_ntt_ex(size_t n, uint32_t q, uint32_t psi, const uint32_t *c0, const uint32_t *c1,
+                        const uint8_t *sk_packed, uint32_t *pt_ntt);
 int orc_encrypt_asym_batch(size_t n, size_t np, size_t batch, const float *values, size_t vlen,
                            const uint8_t *seeds, const uint32_t *pk0, const uint32_t *pk1,
                            uint32_t *out);

@@ -15,6 +15,9 @@ from .api import (  # noqa: F401
     SealEmbedded,
     SebError,
     build_library,
+    ct_from_seal_layout,
+    ct_to_seal_layout,
     load_library,
+    minimal_psi,
 )
 from .shard import Shard, all_gather_ciphertexts, bind_to_gpu_numa, owner_of, shard_range  # noqa: F401

@@ -90,6 +90,7 @@ EXPORTED_SYMBOLS = [
     "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
     "seb_encrypt_sym_seedct_device", "seb_encrypt_sym_seedct_host", "seb_expand_seedct_device",
     "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct", "seb_minimal_psi", "seb_uniform_spec_misses",
+    "seb_set_option", "seb_gen_secret_key", "seb_digest_device", "seb_ct_to_seal_layout", "seb_ct_from_seal_layout",
 ]
 
 
@@ -111,6 +112,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_minimal_psi.restype = u32
     L.seb_destroy.argtypes = [vp]
     L.seb_destroy.restype = None
+    L.seb_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.seb_gen_secret_key.argtypes = [vp, vp, vp]
+    L.seb_digest_device.argtypes = [vp, vp, sz, sz, vp]
+    L.seb_ct_to_seal_layout.argtypes = [vp, sz, sz, sz, vp]
+    L.seb_ct_from_seal_layout.argtypes = [vp, sz, sz, sz, vp]
     L.seb_set_stream.argtypes = [vp, vp]
     L.seb_set_public_key.argtypes = [vp, vp, vp]
     L.seb_set_secret_key.argtypes = [vp, vp]
@@ -173,6 +179,29 @@ def load_library(path: str | None = None) -> C.CDLL:
     if path is None:
         _lib = L
     return L
+
+
+def ct_to_seal_layout(ct: np.ndarray) -> np.ndarray:
+    """[batch][nprimes][2][n] u32 (device-library stream) -> [batch][2][nprimes][n] u64 (seal::Ciphertext data)."""
+    ct = np.ascontiguousarray(ct, dtype=np.uint32)
+    b, np_, two, n = ct.shape
+    assert two == 2
+    out = np.empty((b, 2, np_, n), np.uint64)
+    rc = load_library().seb_ct_to_seal_layout(_addr(ct), b, np_, n, _addr(out))
+    if rc:
+        raise SebError(f"seb_ct_to_seal_layout: {rc}")
+    return out
+
+
+def ct_from_seal_layout(seal: np.ndarray) -> np.ndarray:
+    seal = np.ascontiguousarray(seal, dtype=np.uint64)
+    b, two, np_, n = seal.shape
+    assert two == 2
+    out = np.empty((b, np_, 2, n), np.uint32)
+    rc = load_library().seb_ct_from_seal_layout(_addr(seal), b, np_, n, _addr(out))
+    if rc:
+        raise SebError(f"seb_ct_from_seal_layout: {rc} (a coefficient does not fit 32 bits)")
+    return out
 
 
 def minimal_psi(n: int, q: int) -> int:
@@ -256,6 +285,21 @@ class Context:
         pk1 = np.empty((self.nprimes, self.n), np.uint32)
         self._check(self.lib.seb_gen_public_key(self.h, _addr(sk), _addr(es), _addr(as_), _addr(pk0), _addr(pk1)))
         return pk0, pk1
+
+    def gen_secret_key(self, seed) -> np.ndarray:
+        """sample_s (ckks_sym.c:162-173) on the GPU: returns the packed n/4-byte key and installs it."""
+        sd = np.frombuffer(bytes(seed), np.uint8).copy()
+        assert sd.size == SEED_BYTES
+        sk = np.empty(self.n // 4, np.uint8)
+        self._check(self.lib.seb_gen_secret_key(self.h, _addr(sd), _addr(sk)))
+        return sk
+
+    def set_option(self, name: str, value: int) -> None:
+        """A/B switches ("uniform_coop", "uniform_fix_wide", "uniform_spec", "uniform_pair", "host_chunk"); < 0 = auto."""
+        self._check(self.lib.seb_set_option(self.h, name.encode(), int(value)))
+
+    def digest_device(self, d_words, words_per_item: int, items: int, d_digests) -> None:
+        self._check(self.lib.seb_digest_device(self.h, _addr(d_words), words_per_item, items, _addr(d_digests)))
 
     def reserve(self, batch: int) -> None:
         self._check(self.lib.seb_reserve(self.h, batch))

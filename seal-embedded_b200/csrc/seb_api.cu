@@ -116,6 +116,30 @@ static inline size_t bitrev(size_t x, int bits)
     return r;
 }
 
+// deterministic Miller-Rabin for q < 2^32 (bases 2, 7, 61)
+static bool is_prime32(uint32_t q)
+{
+    if (q < 2) return false;
+    for (uint32_t p : {2u, 3u, 5u, 7u, 11u, 13u, 17u, 19u, 23u, 29u, 31u, 37u})
+        if (q % p == 0) return q == p;
+    uint32_t d = q - 1;
+    int r      = 0;
+    while (!(d & 1)) d >>= 1, r++;
+    for (uint32_t a : {2u, 7u, 61u})
+    {
+        uint32_t x = powmod(a % q, d, q);
+        if (x == 1 || x == q - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < r && comp; i++)
+        {
+            x = mulmod(x, x, q);
+            if (x == q - 1) comp = false;
+        }
+        if (comp) return false;
+    }
+    return true;
+}
+
 // Smallest primitive 2n-th root of unity mod q (0 when q - 1 is not a multiple of 2n or no root is found):
 // what SEAL's try_minimal_primitive_root computes and — checked for all 27 pairs by the CPU suite — what
 // the reference tabulates per (n, q) in get_ntt_root (ntt.c:199-291).  Lets custom prime chains
@@ -207,7 +231,13 @@ struct seb_ctx
     bool have_pk = false, have_sk = false;
     SebSpecPlan spec_plan;            // counter windows for the lone-call uniform chain (symmetric, np >= 2)
     uint32_t *d_spec_misses = nullptr;  // how often a true counter fell outside its window (diagnostic)
-    Scratch slot[2];
+    // The asynchronous *_device entry points own `dev` (used on c->stream); the host-pointer pipeline owns
+    // `hslot` (two chunks in flight, each on its own stream).  They share nothing that is written, so a host call
+    // may follow an un-synchronised device call (and the other way round), and seb_encode_failures() always
+    // reports the last *_device call.
+    Scratch dev;
+    Scratch hslot[2];
+    SebKnobs knobs;  // test / A-B switches: environment read ONCE in seb_create, then seb_set_option
     size_t last_batch = 0;
     uint64_t launches = 0;
     // per-kernel CUDA-event timing of the *_device full-path calls (seb_profile_begin/end)
@@ -227,42 +257,93 @@ static inline void prof_next(seb_ctx *c, cudaStream_t st)
     if (c->prof_on && st == c->stream && c->prof_step < c->prof_max) c->prof_step++;
 }
 
+// cudaFree of a buffer that held secrets (plaintexts, error polynomials, seeds, key material): wiped first.
+// The memset is queued on the legacy default stream and cudaFree synchronises the device, so the order holds.
+static void seb_wipe(void *p, size_t bytes)
+{
+    volatile unsigned char *v = static_cast<volatile unsigned char *>(p);
+    for (size_t i = 0; i < bytes; i++) v[i] = 0;
+}
+
+static void wipe_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes) cudaMemset(p, 0, bytes);
+    cudaFree(p);
+}
+
+// every cudaMalloc of a group succeeds or none is kept: a failed grow leaves the old buffers in place
+struct AllocGroup
+{
+    std::vector<void **> slots;
+    std::vector<void *> fresh;
+    cudaError_t err = cudaSuccess;
+    void want(void **slot, size_t bytes)
+    {
+        if (err != cudaSuccess) return;
+        void *p = nullptr;
+        err     = cudaMalloc(&p, bytes ? bytes : 1);
+        if (err != cudaSuccess) return;
+        slots.push_back(slot);
+        fresh.push_back(p);
+    }
+    // on failure: release what was obtained, report; on success the caller frees the old buffers and commits
+    bool failed()
+    {
+        if (err == cudaSuccess) return false;
+        for (void *p : fresh) cudaFree(p);
+        fresh.clear();
+        cudaGetLastError();
+        return true;
+    }
+    void commit()
+    {
+        for (size_t i = 0; i < slots.size(); i++) *slots[i] = fresh[i];
+    }
+};
+
 static int ensure_scratch(seb_ctx *c, Scratch &s, size_t batch)
 {
     if (batch <= s.cap) return 0;
-    cudaFree(s.pt);
-    cudaFree(s.e);
-    cudaFree(s.u);
+    const size_t n = c->n, rc = (size_t)(c->rej_cap ? c->rej_cap : 1);
+    Scratch f;  // the new buffers
+    AllocGroup g;
+    g.want((void **)&f.pt, batch * n * sizeof(int64_t));
+    g.want((void **)&f.e, batch * 2 * n);
+    g.want((void **)&f.u, batch * (n / 4));
+    g.want((void **)&f.ctr, batch * sizeof(uint32_t));
+    g.want((void **)&f.ctr_a, batch * sizeof(uint32_t));
+    g.want((void **)&f.fail, batch * sizeof(int));
+    g.want((void **)&f.mag, batch * sizeof(uint32_t));
+    if (!c->asym)
+    {
+        g.want((void **)&f.rej_idx, batch * rc * sizeof(uint16_t));
+        g.want((void **)&f.rej_cnt, batch * sizeof(uint32_t));
+    }
+    if (g.failed())
+        return fail(SE_ERR_NO_MEMORY, "scratch for %zu ciphertexts: %s (the context keeps its %zu-item scratch)", batch,
+                    cudaGetErrorString(g.err), s.cap);
+    g.commit();
+    wipe_free(s.pt, s.cap * n * sizeof(int64_t));
+    wipe_free(s.e, s.cap * 2 * n);
+    wipe_free(s.u, s.cap * (n / 4));
     cudaFree(s.ctr);
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
     cudaFree(s.mag);
     cudaFree(s.rej_idx);
     cudaFree(s.rej_cnt);
-    s.rej_idx = nullptr;
-    s.rej_cnt = nullptr;
-    s.cap = 0;
-    CU(cudaMalloc(&s.pt, batch * c->n * sizeof(int64_t)));
-    CU(cudaMalloc(&s.e, batch * 2 * c->n));
-    CU(cudaMalloc(&s.u, batch * (c->n / 4)));
-    CU(cudaMalloc(&s.ctr, batch * sizeof(uint32_t)));
-    CU(cudaMalloc(&s.ctr_a, batch * sizeof(uint32_t)));
-    CU(cudaMalloc(&s.fail, batch * sizeof(int)));
-    CU(cudaMalloc(&s.mag, batch * sizeof(uint32_t)));
-    if (!c->asym)
-    {
-        CU(cudaMalloc(&s.rej_idx, batch * (size_t)(c->rej_cap ? c->rej_cap : 1) * sizeof(uint16_t)));
-        CU(cudaMalloc(&s.rej_cnt, batch * sizeof(uint32_t)));
-    }
-    s.cap = batch;
+    s.pt = f.pt, s.e = f.e, s.u = f.u, s.ctr = f.ctr, s.ctr_a = f.ctr_a, s.fail = f.fail, s.mag = f.mag;
+    s.rej_idx = f.rej_idx, s.rej_cnt = f.rej_cnt;
+    s.cap     = batch;
     return 0;
 }
 
-static void free_scratch(Scratch &s)
+static void free_scratch(Scratch &s, size_t n)
 {
-    cudaFree(s.pt);
-    cudaFree(s.e);
-    cudaFree(s.u);
+    wipe_free(s.pt, s.cap * n * sizeof(int64_t));
+    wipe_free(s.e, s.cap * 2 * n);
+    wipe_free(s.u, s.cap * (n / 4));
     cudaFree(s.ctr);
     cudaFree(s.ctr_a);
     cudaFree(s.fail);
@@ -273,8 +354,8 @@ static void free_scratch(Scratch &s)
     cudaFree(s.cand_rows);
     cudaFree(s.cand_list);
     cudaFree(s.cand_cnt);
-    cudaFree(s.d_values);
-    cudaFree(s.d_seeds);
+    wipe_free(s.d_values, s.io_cap * (n / 2) * sizeof(float));
+    wipe_free(s.d_seeds, s.io_cap * SEB_SEED_BYTES);
     cudaFree(s.d_sseeds);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_fail);
@@ -399,12 +480,23 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     {
         const uint32_t q = c->primes[i], psi = c->psis[i];
         // q < 2^30 keeps lazy values below 2^32; psi^n = -1 makes psi a primitive 2n-th root
-        if (q < 3 || q >= (1u << 30) || psi == 0 || powmod(psi, n, q) != q - 1)
+        // (a composite q can satisfy psi^n = -1 as well: caller-supplied moduli are tested for primality, so that the
+        // NTT is invertible and the ciphertexts decrypt)
+        if (q < 3 || q >= (1u << 30) || (q - 1) % (2 * n) != 0 || !is_prime32(q) || psi == 0 || psi >= q ||
+            powmod(psi, n, q) != q - 1)
         {
-            fail(SE_ERR_INVALD_ARGUMENT, "prime %u / root %u unusable for n=%zu", q, psi, n);
+            fail(SE_ERR_INVALD_ARGUMENT, "modulus %u / root %u unusable for n=%zu (need a prime q < 2^30, q = 1 mod 2n, "
+                                         "psi a primitive 2n-th root of unity)", q, psi, n);
             delete c;
             return nullptr;
         }
+        for (size_t j = 0; j < i; j++)
+            if (c->primes[j] == q)
+            {
+                fail(SE_ERR_INVALD_ARGUMENT, "modulus %u appears twice in the chain", q);
+                delete c;
+                return nullptr;
+            }
         const uint64_t ratio = (uint64_t)(((unsigned __int128)1 << 64) / q);
         c->mods.m[i]         = SebModulus{q, 2 * q, (uint32_t)ratio, (uint32_t)(ratio >> 32)};
     }
@@ -415,6 +507,16 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     c->rej_cap = (uint32_t)(n / 8);
     if (const char *v = getenv("SEB_UNIFORM_LIST_CAP"))
         if (*v && (uint32_t)atoi(v) < c->rej_cap) c->rej_cap = (uint32_t)atoi(v);
+    // the remaining A/B switches: read here, never on the call path (seb_set_option changes them at run time)
+    auto env_int = [](const char *name, long dflt) -> long {
+        const char *v = getenv(name);
+        return (v && *v) ? atol(v) : dflt;
+    };
+    c->knobs.uniform_coop     = (int)env_int("SEB_UNIFORM_COOP", -1);
+    c->knobs.uniform_fix_wide = (int)env_int("SEB_UNIFORM_FIX_WIDE", -1);
+    c->knobs.uniform_spec     = (int)env_int("SEB_UNIFORM_SPEC", -1);
+    c->knobs.uniform_pair     = (int)env_int("SEB_UNIFORM_PAIR", -1);
+    c->knobs.host_chunk       = env_int("SEB_HOST_CHUNK", 0);
 
     memset(&c->spec_plan, 0, sizeof c->spec_plan);
     if (!c->asym && nprimes >= 2)
@@ -460,7 +562,8 @@ extern "C" void seb_destroy(seb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (auto &s : c->slot) free_scratch(s);
+    free_scratch(c->dev, c->n);
+    for (auto &s : c->hslot) free_scratch(s, c->n);
     cudaFree(c->d_roots);
     cudaFree(c->d_tw);
     cudaFree(c->d_src_map);
@@ -494,6 +597,20 @@ extern "C" int seb_set_stream(seb_ctx *c, void *cuda_stream)
 {
     if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
+
+// Run-time access to the A/B switches (SebKnobs).  value < 0 restores the automatic choice.
+extern "C" int seb_set_option(seb_ctx *c, const char *name, long value)
+{
+    if (!c || !name) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    const int v = value < 0 ? -1 : (int)value;
+    if (!strcmp(name, "uniform_coop")) c->knobs.uniform_coop = v;
+    else if (!strcmp(name, "uniform_fix_wide")) c->knobs.uniform_fix_wide = v;
+    else if (!strcmp(name, "uniform_spec")) c->knobs.uniform_spec = v;
+    else if (!strcmp(name, "uniform_pair")) c->knobs.uniform_pair = v;
+    else if (!strcmp(name, "host_chunk")) c->knobs.host_chunk = value < 0 ? 0 : value;
+    else return fail(SE_ERR_INVALD_ARGUMENT, "unknown option '%s'", name);
     return 0;
 }
 
@@ -542,6 +659,12 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     CU(cudaSetDevice(c->device));
     const size_t n = c->n;
     std::vector<uint32_t> s(c->np * n);
+    // the expanded key is secret: the host copy is wiped on every way out, the device copy before it is freed
+    struct Wipe
+    {
+        std::vector<uint32_t> &v;
+        ~Wipe() { seb_wipe(v.data(), v.size() * sizeof(uint32_t)); }
+    } wipe{s};
     for (size_t p = 0; p < c->np; p++)
         for (size_t i = 0; i < n; i++)
         {
@@ -551,12 +674,15 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
         }
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, s.size() * sizeof(uint32_t)));
-    CU(cudaMemcpy(d, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    cudaError_t e = seb_launch_ntt(c->logn, d, c->d_roots, c->mods, (int)c->np, c->np, c->stream);
-    c->launches++;
+    cudaError_t e = cudaMemcpy(d, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        e = seb_launch_ntt(c->logn, d, c->d_roots, c->mods, (int)c->np, c->np, c->stream);
+        c->launches++;
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(s.data(), d, s.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    wipe_free(d, s.size() * sizeof(uint32_t));
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "ntt(s): %s", cudaGetErrorString(e));
     int r = upload_shoup(c, s.data(), &c->d_ntt_s);
     if (r) return r;
@@ -564,6 +690,32 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     CU(cudaMemcpy(c->d_ntt_s_nat, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     c->have_sk = true;
     return 0;
+}
+
+// ckks_setup_s with parms->sample_s set (device/lib/ckks_sym.c:162-173): s = sample_small_poly_ternary_prng_96 from
+// PRNG(seed) at counter 0 (sample.c:218-242) — the same sampler as the asymmetric path's u, so the same kernel.
+// sk_out receives the n/4 packed bytes (sk_<n>.dat format); the key is installed as by seb_set_secret_key.
+extern "C" int seb_gen_secret_key(seb_ctx *c, const uint8_t *seed, uint8_t *sk_out)
+{
+    if (!c || !seed || !sk_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->n;
+    uint8_t *d     = nullptr;  // [64 seed][n/4 key][4 counter]
+    const size_t bytes = SEB_SEED_BYTES + n / 4 + sizeof(uint32_t);
+    CU(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpyAsync(d, seed, SEB_SEED_BYTES, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+    {
+        seb_launch_sample_ternary(d, d + SEB_SEED_BYTES, reinterpret_cast<uint32_t *>(d + SEB_SEED_BYTES + n / 4), (int)n, 1,
+                                  c->stream);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sk_out, d + SEB_SEED_BYTES, n / 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    wipe_free(d, bytes);
+    if (e != cudaSuccess) return fail(SE_ERR_CUDA, "seb_gen_secret_key: %s", cudaGetErrorString(e));
+    return seb_set_secret_key(c, sk_out);
 }
 
 // gen_pk (device/lib/ckks_asym.c:159-171) for every prime: a symmetric encryption of zero whose error
@@ -593,12 +745,13 @@ extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const ui
     const uint32_t cap = c->rej_cap ? c->rej_cap : 1;
     cudaStream_t st = c->stream;
     auto cleanup = [&]() {
-        cudaFree(d_seeds);
-        cudaFree(d_e);
+        wipe_free(d_seeds, seeds.size());  // ep_seed and ep are the key pair's secret error
+        wipe_free(d_e, n);
         cudaFree(d_pt);
         cudaFree(d_small);
         cudaFree(d_out);
         cudaFree(d_rej);
+        seb_wipe(seeds.data(), seeds.size());
     };
 #define CUK(call)                                                                          \
     do                                                                                     \
@@ -624,7 +777,7 @@ extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const ui
     {
         CUK(cudaMemsetAsync(d_small + 1, 0, sizeof(uint32_t), st));  // a fresh PRNG per prime: counter 0
         seb_launch_uniform(d_seeds + (p + 1) * SEB_SEED_BYTES, d_small + 1, d_out + (2 * p + 1) * n, 2 * np * n, (int)n,
-                           c->mods.m[p], 1, d_rej, d_small + 2, cap, st);
+                           c->mods.m[p], 1, d_rej, d_small + 2, cap, c->knobs, st);
     }
     CUK(cudaGetLastError());
     CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots, c->d_ntt_s, c->mods,
@@ -648,7 +801,7 @@ extern "C" int seb_reserve(seb_ctx *c, size_t batch)
 {
     if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
     CU(cudaSetDevice(c->device));
-    return ensure_scratch(c, c->slot[0], batch);
+    return ensure_scratch(c, c->dev, batch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -676,9 +829,9 @@ extern "C" int seb_encode_device(seb_ctx *c, const float *d_values, size_t vlen,
     if (!c || !d_values || !d_pt) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
     int r = check_vlen(c, vlen);
     if (r) return r;
-    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    if ((r = ensure_scratch(c, c->dev, batch))) return r;
     c->last_batch = batch;
-    return run_encode(c, d_values, vlen, batch, d_pt, c->slot[0].fail, nullptr, c->stream);
+    return run_encode(c, d_values, vlen, batch, d_pt, c->dev.fail, nullptr, c->stream);
 }
 
 extern "C" int seb_sample_asym_device(seb_ctx *c, const uint8_t *d_seeds, size_t batch, uint8_t *d_u, int8_t *d_e,
@@ -708,10 +861,10 @@ extern "C" int seb_sample_uniform_device(seb_ctx *c, const uint8_t *d_seeds, uin
     if (!c || !d_seeds || !d_ctr || !d_out || prime_idx >= c->np)
         return fail(SE_ERR_INVALD_ARGUMENT, "bad argument");
     if (c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "the uniform sampler belongs to a symmetric context");
-    int r = ensure_scratch(c, c->slot[0], batch);
+    int r = ensure_scratch(c, c->dev, batch);
     if (r) return r;
     seb_launch_uniform(d_seeds, d_ctr, d_out, ct_stride, (int)c->n, c->mods.m[prime_idx], (int)batch,
-                       c->slot[0].rej_idx, c->slot[0].rej_cnt, c->rej_cap, c->stream);
+                       c->dev.rej_idx, c->dev.rej_cnt, c->rej_cap, c->knobs, c->stream);
     c->launches += 2;
     CU(cudaGetLastError());
     return 0;
@@ -745,6 +898,18 @@ extern "C" int seb_decrypt_decode_device(seb_ctx *c, const uint32_t *d_ct, size_
     CU(seb_launch_decrypt_decode(d_ct, c->d_ntt_s_nat, c->d_iroots, c->d_ninv, c->d_tw, c->d_index_map, c->mods,
                                  (int)c->n, (int)c->np, (int)prime_idx, c->scale, c->d_work, c->verify_ctas, (int)vlen,
                                  d_values_out, batch, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// Per-item 64-bit digest of d_words [items][words_per_item] (seb_verify.cu: k_digest): lets a parity test compare
+// every ciphertext of a full-size batch with the compiled reference by moving 8 bytes per item.
+extern "C" int seb_digest_device(seb_ctx *c, const uint32_t *d_words, size_t words_per_item, size_t items,
+                                 uint64_t *d_digests)
+{
+    if (!c || !d_words || !d_digests) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (words_per_item % 4 != 0) return fail(SE_ERR_INVALD_ARGUMENT, "words_per_item must be a multiple of 4");
+    CU(seb_launch_digest(d_words, words_per_item, items, d_digests, c->stream));
     c->launches++;
     return 0;
 }
@@ -793,7 +958,7 @@ static int encrypt_asym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t
 // the chain serially costs np squeezes at 2.9 us: speculation pays while the candidates number less than about
 // 1400 x np warps — 16-20 ciphertexts at n = 4096 x 3 primes (~215 candidates each), 4-5 at n = 16384 x 6 (~1500
 // each); measured in profiles/r01_ab_sym_small_batches.txt.
-// SEB_UNIFORM_SPEC=0/1 forces the choice for up to 64 ciphertexts (tests, A/B measurements).
+// The "uniform_spec" option (0/1) forces the choice for up to 64 ciphertexts (tests, A/B measurements).
 #define SEB_SPEC_MAX_BATCH 64
 #define SEB_SPEC_WARPS_PER_PRIME 1400
 
@@ -804,10 +969,10 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
 {
     const int n = (int)c->n;
     CU(cudaMemsetAsync(s.ctr_a, 0, batch * sizeof(uint32_t), st));
-    const char *e   = getenv("SEB_UNIFORM_SPEC");
     const bool fits = batch <= SEB_SPEC_MAX_BATCH &&
                       batch * ((size_t)c->spec_plan.total + 1) <= (size_t)SEB_SPEC_WARPS_PER_PRIME * c->np;
-    const bool spec = c->spec_plan.total > 0 && ((e && *e) ? (atoi(e) != 0 && batch <= SEB_SPEC_MAX_BATCH) : fits);
+    const int force = c->knobs.uniform_spec;
+    const bool spec = c->spec_plan.total > 0 && (force >= 0 ? (force != 0 && batch <= SEB_SPEC_MAX_BATCH) : fits);
     if (spec)
     {
         if (s.cand_cap < batch)
@@ -833,14 +998,14 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
         }
         seb_launch_uniform_chain_spec(d_sseeds, s.ctr_a, a_p0, ct_stride, p_stride, n, c->mods, (int)c->np, c->spec_plan,
                                       (int)batch, s.cand_rows, s.cand_list, s.cand_cnt, s.rej_idx, s.rej_cnt, c->rej_cap,
-                                      c->d_spec_misses, st);
+                                      c->d_spec_misses, c->knobs, st);
         c->launches += 2 * c->np;  // one squeeze launch, a select per later prime, a fix-up per prime
     }
     else
     {
         for (size_t p = 0; p < c->np; p++)
             seb_launch_uniform(d_sseeds, s.ctr_a, a_p0 + p * p_stride, ct_stride, n, c->mods.m[p], (int)batch, s.rej_idx,
-                               s.rej_cnt, c->rej_cap, st);
+                               s.rej_cnt, c->rej_cap, c->knobs, st);
         c->launches += 2 * c->np;
     }
     CU(cudaGetLastError());
@@ -889,9 +1054,9 @@ extern "C" int seb_encrypt_asym_device(seb_ctx *c, const float *d_values, size_t
     if (!c->have_pk) return fail(SE_ERR_NO_KEY, "no public key loaded");
     int r = check_vlen(c, vlen);
     if (r) return r;
-    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    if ((r = ensure_scratch(c, c->dev, batch))) return r;
     c->last_batch = batch;
-    return encrypt_asym_on(c, c->slot[0], d_values, vlen, d_seeds, batch, d_out, c->stream);
+    return encrypt_asym_on(c, c->dev, d_values, vlen, d_seeds, batch, d_out, c->stream);
 }
 
 static int encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
@@ -902,9 +1067,9 @@ static int encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, co
     if (!c->have_sk) return fail(SE_ERR_NO_KEY, "no secret key loaded");
     int r = check_vlen(c, vlen);
     if (r) return r;
-    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
+    if ((r = ensure_scratch(c, c->dev, batch))) return r;
     c->last_batch = batch;
-    return encrypt_sym_on(c, c->slot[0], d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, seedct, c->stream);
+    return encrypt_sym_on(c, c->dev, d_values, vlen, d_sseeds, d_seeds, batch, d_out, quirk, seedct, c->stream);
 }
 
 extern "C" int seb_encrypt_sym_device(seb_ctx *c, const float *d_values, size_t vlen, const uint8_t *d_sseeds,
@@ -929,8 +1094,8 @@ extern "C" int seb_expand_seedct_device(seb_ctx *c, const uint8_t *d_sseeds, con
     if (c->asym) return fail(SE_ERR_INVALD_ARGUMENT, "seed-compressed ciphertexts are symmetric");
     if (batch == 0) return 0;
     int r;
-    if ((r = ensure_scratch(c, c->slot[0], batch))) return r;
-    Scratch &s      = c->slot[0];
+    if ((r = ensure_scratch(c, c->dev, batch))) return r;
+    Scratch &s      = c->dev;
     cudaStream_t st = c->stream;
     const size_t n  = c->n;
     if (d_c0)
@@ -977,7 +1142,7 @@ extern "C" int seb_encode_failures(seb_ctx *c)
     CU(cudaStreamSynchronize(c->stream));
     if (!c->last_batch) return 0;
     std::vector<int> f(c->last_batch);
-    CU(cudaMemcpy(f.data(), c->slot[0].fail, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(f.data(), c->dev.fail, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
     int bad = 0;
     for (int v : f) bad += v != 0;
     return bad;
@@ -1005,16 +1170,15 @@ static bool is_pinned(const void *p)
 // GPU: the asymmetric path's ternary sampler is a warp per ciphertext, and the symmetric path's uniform
 // sampler is ONE sequential sponge per ciphertext whose latency (~2 ms per prime at n = 16384) is paid
 // per chunk whatever its size — 85-item chunks made config D's host path 12x slower than its device
-// path (profiles/README.md).  Chunks are balanced so the last one is not a sliver.  SEB_HOST_CHUNK
-// overrides the item count.
+// path (profiles/README.md).  Chunks are balanced so the last one is not a sliver.  The "host_chunk"
+// option (SEB_HOST_CHUNK at seb_create) overrides the item count.
 static size_t host_chunk(const seb_ctx *c, bool sym, size_t batch)
 {
     const size_t per_ct = 2 * c->np * c->n * sizeof(uint32_t);
     size_t chunk        = (64u << 20) / per_ct;
     const size_t fill   = sym ? 8192 : 2048;
     if (chunk < fill) chunk = fill;
-    if (const char *v = getenv("SEB_HOST_CHUNK"))
-        if (atol(v) > 0) chunk = (size_t)atol(v);
+    if (c->knobs.host_chunk > 0) chunk = (size_t)c->knobs.host_chunk;
     if (chunk >= batch) return batch;
     const size_t nchunks = (batch + chunk - 1) / chunk;
     return (batch + nchunks - 1) / nchunks;
@@ -1022,26 +1186,31 @@ static size_t host_chunk(const seb_ctx *c, bool sym, size_t batch)
 
 static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym, size_t per_ct)
 {
+    (void)sym;
     if (!s.stream) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if (!s.done) CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    if (chunk <= s.io_cap && per_ct <= s.io_out_words && (!sym || s.d_sseeds)) return 0;
-    cudaFree(s.d_values);
-    cudaFree(s.d_seeds);
+    if (chunk <= s.io_cap && per_ct <= s.io_out_words) return 0;
+    if (chunk < s.io_cap) chunk = s.io_cap;
+    if (per_ct < s.io_out_words) per_ct = s.io_out_words;
+    // allocate-then-swap (like ensure_scratch): a failed grow keeps the old staging buffers
+    Scratch f;
+    AllocGroup g;
+    g.want((void **)&f.d_values, chunk * (c->n / 2) * sizeof(float));
+    g.want((void **)&f.d_seeds, chunk * SEB_SEED_BYTES);
+    g.want((void **)&f.d_sseeds, chunk * SEB_SEED_BYTES);
+    g.want((void **)&f.d_out, chunk * per_ct * sizeof(uint32_t));
+    int *h_fail = nullptr;
+    if (g.err == cudaSuccess) g.err = cudaMallocHost(&h_fail, chunk * sizeof(int));
+    if (g.failed())
+        return fail(SE_ERR_NO_MEMORY, "staging for %zu-item chunks: %s", chunk, cudaGetErrorString(g.err));
+    g.commit();
+    wipe_free(s.d_values, s.io_cap * (c->n / 2) * sizeof(float));
+    wipe_free(s.d_seeds, s.io_cap * SEB_SEED_BYTES);
     cudaFree(s.d_sseeds);
     cudaFree(s.d_out);
     cudaFreeHost(s.h_fail);
-    s.d_values = nullptr;
-    s.d_seeds = s.d_sseeds = nullptr;
-    s.d_out  = nullptr;
-    s.h_fail = nullptr;
-    s.io_cap = 0;
-    if (chunk < s.io_cap) chunk = s.io_cap;
-    if (per_ct < s.io_out_words) per_ct = s.io_out_words;
-    CU(cudaMalloc(&s.d_values, chunk * (c->n / 2) * sizeof(float)));
-    CU(cudaMalloc(&s.d_seeds, chunk * SEB_SEED_BYTES));
-    CU(cudaMalloc(&s.d_sseeds, chunk * SEB_SEED_BYTES));
-    CU(cudaMalloc(&s.d_out, chunk * per_ct * sizeof(uint32_t)));
-    CU(cudaMallocHost(&s.h_fail, chunk * sizeof(int)));
+    s.d_values = f.d_values, s.d_seeds = f.d_seeds, s.d_sseeds = f.d_sseeds, s.d_out = f.d_out;
+    s.h_fail       = h_fail;
     s.io_cap       = chunk;
     s.io_out_words = per_ct;
     return 0;
@@ -1064,8 +1233,8 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     const size_t nslots = chunk < batch ? 2 : 1;
     for (size_t k = 0; k < nslots; k++)
     {
-        if ((r = ensure_scratch(c, c->slot[k], chunk))) return r;
-        if ((r = ensure_io(c, c->slot[k], chunk, sym, per_ct))) return r;
+        if ((r = ensure_scratch(c, c->hslot[k], chunk))) return r;
+        if ((r = ensure_io(c, c->hslot[k], chunk, sym, per_ct))) return r;
     }
     struct Pending
     {
@@ -1077,7 +1246,7 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     // wait for chunk k's results to be in the caller's buffer
     auto drain = [&](int k) -> int {
         if (!pend[k].live) return 0;
-        Scratch &s = c->slot[k];
+        Scratch &s = c->hslot[k];
         if (!pin_out)  // blocking copy, ordered after the chunk's kernels on its stream
             CU(cudaMemcpyAsync(out + pend[k].first * per_ct, s.d_out, pend[k].count * per_ct * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, s.stream));
@@ -1091,7 +1260,7 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     for (size_t first = 0; first < batch; first += chunk, k ^= 1)
     {
         const size_t count = batch - first < chunk ? batch - first : chunk;
-        Scratch &s         = c->slot[k];  // free: its previous chunk was drained one iteration ago
+        Scratch &s         = c->hslot[k];  // free: its previous chunk was drained one iteration ago
         const float *hv    = values + first * vlen;
         const uint8_t *hs  = seeds + first * SEB_SEED_BYTES;
         const uint8_t *hss = sym ? sseeds + first * SEB_SEED_BYTES : nullptr;

@@ -13,6 +13,19 @@ struct SebModuli
     SebModulus m[SEB_MAX_PRIMES];
 };
 
+// Test / A-B switches of a context.  -1 = automatic (the library decides from the batch size), 0 / 1 force a path.
+// Initialised from the environment ONCE in seb_create (SEB_UNIFORM_COOP, SEB_UNIFORM_FIX_WIDE, SEB_UNIFORM_SPEC,
+// SEB_UNIFORM_PAIR, SEB_HOST_CHUNK) and changed at run time with seb_set_option; never read from the environment
+// on the call path.
+struct SebKnobs
+{
+    int uniform_coop     = -1;  // bulk squeeze by a warp per ciphertext (25 lanes per sponge)
+    int uniform_fix_wide = -1;  // fix-up by a CTA per ciphertext
+    int uniform_spec     = -1;  // speculative prime chain for lone calls
+    int uniform_pair     = -1;  // bulk squeeze by two lanes per sponge (bit-interleaved halves)
+    long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
+};
+
 // ---- samplers (seb_sample.cu) ----
 void seb_launch_prng_blocks(const uint8_t *seeds, const uint64_t *counters, uint64_t *out, int count,
                             cudaStream_t st);
@@ -23,7 +36,7 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
 // rej_idx [batch][rej_cap] / rej_cnt [batch]: scratch for the per-ciphertext lists of rejected words
 void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
                         const SebModulus &mod, int batch, uint16_t *rej_idx, uint32_t *rej_cnt, uint32_t rej_cap,
-                        cudaStream_t st);
+                        const SebKnobs &knobs, cudaStream_t st);
 
 // Lone calls: all primes' squeezes at once, speculating on the chained counters (seb_sample.cu).
 struct SebSpecPrime
@@ -39,7 +52,8 @@ void seb_uniform_spec_plan(int n, const SebModuli &mods, int np, double sigmas, 
 void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t *out_p0, size_t ct_stride, size_t p_stride,
                                    int n, const SebModuli &mods, int np, const SebSpecPlan &plan, int batch,
                                    uint32_t *cand_rows, uint16_t *cand_list, uint32_t *cand_cnt, uint16_t *rej_idx,
-                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, cudaStream_t st);
+                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, const SebKnobs &knobs,
+                                   cudaStream_t st);
 
 // ---- encode (seb_encode.cu) ----
 // values: [batch][v_stride] floats, the first vlen of each row are used (zero padded to n/2);
@@ -76,7 +90,9 @@ cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *
                                    size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st);
 cudaError_t seb_encrypt_configure(int logn);
 
-// ---- verifier: inverse NTT, decrypt + decode (seb_verify.cu) ----
+// ---- verifier: inverse NTT, decrypt + decode, per-item digests (seb_verify.cu) ----
+// digests[b] = sum_i mix64((i << 32) | words[b][i]) mod 2^64 (words_per_item a multiple of 4, rows 16-byte aligned)
+cudaError_t seb_launch_digest(const uint32_t *words, size_t words_per_item, size_t items, uint64_t *digests, cudaStream_t st);
 // iroots: per prime n Shoup pairs, iroots[i] = inverse of the forward table's root i; ninvs: n^-1 per prime
 cudaError_t seb_verify_configure(int n);
 cudaError_t seb_launch_intt(uint32_t *polys, const uint2 *iroots, const uint2 *ninvs, const SebModuli &mods, int n,

@@ -639,14 +639,13 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
 }
 
 // fix-up launch: a CTA per ciphertext with one round of ~n/50 + 32 candidates for a handful of ciphertexts (latency),
-// a warp per ciphertext with 32-candidate waves otherwise (throughput).  SEB_UNIFORM_FIX_WIDE=0/1 forces the choice.
+// a warp per ciphertext with 32-candidate waves otherwise (throughput).  knobs.uniform_fix_wide = 0/1 forces the choice.
 #define SEB_FIX_WIDE_MAX_BATCH 64
 static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
                                    const SebModulus &mod, uint32_t max_multiple, int batch, uint16_t *rej_idx,
-                                   uint32_t *rej_cnt, uint32_t rej_cap, cudaStream_t st)
+                                   uint32_t *rej_cnt, uint32_t rej_cap, const SebKnobs &knobs, cudaStream_t st)
 {
-    const char *e   = getenv("SEB_UNIFORM_FIX_WIDE");
-    const bool wide = (e && *e) ? atoi(e) != 0 : batch <= SEB_FIX_WIDE_MAX_BATCH;
+    const bool wide = knobs.uniform_fix_wide >= 0 ? knobs.uniform_fix_wide != 0 : batch <= SEB_FIX_WIDE_MAX_BATCH;
     if (wide)
     {
         // expected rejections: 2 % of n at most (30-bit primes), plus head-room for the candidates' own rejections
@@ -689,7 +688,8 @@ void seb_uniform_spec_plan(int n, const SebModuli &mods, int np, double sigmas, 
 void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t *out_p0, size_t ct_stride, size_t p_stride,
                                    int n, const SebModuli &mods, int np, const SebSpecPlan &plan, int batch,
                                    uint32_t *cand_rows, uint16_t *cand_list, uint32_t *cand_cnt, uint16_t *rej_idx,
-                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, cudaStream_t st)
+                                   uint32_t *rej_cnt, uint32_t rej_cap, uint32_t *misses, const SebKnobs &knobs,
+                                   cudaStream_t st)
 {
     if (batch <= 0) return;
     const size_t warps = ((size_t)plan.total + 1) * (size_t)batch;
@@ -704,13 +704,14 @@ void seb_launch_uniform_chain_spec(const uint8_t *seeds, uint32_t *ctr, uint32_t
             k_uniform_select<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, plan.p[p],
                                                               plan.total, batch, cand_rows, cand_list, cand_cnt, rej_idx,
                                                               rej_cnt, rej_cap, misses);
-        seb_launch_uniform_fix(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, st);
+        seb_launch_uniform_fix(seeds, ctr, out_p, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, knobs,
+                               st);
     }
 }
 
 void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size_t ct_stride, int n,
                         const SebModulus &mod, int batch, uint16_t *rej_idx, uint32_t *rej_cnt, uint32_t rej_cap,
-                        cudaStream_t st)
+                        const SebKnobs &knobs, cudaStream_t st)
 {
     if (batch <= 0) return;
     // max_multiple = 0xFFFFFFFF - (0xFFFFFFFF mod q) - 1 (sample.c:45-46)
@@ -718,14 +719,13 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     // Small batches: a warp per ciphertext with the sponge spread over its lanes (latency of the dependent
     // permutations / 4); otherwise one sequential sponge per thread, in single-warp CTAs that spread the batch over
     // all SM sub-partitions (131072-item config D leaves 16384 items = 512 warps per GPU for 592 sub-partitions).
-    // SEB_UNIFORM_COOP=0/1 forces either (tests, A/B measurements).
-    const char *e   = getenv("SEB_UNIFORM_COOP");
-    const bool coop = (e && *e) ? atoi(e) != 0 : batch <= SEB_UNIFORM_COOP_MAX_BATCH;
+    // knobs.uniform_coop = 0/1 forces either (tests, A/B measurements).
+    const bool coop = knobs.uniform_coop >= 0 ? knobs.uniform_coop != 0 : batch <= SEB_UNIFORM_COOP_MAX_BATCH;
     if (coop)
         k_uniform_bulk_coop<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
                                                              rej_idx, rej_cnt, rej_cap);
     else
         k_uniform_bulk<<<(batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
                                                          rej_idx, rej_cnt, rej_cap);
-    seb_launch_uniform_fix(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, st);
+    seb_launch_uniform_fix(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt, rej_cap, knobs, st);
 }

@@ -122,6 +122,55 @@ __global__ void __launch_bounds__(SEB_VERIFY_THREADS)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-item 64-bit digest of a batch of word streams, so that a FULL batch can be compared with the compiled
+// reference item by item without moving 6 GB to the host:
+//   digest(item) = sum over i of mix64((i << 32) | word_i)  mod 2^64,   mix64 = the splitmix64 finaliser
+// (position-keyed, so a changed, moved or swapped word changes the sum; oracle/ref_shim.c and oracle/se_oracle.c
+// compute the same function on the CPU).  One CTA per item, 128-bit loads, warp-shuffle reduction.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t seb_mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_digest(const uint32_t *__restrict__ words, size_t words_per_item, size_t items,
+                                                uint64_t *__restrict__ digests)
+{
+    __shared__ uint64_t s_part[8];
+    const size_t b = blockIdx.x;
+    if (b >= items) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(words + b * words_per_item);
+    uint64_t acc     = 0;
+    for (size_t i = threadIdx.x; i < words_per_item / 4; i += blockDim.x)
+    {
+        const uint4 v    = src[i];
+        const uint64_t k = (uint64_t)(4 * i) << 32;
+        acc += seb_mix64(k | v.x) + seb_mix64((k + (1ULL << 32)) | v.y) + seb_mix64((k + (2ULL << 32)) | v.z) +
+               seb_mix64((k + (3ULL << 32)) | v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint64_t t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w];
+        digests[b] = t;
+    }
+}
+
+cudaError_t seb_launch_digest(const uint32_t *words, size_t words_per_item, size_t items, uint64_t *digests, cudaStream_t st)
+{
+    if (items == 0) return cudaSuccess;
+    if (words_per_item % 4 != 0 || items > 0x7FFFFFFFu) return cudaErrorInvalidValue;
+    k_digest<<<(unsigned)items, 256, 0, st>>>(words, words_per_item, items, digests);
+    return cudaGetLastError();
+}
+
 cudaError_t seb_verify_configure(int n)
 {
     // The attribute belongs to the kernel, not to a context: contexts of several degrees live in one

@@ -65,6 +65,14 @@ static void read_key_file(const char *fpath, size_t bytes_expected, void *vec)
     }
 }
 
+/* free() of a buffer that held secret material */
+static void wipe_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    explicit_bzero(p, bytes);
+    free(p);
+}
+
 static void die_on(int rc, const char *what)
 {
     if (rc == 0) return;
@@ -101,9 +109,12 @@ static void release_all(void)
     if (g_ctx) seb_destroy(g_ctx);
     g_ctx = NULL;
     free(g_parms.moduli);
-    free(g_ptrs.values);
+    if (g_parms.coeff_count)
+    {
+        wipe_free(g_ptrs.values, (g_parms.coeff_count / 2) * sizeof(flpt)); /* the last message */
+        wipe_free(g_ptrs.ternary, g_parms.coeff_count / 4);                 /* the secret key */
+    }
     free(g_ptrs.index_map_ptr);
-    free(g_ptrs.ternary);
     free(g_ct);
     g_ct = NULL;
     memset(&g_parms, 0, sizeof g_parms);
@@ -122,7 +133,14 @@ SE_PARMS *se_setup_custom(size_t degree, size_t nprimes, const ZZ *modulus_vals,
 
     /* With default parameters the requested scale is overridden by the degree's default exactly
      * as set_parms_ckks does (parameters.c:197-225).  Custom moduli keep the caller's
-     * scale (parameters.c:232-249); their 2n-th roots must be tabulated (ntt.c:199-291). */
+     * scale (parameters.c:232-249).  Their 2n-th roots come from the reference's table where it has
+     * one (ntt.c:199-291) and are computed otherwise (seb_minimal_psi); seb_create rejects a modulus
+     * that is not a prime = 1 mod 2n below 2^30.
+     * `ratios` only selects the custom path (non-NULL, as in parameters.c:235): its VALUES are not
+     * read.  The header documents "high word, low word" per modulus (seal_embedded.h:86-87) while
+     * set_custom_parms_ckks reads ratios[i], ratios[i+1] (parameters.c:246) - two layouts that agree
+     * for one prime only - so const_ratio is always floor(2^64/q) computed here (modulus.c:23-56),
+     * which is what either layout is meant to carry. */
     int custom = modulus_vals && ratios;
     g_ctx      = seb_create(degree, nprimes, custom ? modulus_vals : NULL, NULL, custom ? scale : 0.0, asym, device);
     if (!g_ctx)
@@ -158,8 +176,8 @@ SE_PARMS *se_setup_custom(size_t degree, size_t nprimes, const ZZ *modulus_vals,
         unsigned __int128 one     = (unsigned __int128)1 << 64;
         uint64_t ratio            = (uint64_t)(one / q);
         g_parms.moduli[i].value          = q;
-        g_parms.moduli[i].const_ratio[0] = custom ? ratios[2 * i + 1] : (ZZ)ratio;
-        g_parms.moduli[i].const_ratio[1] = custom ? ratios[2 * i] : (ZZ)(ratio >> 32);
+        g_parms.moduli[i].const_ratio[0] = (ZZ)ratio;
+        g_parms.moduli[i].const_ratio[1] = (ZZ)(ratio >> 32);
     }
     g_parms.curr_modulus_idx = 0;
     g_parms.curr_modulus     = &g_parms.moduli[0];
@@ -260,7 +278,12 @@ bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seed
 {
     if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v || !out) return false;
     if (batch == 0) return true;
-    if (vlen > g_parms.coeff_count / 2) vlen = g_parms.coeff_count / 2;
+    /* vlen is also the row stride of v: clamping it would read items b >= 1 from the wrong offsets */
+    if (vlen > g_parms.coeff_count / 2)
+    {
+        printf("Error! vlen %zu exceeds n/2 = %zu values per message.\n", vlen, g_parms.coeff_count / 2);
+        return false;
+    }
     uint8_t *sd = malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
     uint8_t *ss = g_parms.is_asymmetric ? NULL : malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
     if (!sd || (!g_parms.is_asymmetric && !ss))
@@ -280,7 +303,7 @@ bool se_encrypt_batch_seeded(const uint8_t *shareable_seeds, const uint8_t *seed
         fill_seeds(ss, shareable_seeds, batch);
         rc = seb_encrypt_sym_host(g_ctx, v, vlen, ss, sd, batch, out, g_ref_quirk);
     }
-    free(sd);
+    wipe_free(sd, batch * SE_PRNG_SEED_BYTE_COUNT); /* the private seeds are secrets */
     free(ss);
     if (rc == SE_ERR_ENCODE_RANGE)
     {
@@ -300,7 +323,11 @@ bool se_encrypt_batch_seedct(const uint8_t *shareable_seeds, const uint8_t *seed
     if (!se_parms || se_parms != &g_se_parms || !g_ctx || !v || !c0_out || !shareable_seeds) return false;
     if (g_parms.is_asymmetric) return false;
     if (batch == 0) return true;
-    if (vlen > g_parms.coeff_count / 2) vlen = g_parms.coeff_count / 2;
+    if (vlen > g_parms.coeff_count / 2)
+    {
+        printf("Error! vlen %zu exceeds n/2 = %zu values per message.\n", vlen, g_parms.coeff_count / 2);
+        return false;
+    }
     uint8_t *sd = malloc(batch * SE_PRNG_SEED_BYTE_COUNT);
     if (!sd)
     {
@@ -309,7 +336,7 @@ bool se_encrypt_batch_seedct(const uint8_t *shareable_seeds, const uint8_t *seed
     }
     fill_seeds(sd, seeds, batch);
     int rc = seb_encrypt_sym_seedct_host(g_ctx, v, vlen, shareable_seeds, sd, batch, c0_out);
-    free(sd);
+    wipe_free(sd, batch * SE_PRNG_SEED_BYTE_COUNT);
     if (rc == SE_ERR_ENCODE_RANGE)
     {
         printf("Error! Value is possibly too large.\n"); /* ckks_common.c:197 */
@@ -382,6 +409,51 @@ bool se_encrypt_seeded(uint8_t *shareable_seed, uint8_t *seed, SEND_FNCT_PTR net
 bool se_encrypt(SEND_FNCT_PTR network_send_function, void *v, size_t vlen_bytes, bool print, SE_PARMS *se_parms)
 {
     return se_encrypt_seeded(NULL, NULL, network_send_function, v, vlen_bytes, print, se_parms);
+}
+
+/* SEAL-side layout.  The device library's stream is, per ciphertext, [nprimes][2][n] 32-bit words
+ * (c0_p0, c1_p0, c0_p1, ...: seal_embedded.c:196-203).  A seal::Ciphertext of size 2 holds [2][nprimes][n] 64-bit
+ * coefficients, which is how the adapter fills it from that stream: ct_ptr[i + j*n] = c0 of prime j,
+ * ct_ptr[i + j*n + nprimes*n] = c1 of prime j (adapter/fileops.cpp:518-527).  Host-side, no GPU involved. */
+int seb_ct_to_seal_layout(const ZZ *ct, size_t batch, size_t nprimes, size_t n, uint64_t *seal)
+{
+    if (!ct || !seal || !nprimes || !n) return SE_ERR_INVALD_ARGUMENT;
+    for (size_t b = 0; b < batch; b++)
+    {
+        const ZZ *src = ct + b * 2 * nprimes * n;
+        uint64_t *dst = seal + b * 2 * nprimes * n;
+        for (size_t j = 0; j < nprimes; j++)
+            for (size_t k = 0; k < 2; k++)
+            {
+                const ZZ *s = src + (2 * j + k) * n;
+                uint64_t *d = dst + (k * nprimes + j) * n;
+                for (size_t i = 0; i < n; i++) d[i] = s[i];
+            }
+    }
+    return SE_SUCCESS;
+}
+
+/* the inverse; a coefficient that does not fit 32 bits (a SEAL ciphertext over wider primes) is an error */
+int seb_ct_from_seal_layout(const uint64_t *seal, size_t batch, size_t nprimes, size_t n, ZZ *ct)
+{
+    if (!ct || !seal || !nprimes || !n) return SE_ERR_INVALD_ARGUMENT;
+    for (size_t b = 0; b < batch; b++)
+    {
+        const uint64_t *src = seal + b * 2 * nprimes * n;
+        ZZ *dst             = ct + b * 2 * nprimes * n;
+        for (size_t j = 0; j < nprimes; j++)
+            for (size_t k = 0; k < 2; k++)
+            {
+                const uint64_t *s = src + (k * nprimes + j) * n;
+                ZZ *d             = dst + (2 * j + k) * n;
+                for (size_t i = 0; i < n; i++)
+                {
+                    if (s[i] >> 32) return SE_ERR_INVALD_ARGUMENT;
+                    d[i] = (ZZ)s[i];
+                }
+            }
+    }
+    return SE_SUCCESS;
 }
 
 void se_cleanup(SE_PARMS *se_parms)

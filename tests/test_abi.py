@@ -154,3 +154,96 @@ def test_c_application_links_against_the_library(seb, tmp_path):
     assert "libseal_embedded_b200.so" in out
     r = subprocess.run([exe], capture_output=True, text=True)  # no arguments: usage, exit code 2, no CUDA call
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_struct_layouts_match_the_reference_headers(tmp_path):
+    """sizeof / offsetof of every caller-visible struct, the enum values and the error codes, printed by
+    tests/layout_probe.c compiled against include/ — must equal the output of the SAME probe compiled against the
+    reference's own header tree: committed as tests/golden/ref_struct_layout.txt, and regenerated on the spot when
+    /root/reference is mounted (device/lib/seal_embedded.h:31-65, parameters.h:43-67, modulus.h:22-30,
+    ckks_common.h:36-52)."""
+    probe = os.path.join(ROOT, "tests", "layout_probe.c")
+    ours = str(tmp_path / "ours")
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), probe, "-o", ours], check=True)
+    mine = subprocess.run([ours], capture_output=True, text=True, check=True).stdout
+    golden = open(os.path.join(ROOT, "tests", "golden", "ref_struct_layout.txt")).read()
+    assert mine == golden
+    assert mine.count("offsetof") >= 27
+    ref_inc = "/root/reference/device/lib"
+    if os.path.isdir(ref_inc):
+        theirs = str(tmp_path / "theirs")
+        subprocess.run(["gcc", "-std=gnu11", "-I", ref_inc, probe, "-o", theirs], check=True)
+        assert subprocess.run([theirs], capture_output=True, text=True, check=True).stdout == mine
+
+
+def test_reference_api_demo_compiles_against_both_headers(seb, tmp_path):
+    """examples/se_reference_api_demo.c includes only "seal_embedded.h": it must build against include/ (the compat
+    shim) and, where the reference tree is mounted, against the reference's own header, and link against the product
+    library both times (it is RUN in tests/test_gpu_round2.py::test_application_built_against_reference_header)."""
+    seb.build_library()
+    src = os.path.join(ROOT, "examples", "se_reference_api_demo.c")
+    incs = [os.path.join(ROOT, "include")]
+    if os.path.isdir("/root/reference/device/lib"):
+        incs.append("/root/reference/device/lib")
+    for k, inc in enumerate(incs):
+        exe = str(tmp_path / f"demo{k}")
+        subprocess.run(["gcc", "-std=gnu11", "-O2", "-Wall", "-Werror", src, "-I", inc, "-L", PKG, "-lseal_embedded_b200",
+                        f"-Wl,-rpath,{PKG}", "-o", exe], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_seal_layout_conversion(seb):
+    """seb_ct_to_seal_layout / seb_ct_from_seal_layout (host functions, no GPU): the device library's per-ciphertext
+    stream [nprimes][2][n] u32 against a restatement of the adapter's loader loop (adapter/fileops.cpp:518-527:
+    ct_ptr[i + j*n] = c0 of prime j, ct_ptr[i + j*n + nprimes*n] = c1 of prime j, 64-bit coefficients)."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    for batch, np_, n in ((1, 1, 1024), (3, 3, 4096), (2, 6, 16)):
+        ct = rng.integers(0, 1 << 30, (batch, np_, 2, n), dtype=np.uint32)
+        seal = seb.ct_to_seal_layout(ct)
+        for b in range(batch):
+            ct_ptr = np.zeros(2 * np_ * n, np.uint64)
+            for j in range(np_):  # the adapter's loop, one prime (two components) at a time
+                ct_temp_1p = np.concatenate([ct[b, j, 0], ct[b, j, 1]]).astype(np.uint64)
+                for i in range(n):
+                    ct_ptr[i + j * n] = ct_temp_1p[i]
+                    ct_ptr[i + j * n + np_ * n] = ct_temp_1p[i + n]
+            assert np.array_equal(seal[b].reshape(-1), ct_ptr)
+        assert np.array_equal(seb.ct_from_seal_layout(seal), ct)
+    wide = np.zeros((1, 2, 1, 16), np.uint64)
+    wide[0, 1, 0, 5] = 1 << 40  # a coefficient of a wider SEAL prime cannot enter the 32-bit stream
+    with pytest.raises(seb.SebError):
+        seb.ct_from_seal_layout(wide)
+
+
+def test_caller_moduli_are_validated(seb):
+    """seb_create with caller-supplied moduli (se_setup_custom's path): composite numbers — including ones for which
+    some psi satisfies psi^n = -1 —, primes that are not 1 mod 2n, moduli of 30 bits or more and duplicates are
+    rejected before any CUDA call."""
+    import numpy as np
+
+    lib = seb.load_library()
+
+    def create(n, primes, psis=None):
+        pa = np.asarray(primes, np.uint32)
+        ps = np.asarray(psis, np.uint32) if psis is not None else None
+        return lib.seb_create(n, len(primes), pa.ctypes.data, ps.ctypes.data if ps is not None else None, 0.0, 1, 0)
+
+    n = 1024
+    # a composite q = 1 mod 2n for which a psi with psi^n = -1 mod q exists: q = p1 * p2 with both p_i = 1 mod 2n,
+    # psi built by the Chinese remainder theorem from an element of order 2n modulo each
+    p1, p2 = 12289, 18433  # 6 * 2048 + 1 and 9 * 2048 + 1
+    roots = []
+    for p_ in (p1, p2):
+        c = next(pow(g, (p_ - 1) // (2 * n), p_) for g in range(2, 50) if pow(pow(g, (p_ - 1) // (2 * n), p_), n, p_) == p_ - 1)
+        roots.append(c)
+    q = p1 * p2
+    psi = (roots[0] * p2 * pow(p2, -1, p1) + roots[1] * p1 * pow(p1, -1, p2)) % q
+    assert q < (1 << 30) and (q - 1) % (2 * n) == 0 and pow(psi, n, q) == q - 1
+    found = (q, psi)
+    assert not create(n, [found[0]], [found[1]]) and b"unusable" in lib.seb_last_error()
+    assert not create(n, [1000003]) and b"unusable" in lib.seb_last_error()          # prime, but 1000002 % 2048 != 0
+    assert not create(n, [3221225473]) and b"unusable" in lib.seb_last_error()       # 3 * 2^30 + 1: a prime >= 2^30
+    assert not create(4096, [1053818881, 1053818881]) and b"twice" in lib.seb_last_error()

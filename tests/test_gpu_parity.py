@@ -142,21 +142,25 @@ def test_samplers_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
 def test_sampler_uniform_both_kernels(n, np_, coop, wide, seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
     """sample_poly_uniform (sample.c:39-57) through each of the two bulk kernels — one sequential sponge per thread
     (large batches) and the warp-cooperative sponge spread over 25 lanes (small batches), forced with
-    SEB_UNIFORM_COOP — and each of the two fix-up kernels — a warp per ciphertext with 32-candidate waves and a CTA
-    per ciphertext with one round of candidates, forced with SEB_UNIFORM_FIX_WIDE: same polynomials, same
+    the "uniform_coop" option — and each of the two fix-up kernels — a warp per ciphertext with 32-candidate waves and a CTA
+    per ciphertext with one round of candidates, forced with "uniform_fix_wide": same polynomials, same
     counters as the oracle, for a batch that is not a multiple of the warps per CTA."""
     torch = torch_cuda
-    monkeypatch.setenv("SEB_UNIFORM_COOP", coop)
-    monkeypatch.setenv("SEB_UNIFORM_FIX_WIDE", wide)
     ctx = ctxs(n, np_, False)
+    ctx.set_option("uniform_coop", int(coop))  # switches are context state (read from the environment only in seb_create)
+    ctx.set_option("uniform_fix_wide", int(wide))
     batch = 9
     seeds = oracle_mod.make_seeds(batch, b"uniform-k-%d" % n)
     d_seeds = dev(torch, seeds)
     d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
     d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
-    for p in range(np_):
-        ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
-    torch.cuda.synchronize()
+    try:
+        for p in range(np_):
+            ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("uniform_coop", -1)
+        ctx.set_option("uniform_fix_wide", -1)
     out = host(d_out, np.uint32).reshape(batch, np_, n)
     ctr = host(d_ctr, np.uint32)
     for b in range(batch):
@@ -703,7 +707,7 @@ def test_edge_cases_and_errors(seb, torch_cuda, oracle_mod, orc):
 
 
 def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
-    """Host-pointer batch API: pageable and pinned buffers, several chunks in flight (SEB_HOST_CHUNK forces
+    """Host-pointer batch API: pageable and pinned buffers, several chunks in flight (the "host_chunk" option forces
     3 balanced chunks of 500 items; the default policy would take 1500 items in one), ragged vlen, and
     the symmetric flavours (full and seed-compressed) through the same pipeline."""
     torch = torch_cuda
@@ -716,7 +720,7 @@ def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
     vals = oracle_mod.make_values(batch, vlen, seed=99)
     seeds = oracle_mod.make_seeds(batch, b"host")
     one = ctx.encrypt_asym_host(vals, seeds)  # default policy: a single chunk
-    monkeypatch.setenv("SEB_HOST_CHUNK", "600")
+    ctx.set_option("host_chunk", 600)
     out = ctx.encrypt_asym_host(vals, seeds)  # pageable buffers
     assert np.array_equal(out, one)
     pv = torch.from_numpy(vals).pin_memory()
@@ -724,17 +728,19 @@ def test_host_api_chunked(seb, torch_cuda, oracle_mod, orc, ctxs, monkeypatch):
     po = torch.empty((batch, np_, 2, n), dtype=torch.int32).pin_memory()
     ctx.lib.seb_encrypt_asym_host(ctx.h, pv.data_ptr(), vlen, ps.data_ptr(), batch, po.data_ptr())
     assert np.array_equal(out, po.numpy().view(np.uint32))
+    ctx.set_option("host_chunk", 0)
     for b in (0, 1, 499, 500, 501, 999, 1000, 1499):
         ok, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
         assert ok and np.array_equal(out[b], exp), b
     # symmetric: chunks of 40 out of 100 items -> 3 chunks of 34/34/32
     sctx = ctxs(n, np_, False)
     sctx.set_secret_key(sk)
-    monkeypatch.setenv("SEB_HOST_CHUNK", "40")
+    sctx.set_option("host_chunk", 40)
     sb = 100
     sseeds = oracle_mod.make_seeds(sb, b"host-share")
     full = sctx.encrypt_sym_host(vals[:sb], sseeds, seeds[:sb])
     c0 = sctx.encrypt_sym_seedct_host(vals[:sb], sseeds, seeds[:sb])
+    sctx.set_option("host_chunk", 0)
     assert np.array_equal(c0, full[:, :, 0, :])
     for b in (0, 33, 34, 67, 68, 99):
         ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
