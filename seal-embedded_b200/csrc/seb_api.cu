@@ -216,7 +216,9 @@ struct seb_ctx
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint32_t rej_cap = 0;  // capacity of the uniform sampler's per-ciphertext reject lists (n/8)
     // resident tables
-    seb_oct *d_roots    = nullptr;  // [np][seb_table_octs]: per-pass twiddle tables
+    seb_oct *d_roots    = nullptr;  // [np][seb_table_octs(logn)]: per-pass twiddle tables, 16-coefficient plan (asymmetric kernel)
+    seb_oct *d_roots1   = nullptr;  // the same roots in the plan of the one-polynomial kernels (= d_roots below n = 8192)
+    int key1 = 0;                   // seb_ntt_key1(logn)
     double2 *d_tw       = nullptr;  // [n] natural order + [7][n/8] pass-0 copies (seb_encode.cuh)
     uint16_t *d_src_map = nullptr;  // [n]
     seb_oct *d_pk0 = nullptr, *d_pk1 = nullptr;  // [np][n/4] Shoup pairs, epilogue order
@@ -369,9 +371,11 @@ static int build_tables(seb_ctx *c)
     const size_t n = c->n;
     // NTT roots: bit-reversed powers of psi in Shoup form (ntt.c:40-52, uintmodarith.h:293-297),
     // re-ordered per pass into the layout the kernels read with coalesced 256-bit loads
-    const size_t octs = seb_table_octs(c->logn);
-    std::vector<seb_oct> tabs(c->np * octs);
+    c->key1 = seb_ntt_key1(c->logn);
+    const size_t octs = seb_table_octs(c->logn), octs1 = seb_table_octs(c->key1);
+    std::vector<seb_oct> tabs(c->np * octs), tabs1(c->key1 != c->logn ? c->np * octs1 : 0);
     memset(tabs.data(), 0, tabs.size() * sizeof(seb_oct));
+    if (!tabs1.empty()) memset(tabs1.data(), 0, tabs1.size() * sizeof(seb_oct));
     std::vector<uint2> roots(n);
     for (size_t p = 0; p < c->np; p++)
     {
@@ -383,9 +387,17 @@ static int build_tables(seb_ctx *c)
             pw                        = mulmod(pw, psi, q);
         }
         seb_host_build_tw(c->logn, roots.data(), tabs.data() + p * octs);
+        if (!tabs1.empty()) seb_host_build_tw(c->key1, roots.data(), tabs1.data() + p * octs1);
     }
     CU(cudaMalloc(&c->d_roots, tabs.size() * sizeof(seb_oct)));
     CU(cudaMemcpy(c->d_roots, tabs.data(), tabs.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
+    if (tabs1.empty())
+        c->d_roots1 = c->d_roots;
+    else
+    {
+        CU(cudaMalloc(&c->d_roots1, tabs1.size() * sizeof(seb_oct)));
+        CU(cudaMemcpy(c->d_roots1, tabs1.data(), tabs1.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
+    }
 
     // inverse roots for the verifier's INTT: iroots[bitrev(i)] = psi^-i, and n^-1
     {
@@ -564,6 +576,7 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaDeviceSynchronize();
     free_scratch(c->dev, c->n);
     for (auto &s : c->hslot) free_scratch(s, c->n);
+    if (c->d_roots1 != c->d_roots) cudaFree(c->d_roots1);
     cudaFree(c->d_roots);
     cudaFree(c->d_tw);
     cudaFree(c->d_src_map);
@@ -620,7 +633,8 @@ extern "C" double seb_scale(const seb_ctx *c) { return c ? c->scale : 0; }
 extern "C" uint32_t seb_prime(const seb_ctx *c, size_t i) { return (c && i < c->np) ? c->primes[i] : 0; }
 extern "C" uint64_t seb_launch_count(const seb_ctx *c) { return c ? c->launches : 0; }
 
-static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst)
+// key: the plan whose epilogue order the table is laid out in (logn for pk0/pk1, key1 for ntt(s))
+static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst, int key)
 {
     std::vector<uint2> nat(c->n);
     std::vector<seb_oct> tab(c->np * (c->n / 4));
@@ -632,7 +646,7 @@ static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst)
             if (w >= c->primes[p]) return fail(SE_ERR_INVALD_ARGUMENT, "key coefficient %u >= modulus", w);
             nat[i] = make_uint2(w, shoup(w, c->primes[p]));
         }
-        seb_host_build_epi(c->logn, nat.data(), tab.data() + p * (c->n / 4));
+        seb_host_build_epi(key, nat.data(), tab.data() + p * (c->n / 4));
     }
     if (!*dst) CU(cudaMalloc(dst, tab.size() * sizeof(seb_oct)));
     CU(cudaMemcpy(*dst, tab.data(), tab.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
@@ -643,9 +657,9 @@ extern "C" int seb_set_public_key(seb_ctx *c, const uint32_t *pk0, const uint32_
 {
     if (!c || !pk0 || !pk1) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
     CU(cudaSetDevice(c->device));
-    int r = upload_shoup(c, pk0, &c->d_pk0);
+    int r = upload_shoup(c, pk0, &c->d_pk0, c->logn);
     if (r) return r;
-    r = upload_shoup(c, pk1, &c->d_pk1);
+    r = upload_shoup(c, pk1, &c->d_pk1, c->logn);
     if (r) return r;
     c->have_pk = true;
     return 0;
@@ -677,14 +691,14 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     cudaError_t e = cudaMemcpy(d, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
     {
-        e = seb_launch_ntt(c->logn, d, c->d_roots, c->mods, (int)c->np, c->np, c->stream);
+        e = seb_launch_ntt(c->logn, d, c->d_roots1, c->mods, (int)c->np, c->np, c->stream);
         c->launches++;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(s.data(), d, s.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     wipe_free(d, s.size() * sizeof(uint32_t));
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "ntt(s): %s", cudaGetErrorString(e));
-    int r = upload_shoup(c, s.data(), &c->d_ntt_s);
+    int r = upload_shoup(c, s.data(), &c->d_ntt_s, c->key1);
     if (r) return r;
     if (!c->d_ntt_s_nat) CU(cudaMalloc(&c->d_ntt_s_nat, s.size() * sizeof(uint32_t)));
     CU(cudaMemcpy(c->d_ntt_s_nat, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -780,7 +794,7 @@ extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const ui
                            c->mods.m[p], 1, d_rej, d_small + 2, cap, c->knobs, st);
     }
     CUK(cudaGetLastError());
-    CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots, c->d_ntt_s, c->mods,
+    CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots1, c->d_ntt_s, c->mods,
                                (int)np, d_out + n, d_out, 2 * np * n, 2 * n, 0, 1, st));
     c->launches += 2 + 2 * np;
     std::vector<uint32_t> out(2 * np * n);
@@ -873,7 +887,7 @@ extern "C" int seb_sample_uniform_device(seb_ctx *c, const uint8_t *d_seeds, uin
 extern "C" int seb_ntt_device(seb_ctx *c, uint32_t *d_polys, size_t batch)
 {
     if (!c || !d_polys) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
-    CU(seb_launch_ntt(c->logn, d_polys, c->d_roots, c->mods, (int)c->np, batch * c->np, c->stream));
+    CU(seb_launch_ntt(c->logn, d_polys, c->d_roots1, c->mods, (int)c->np, batch * c->np, c->stream));
     c->launches++;
     return 0;
 }
@@ -1039,7 +1053,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     prof_mark(c, st, 2);
     if ((r = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, st))) return r;
     prof_mark(c, st, 3);
-    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
+    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots1, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
                               ct_stride, p_stride, seedct ? 0 : quirk, (int)batch, st));
     prof_mark(c, st, 4);
     prof_next(c, st);

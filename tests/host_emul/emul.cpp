@@ -24,14 +24,16 @@ struct HostLoad
     uint32_t operator()(int p, uint32_t pos) const { return src[(size_t)p * n + pos]; }
 };
 
+// LOGN below is a plan KEY (seb_ntt.cuh NttCfg): log2(n) for 16 coefficients per thread, 16 + log2(n) for 32
 template <int LOGN, int NPOLY, int P>
-static void ntt_passes(std::vector<std::array<uint32_t[SEB_E], NPOLY>> &regs, uint32_t *smem, const seb_oct *tw,
+static void ntt_passes(std::vector<std::array<uint32_t[NttCfg<LOGN>::E], NPOLY>> &regs, uint32_t *smem, const seb_oct *tw,
                        uint32_t q, HostLoad &ld)
 {
-    constexpr int T = (1 << LOGN) / SEB_E;
+    constexpr int T = NttCfg<LOGN>::T;
+    constexpr int E = NttCfg<LOGN>::E;
     for (int t = 0; t < T; t++)
     {
-        uint32_t(&x)[NPOLY][SEB_E] = *reinterpret_cast<uint32_t(*)[NPOLY][SEB_E]>(regs[t].data());
+        uint32_t(&x)[NPOLY][E] = *reinterpret_cast<uint32_t(*)[NPOLY][E]>(regs[t].data());
         seb_ntt_pass<LOGN, P, NPOLY>(x, smem, t, tw, q, 2 * q, ld);
     }
     if constexpr (P + 1 < NttPlan<LOGN>::NPASS) ntt_passes<LOGN, NPOLY, P + 1>(regs, smem, tw, q, ld);
@@ -40,9 +42,9 @@ static void ntt_passes(std::vector<std::array<uint32_t[SEB_E], NPOLY>> &regs, ui
 template <int LOGN, int NPOLY>
 static void ntt_emul(const uint32_t *in, const uint2 *tw, uint32_t q, uint32_t *out)
 {
-    constexpr int N = 1 << LOGN;
-    constexpr int T = N / SEB_E;
-    std::vector<std::array<uint32_t[SEB_E], NPOLY>> regs(T);
+    constexpr int N = 1 << NttCfg<LOGN>::LOGN;
+    constexpr int T = NttCfg<LOGN>::T;
+    std::vector<std::array<uint32_t[NttCfg<LOGN>::E], NPOLY>> regs(T);
     std::vector<uint32_t> smem_store((size_t)NPOLY * NttSmem<LOGN>::WORDS + 4, 0xDEADBEEFu);
     uint32_t *smem_al = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(smem_store.data()) + 15) & ~uintptr_t(15));
     HostLoad ld{in, N};
@@ -72,7 +74,7 @@ static void ntt_emul(const uint32_t *in, const uint2 *tw, uint32_t q, uint32_t *
 extern "C" int emul_ntt(int logn, int npoly, const uint32_t *in, const uint32_t *roots_w, const uint32_t *roots_wq,
                         uint32_t q, uint32_t *out)
 {
-    const int n = 1 << logn;
+    const int n = 1 << (logn & 15);
     std::vector<uint2> tw(n);
     for (int i = 0; i < n; i++) tw[i] = make_uint2(roots_w[i], roots_wq[i]);
 #define CASE(L)                                                  \
@@ -91,6 +93,8 @@ extern "C" int emul_ntt(int logn, int npoly, const uint32_t *in, const uint32_t 
         CASE(12)
         CASE(13)
         CASE(14)
+        CASE(29)
+        CASE(30)
     }
 #undef CASE
     return -1;
@@ -105,6 +109,8 @@ extern "C" uint32_t emul_pad(int logn, uint32_t a)
         case 12: return seb_pad<12>(a);
         case 13: return seb_pad<13>(a);
         case 14: return seb_pad<14>(a);
+        case 29: return seb_pad<29>(a);
+        case 30: return seb_pad<30>(a);
     }
     return a;
 }
@@ -118,6 +124,8 @@ extern "C" uint32_t emul_smem_words(int logn)
         case 12: return NttSmem<12>::WORDS;
         case 13: return NttSmem<13>::WORDS;
         case 14: return NttSmem<14>::WORDS;
+        case 29: return NttSmem<29>::WORDS;
+        case 30: return NttSmem<30>::WORDS;
     }
     return 0;
 }
@@ -135,6 +143,8 @@ extern "C" int emul_plan(int logn, int *radices)
         CASE(12)
         CASE(13)
         CASE(14)
+        CASE(29)
+        CASE(30)
     }
 #undef CASE
     return 0;
@@ -149,12 +159,12 @@ extern "C" int64_t emul_ntt_elem(int logn, int pass, uint32_t t, uint32_t i, uin
         if (P >= NttPlan<L>::NPASS) return -1;                                                        \
         constexpr int PP = P < NttPlan<L>::NPASS ? P : 0;                                             \
         constexpr int R  = NttPlan<L>::R[PP];                                                         \
-        constexpr int LS = L - NttS0<L, PP>::value - R;                                               \
-        if (i >= (uint32_t)(SEB_E >> R) || j >= (1u << R)) return -1;                                 \
+        constexpr int LS = NttCfg<L>::LOGN - NttS0<L, PP>::value - R;                                 \
+        if (i >= (uint32_t)(NttCfg<L>::E >> R) || j >= (1u << R)) return -1;                          \
         return (int64_t)(seb_ntt_group_base<L, PP>(t, i) | (j << LS));                                \
     }
 #define CASEL(L) CASEP(L, 0) CASEP(L, 1) CASEP(L, 2) CASEP(L, 3)
-    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14)
+    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14) CASEL(29) CASEL(30)
 #undef CASEL
 #undef CASEP
     return -1;
@@ -168,7 +178,7 @@ extern "C" int emul_ntt_sync_scope(int logn, int pass)
     if (logn == L && pass == P)                                                                      \
         return NttSync<L, P>::value == SEB_SYNC_CTA ? 0 : NttSync<L, P>::value == SEB_SYNC_WARP ? 32 : NttSync<L, P>::GROUP;
 #define CASEL(L) CASEP(L, 0) CASEP(L, 1) CASEP(L, 2) CASEP(L, 3)
-    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14)
+    CASEL(10) CASEL(11) CASEL(12) CASEL(13) CASEL(14) CASEL(29) CASEL(30)
 #undef CASEL
 #undef CASEP
     return 0;

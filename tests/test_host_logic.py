@@ -13,6 +13,16 @@ import numpy as np
 import pytest
 
 LOGNS = [10, 11, 12, 13, 14]
+# NTT plan keys (seb_ntt.cuh NttCfg): log2(n) = 16 coefficients per thread; 16 + log2(n) = 32 per thread (n >= 8192)
+KEYS = [10, 11, 12, 13, 14, 29, 30]
+
+
+def _key_logn(key):
+    return key & 15
+
+
+def _key_e(key):
+    return 32 if key & 16 else 16
 
 
 def _p(a, t):
@@ -83,40 +93,43 @@ def test_barrett_and_shoup(E):
 # ------------------------------------------------------------------------------------------------
 # NTT: plan, layout, transform
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("logn", LOGNS)
-def test_ntt_plan(logn, E):
-    plan = _plan(E, logn)
-    assert sum(plan) == logn and all(r in (3, 4) for r in plan)
-    assert plan[0] == 4  # the first pass reads 16 strided coefficients per thread
+@pytest.mark.parametrize("key", KEYS)
+def test_ntt_plan(key, E):
+    plan = _plan(E, key)
+    logn, e = _key_logn(key), _key_e(key)
+    assert sum(plan) == logn and all(r in (3, 4, 5) for r in plan)
+    assert (1 << plan[0]) == e  # the first pass reads E strided coefficients per thread: one group
+    assert all((1 << r) <= e for r in plan)
 
 
-@pytest.mark.parametrize("logn", LOGNS)
-def test_smem_layout_conflict_free(logn, E):
+@pytest.mark.parametrize("key", KEYS)
+def test_smem_layout_conflict_free(key, E):
     """seb_pad: (1) injective and inside NttSmem::WORDS; (2) additive over bit-disjoint fields, which is
     what turns every per-element address into base + immediate; (3) for every pass, the 32 lanes of
     every warp hit 32 distinct banks on each scalar access, and the last pass' 128-bit reads are
     conflict free per quarter-warp phase."""
+    logn, epl = _key_logn(key), _key_e(key)
     n = 1 << logn
-    T = n // 16
-    pad = np.array([E.emul_pad(logn, a) for a in range(n)], dtype=np.int64)
-    words = E.emul_smem_words(logn)
+    T = n // epl
+    pad = np.array([E.emul_pad(key, a) for a in range(n)], dtype=np.int64)
+    words = E.emul_smem_words(key)
     assert len(set(pad.tolist())) == n and pad.max() < words and words % 4 == 0
     rng = np.random.default_rng(logn)
     for _ in range(2000):
         x = int(rng.integers(0, n))
         y = int(rng.integers(0, n)) & ~x
-        assert E.emul_pad(logn, x | y) == E.emul_pad(logn, x) + E.emul_pad(logn, y)
-    plan = _plan(E, logn)
+        assert E.emul_pad(key, x | y) == E.emul_pad(key, x) + E.emul_pad(key, y)
+    plan = _plan(E, key)
     s0 = 0
     for pi, R in enumerate(plan):
         LS = logn - s0 - R
-        GP = 16 >> R
+        GP = epl >> R
         last = pi == len(plan) - 1
         if pi > 0 or not last:
             for i in range(GP):
                 for w0 in range(0, T, 32):
                     # element 0 of slot i of the warp's 32 threads, from the kernels' own mapping
-                    base = np.array([E.emul_ntt_elem(logn, pi, t, i, 0) for t in range(w0, w0 + 32)], dtype=np.int64)
+                    base = np.array([E.emul_ntt_elem(key, pi, t, i, 0) for t in range(w0, w0 + 32)], dtype=np.int64)
                     if last and pi > 0:
                         # 128-bit reads: 8 lanes per phase, each 4 consecutive words
                         for k in range((1 << R) // 4):
@@ -124,55 +137,58 @@ def test_smem_layout_conflict_free(logn, E):
                             assert (addr % 4 == 0).all()
                             for ph in range(4):
                                 banks = (addr[8 * ph: 8 * ph + 8] // 4) % 8
-                                assert len(set(banks.tolist())) == 8, (logn, pi, i, w0, k)
+                                assert len(set(banks.tolist())) == 8, (key, pi, i, w0, k)
                     else:
                         for j in range(1 << R):
                             banks = pad[base | (j << LS)] % 32
-                            assert len(set(banks.tolist())) == 32, (logn, pi, i, j, w0)
+                            assert len(set(banks.tolist())) == 32, (key, pi, i, j, w0)
         s0 += R
 
 
-@pytest.mark.parametrize("logn", LOGNS)
-def test_ntt_barrier_scopes(logn, E):
+@pytest.mark.parametrize("key", KEYS)
+def test_ntt_barrier_scopes(key, E):
     """Each pass covers every coefficient exactly once, and wherever the kernels replace the CTA barrier
     between two passes by a narrower one (NttSync: __syncwarp() or a named barrier over an aligned group of
     64 / 128 threads), every coefficient a thread reads in the later pass was written in the earlier one by
     a thread of the same warp / group."""
+    logn, epl = _key_logn(key), _key_e(key)
     n = 1 << logn
-    T = n // 16
-    plan = _plan(E, logn)
+    T = n // epl
+    plan = _plan(E, key)
     owner = []
     for p, R in enumerate(plan):
         own = np.full(n, -1, np.int64)
         for t in range(T):
-            for i in range(16 >> R):
+            for i in range(epl >> R):
                 for j in range(1 << R):
-                    e = E.emul_ntt_elem(logn, p, t, i, j)
+                    e = E.emul_ntt_elem(key, p, t, i, j)
                     assert 0 <= e < n and own[e] == -1
                     own[e] = t
         assert (own >= 0).all()
         owner.append(own)
     scopes = []
     for p in range(len(plan) - 1):
-        width = E.emul_ntt_sync_scope(logn, p)  # 0: whole CTA, 32: warp, else threads per named barrier
+        width = E.emul_ntt_sync_scope(key, p)  # 0: whole CTA, 32: warp, else threads per named barrier
         if width:
             shift = width.bit_length() - 1
             assert 1 << shift == width
-            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (logn, p, width)
+            assert bool(((owner[p] >> shift) == (owner[p + 1] >> shift)).all()), (key, p, width)
             if width > 32:
                 # hardware barriers 1..15 only: barrier 0 is __syncthreads()
                 assert T % width == 0 and T // width <= 15
         scopes.append(width)
-    expect = {10: [0, 32], 11: [0, 0], 12: [0, 32], 13: [0, 64, 32], 14: [0, 128, 32]}[logn]
+    # the 32-coefficient plans keep ONE CTA-wide barrier per transform
+    expect = {10: [0, 32], 11: [0, 0], 12: [0, 32], 13: [0, 64, 32], 14: [0, 128, 32], 29: [0, 32], 30: [0, 32]}[key]
     assert scopes == expect
-    assert E.emul_ntt_sync_scope(logn, len(plan) - 1) == 0
+    assert E.emul_ntt_sync_scope(key, len(plan) - 1) == 0
 
 
-@pytest.mark.parametrize("logn", LOGNS)
+@pytest.mark.parametrize("key", KEYS)
 @pytest.mark.parametrize("npoly", [1, 3])
-def test_ntt_emulation_matches_oracle(logn, npoly, E, orc):
+def test_ntt_emulation_matches_oracle(key, npoly, E, orc):
     """The register-blocked multi-pass transform (seb_ntt_pass + per-pass twiddle tables + the
     epilogue-order key-table indexing) equals ntt_inpl (ntt.c:124-189) bit for bit."""
+    logn = _key_logn(key)
     n = 1 << logn
     nprimes = {10: 1, 11: 1, 12: 3, 13: 6, 14: 13}[logn]
     rng = np.random.default_rng(100 + logn)
@@ -182,11 +198,11 @@ def test_ntt_emulation_matches_oracle(logn, npoly, E, orc):
         x = rng.integers(0, q, (npoly, n), dtype=np.uint32)
         x[0, :4] = (0, 1, q - 1, q - 2)
         out = np.zeros_like(x)
-        rc = E.emul_ntt(logn, npoly, _p(x, C.c_uint32), _p(roots, C.c_uint32), _p(wq, C.c_uint32), q,
+        rc = E.emul_ntt(key, npoly, _p(x, C.c_uint32), _p(roots, C.c_uint32), _p(wq, C.c_uint32), q,
                         _p(out, C.c_uint32))
         assert rc == 0
         for p in range(npoly):
-            assert np.array_equal(out[p], orc.ntt(n, q, x[p])), (logn, q, p)
+            assert np.array_equal(out[p], orc.ntt(n, q, x[p])), (key, q, p)
 
 
 def test_ntt_emulation_lazy_inputs(E, orc):
