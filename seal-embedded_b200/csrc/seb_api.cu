@@ -561,6 +561,7 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     if ((e = cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device)) != cudaSuccess)
         return bail("cudaDeviceGetAttribute", e);
     c->verify_ctas = c->sms * (n <= 4096 ? 4 : n <= 8192 ? 2 : 1);
+    c->knobs.sms   = c->sms;
     if (build_tables(c) != 0)
     {
         seb_destroy(c);

@@ -24,6 +24,7 @@ struct SebKnobs
     int uniform_spec     = -1;  // speculative prime chain for lone calls
     int uniform_pair     = -1;  // bulk squeeze by two lanes per sponge (bit-interleaved halves)
     long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
+    int sms              = 0;   // SM count of the context's device (kernel selection by machine fill; not an option)
 };
 
 // ---- samplers (seb_sample.cu) ----

@@ -15,10 +15,11 @@
 #include "seb_kernels.h"
 #include "seb_sample.cuh"
 
-// batches up to this size take the warp-cooperative bulk sampler: measured 1.4x faster at 2048 items and 0.9x at
-// 4096, at n = 1024, 4096 and 16384 alike (profiles/r01_ab_uniform_coop.txt)
+// batches up to this size take the warp-cooperative bulk sampler (25 lanes per sponge): it beats the two-lane kernel
+// up to ~1400 items at n = 4096 and 16384 alike (profiles/r02_ab_uniform_pair.txt; against the thread-per-sponge
+// kernel alone the crossover was ~3000, profiles/r01_ab_uniform_coop.txt)
 #ifndef SEB_UNIFORM_COOP_MAX_BATCH
-#define SEB_UNIFORM_COOP_MAX_BATCH 3072
+#define SEB_UNIFORM_COOP_MAX_BATCH 1280
 #endif
 
 __device__ __forceinline__ void load_seed(const uint8_t *seeds, size_t b, uint64_t (&s)[8])
@@ -196,28 +197,37 @@ __global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__
     while (left > 0)
     {
         seb_keccak_f1600(a);
+        // Branch-free over the 17 rate lanes (rejections are 2 % of the words: a branch per word costs more than the
+        // work it skips); the rejected words of the block are collected in a bit mask and listed afterwards.
+        const int nk = min(17, left);
+        uint32_t m0 = 0, m1 = 0;  // bit 2k / 2k+1: low / high word of rate lane k rejected (m1: lane 16)
 #pragma unroll
         for (int k = 0; k < 17; k++)
         {
-            if (k < left)
-            {
-                uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
-                if (lo < max_multiple)
-                    lo = seb_barrett32(lo, mod);
-                else
-                {
-                    if (cnt < cap) list[cnt] = (uint16_t)(word + 2 * k);
-                    cnt++;
-                }
-                if (hi < max_multiple)
-                    hi = seb_barrett32(hi, mod);
-                else
-                {
-                    if (cnt < cap) list[cnt] = (uint16_t)(word + 2 * k + 1);
-                    cnt++;
-                }
-                dst[k] = make_uint2(lo, hi);
-            }
+            const uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
+            const bool in = k < nk;
+            const bool rl = in && lo >= max_multiple, rh = in && hi >= max_multiple;
+            const uint32_t bits = (rl ? 1u : 0u) | (rh ? 2u : 0u);
+            if (k < 16)
+                m0 |= bits << (2 * k);
+            else
+                m1 = bits;
+            const uint32_t vl = rl ? lo : seb_barrett32(lo, mod), vh = rh ? hi : seb_barrett32(hi, mod);
+            if (in) dst[k] = make_uint2(vl, vh);
+        }
+        while (m0)
+        {
+            const int bit = __ffs(m0) - 1;
+            if (cnt < cap) list[cnt] = (uint16_t)(word + bit);
+            cnt++;
+            m0 &= m0 - 1;
+        }
+        while (m1)
+        {
+            const int bit = __ffs(m1) - 1;
+            if (cnt < cap) list[cnt] = (uint16_t)(word + 32 + bit);
+            cnt++;
+            m1 &= m1 - 1;
         }
         dst += 17;
         word += 34;
@@ -373,6 +383,164 @@ __global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__rest
     const uint32_t cnt  = seb_coop_bulk_row(seeds + (size_t)b * SEB_SEED_BYTES, ctr[b], out + (size_t)b * ct_stride,
                                             rej_idx + (size_t)b * cap, n, mod, max_multiple, cap, c, lane);
     if (lane == 0) rej_cnt[b] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the bulk squeeze for MID-SIZE batches: TWO lanes per ciphertext, the Keccak state bit-interleaved
+// ---------------------------------------------------------------------------------------------
+// A shard of a few thousand to a few tens of thousands of ciphertexts (configuration D on eight GPUs: 16384 items)
+// gives the thread-per-sponge kernel ONE warp per SM sub-partition: every instruction waits for the one before
+// it (ncu: ALU pipe 57 %, profiles/README.md), and the 25-lane kernel above costs six times the issue slots.  Here a
+// sponge is split over two adjacent lanes in the classic bit-interleaved representation: the EVEN lane holds bits
+// 0,2,4,... of each of the 25 words (32 bits each), the ODD lane bits 1,3,5,...  Every logic step is bitwise, so
+// each lane works on its own half; a 64-bit rotation by 2k is a 32-bit rotation by k of each half, and a rotation
+// by 2k+1 swaps the halves: even' = rotl32(odd, k+1), odd' = rotl32(even, k).  Twelve of the 24 rho offsets and
+// theta's rotation by one are odd: 17 exchanges (shfl.bfly 1) per round.  Per lane and round: 90 ALU operations
+// (10 column parities, 5 + 24 rotations, 25 + 25 three-input logic, 1 iota) — the SAME 180 per sponge as one thread
+// computes, on twice the warps with half the dependency depth.  The squeezed words are de-interleaved with one more
+// exchange and a 4-step perfect shuffle each (the even lane rebuilds the low 32 bits of every rate word, the odd
+// lane the high 32 bits).  Output, reject lists and counters are exactly those of k_uniform_bulk (sample.c:39-57).
+SEB_CONSTANT uint32_t c_keccak_rc_even[24] = {
+    0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
+    0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
+    0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000000u};
+SEB_CONSTANT uint32_t c_keccak_rc_odd[24] = {
+    0x00000000u, 0x00000089u, 0x8000008bu, 0x80008080u, 0x0000008bu, 0x00008000u, 0x80008088u, 0x80000082u,
+    0x0000000bu, 0x0000000au, 0x00008082u, 0x00008003u, 0x0000808bu, 0x8000000bu, 0x8000008au, 0x80000081u,
+    0x80000081u, 0x80000008u, 0x00000083u, 0x80008003u, 0x80008088u, 0x80000088u, 0x00008000u, 0x80008082u};
+
+// the even (odd = 0) or odd (odd = 1) bits of w, packed
+__device__ __forceinline__ uint32_t seb_half_bits(uint64_t w, const int odd)
+{
+    uint64_t t = (w >> odd) & 0x5555555555555555ULL;
+    t = (t | (t >> 1)) & 0x3333333333333333ULL;
+    t = (t | (t >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    t = (t | (t >> 4)) & 0x00FF00FF00FF00FFULL;
+    t = (t | (t >> 8)) & 0x0000FFFF0000FFFFULL;
+    t = (t | (t >> 16)) & 0x00000000FFFFFFFFULL;
+    return (uint32_t)t;
+}
+
+// v = bytes [a0, b0, a1, b1] of two 16-bit values a, b  ->  bit 2i = a_i, bit 2i+1 = b_i: the last three steps of the
+// 32-bit perfect shuffle (the first, a swap of the two middle bytes, is folded into the byte permute that builds v)
+__device__ __forceinline__ uint32_t seb_interleave_tail(uint32_t v)
+{
+    uint32_t t;
+    t = (v ^ (v >> 4)) & 0x00F000F0u;
+    v = v ^ t ^ (t << 4);
+    t = (v ^ (v >> 2)) & 0x0C0C0C0Cu;
+    v = v ^ t ^ (t << 2);
+    t = (v ^ (v >> 1)) & 0x22222222u;
+    v = v ^ t ^ (t << 1);
+    return v;
+}
+
+// theta + rho + pi of word SRC on this lane's half; e = 1 on the even lane, 0 on the odd lane
+#define SEB_PAIR_RP(SRC, DST, ROT)                                                               \
+    {                                                                                            \
+        const uint32_t t_ = seb_xor3(s[SRC], c[((SRC) % 5 + 4) % 5], r[((SRC) % 5 + 1) % 5]);    \
+        if (((ROT) & 1) == 0)                                                                    \
+            b[DST] = ((ROT) / 2) ? __funnelshift_l(t_, t_, (ROT) / 2) : t_;                       \
+        else                                                                                     \
+        {                                                                                        \
+            const uint32_t p_ = __shfl_xor_sync(0xFFFFFFFFu, t_, 1);                             \
+            b[DST]            = __funnelshift_l(p_, p_, (ROT) / 2 + e);                          \
+        }                                                                                        \
+    }
+
+__device__ __forceinline__ void seb_keccak_pair(uint32_t (&s)[25], const uint32_t e)
+{
+#pragma unroll 1
+    for (int round = 0; round < 24; round++)
+    {
+        uint32_t c[5], r[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = seb_xor3(seb_xor3(s[x], s[x + 5], s[x + 10]), s[x + 15], s[x + 20]);
+        // rotl64(C, 1): even half = rotl32(odd half, 1), odd half = even half
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+        {
+            const uint32_t pc = __shfl_xor_sync(0xFFFFFFFFu, c[x], 1);
+            r[x]              = __funnelshift_l(pc, pc, e);
+        }
+        SEB_PAIR_RP(0, 0, 0) SEB_PAIR_RP(1, 10, 1) SEB_PAIR_RP(2, 20, 62) SEB_PAIR_RP(3, 5, 28) SEB_PAIR_RP(4, 15, 27)
+        SEB_PAIR_RP(5, 16, 36) SEB_PAIR_RP(6, 1, 44) SEB_PAIR_RP(7, 11, 6) SEB_PAIR_RP(8, 21, 55) SEB_PAIR_RP(9, 6, 20)
+        SEB_PAIR_RP(10, 7, 3) SEB_PAIR_RP(11, 17, 10) SEB_PAIR_RP(12, 2, 43) SEB_PAIR_RP(13, 12, 25) SEB_PAIR_RP(14, 22, 39)
+        SEB_PAIR_RP(15, 23, 41) SEB_PAIR_RP(16, 8, 45) SEB_PAIR_RP(17, 18, 15) SEB_PAIR_RP(18, 3, 21) SEB_PAIR_RP(19, 13, 8)
+        SEB_PAIR_RP(20, 14, 18) SEB_PAIR_RP(21, 24, 2) SEB_PAIR_RP(22, 9, 61) SEB_PAIR_RP(23, 19, 56) SEB_PAIR_RP(24, 4, 14)
+#pragma unroll
+        for (int y = 0; y < 25; y += 5)
+#pragma unroll
+            for (int x = 0; x < 5; x++) s[y + x] = seb_chi(b[y + x], b[y + (x + 1) % 5], b[y + (x + 2) % 5]);
+        s[0] ^= e ? c_keccak_rc_even[round] : c_keccak_rc_odd[round];
+    }
+}
+#undef SEB_PAIR_RP
+
+__global__ void __launch_bounds__(32) k_uniform_bulk_pair(const uint8_t *__restrict__ seeds, const uint32_t *__restrict__ ctr,
+                                                           uint32_t *__restrict__ out, size_t ct_stride, int n,
+                                                           SebModulus mod, uint32_t max_multiple, int batch,
+                                                           uint16_t *__restrict__ rej_idx, uint32_t *__restrict__ rej_cnt,
+                                                           uint32_t cap)
+{
+    const int gt     = blockIdx.x * blockDim.x + threadIdx.x;
+    const int odd    = gt & 1;         // which half of the state this lane holds
+    const uint32_t e = 1u - (uint32_t)odd;
+    const bool live  = (gt >> 1) < batch;
+    const int b      = live ? (gt >> 1) : batch - 1;  // idle pairs of the last warp shadow the last ciphertext
+    // absorb seed || LE64(counter), pad (seb_prng_init), this lane's half of every word
+    uint32_t s[25];
+    {
+        const uint64_t *sp = reinterpret_cast<const uint64_t *>(seeds + (size_t)b * SEB_SEED_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = seb_half_bits(__ldg(sp + i), odd);
+        s[8] = seb_half_bits((uint64_t)ctr[b], odd);
+        s[9] = odd ? 0x3u : 0x7u;  // 0x1F: bits 0, 2, 4 | bits 1, 3
+#pragma unroll
+        for (int i = 10; i < 25; i++) s[i] = 0u;
+        s[16] = odd ? 0x80000000u : 0u;  // bit 63
+    }
+    uint32_t *row   = out + (size_t)b * ct_stride;
+    uint16_t *list  = rej_idx + (size_t)b * cap;
+    uint32_t cnt    = 0;
+    // De-interleave: the even lane rebuilds the LOW 32 bits of a rate word from the low 16 bits of the two halves, the
+    // odd lane the HIGH 32 bits from their high 16 bits.  One byte permute of (own, partner) picks the four bytes in
+    // the order [even.lo, odd.lo, even.hi, odd.hi] of those 16-bit values; own is the even half on the even lane
+    // and the odd half on the odd lane, hence the two selectors.
+    const uint32_t sel = odd ? 0x3726u : 0x5140u;
+    for (int word = 0; word < n; word += 34)
+    {
+        seb_keccak_pair(s, e);
+        uint32_t rm       = 0;  // bit k: this lane's word of rate lane k was rejected
+        // the rate block is 17 (even, odd) word pairs; n is even, so only the LAST block of a row is partial and a pair
+        // is inside or outside as a whole: nk = pairs of this block that belong to the row.  Idle lanes store nothing.
+        const int nk  = live ? min(17, (n - word) >> 1) : 0;
+        uint32_t *dst = row + word + odd;
+#pragma unroll
+        for (int k = 0; k < 17; k++)
+        {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, s[k], 1);
+            const uint32_t w     = seb_interleave_tail(__byte_perm(s[k], other, sel));
+            const bool in        = k < nk;
+            const bool rej       = in && w >= max_multiple;
+            rm |= rej ? (1u << k) : 0u;
+            const uint32_t red = seb_barrett32(w, mod);
+            if (in) dst[2 * k] = rej ? w : red;
+        }
+        // ascending word order within the block: (even lane k = 0, odd lane k = 0, even lane k = 1, ...)
+        const uint32_t pm = __shfl_xor_sync(0xFFFFFFFFu, rm, 1);
+        uint32_t m        = rm;
+        while (m)
+        {
+            const int k          = __ffs(m) - 1;
+            const uint32_t below = (1u << k) - 1u;
+            const uint32_t pos   = cnt + (uint32_t)__popc(rm & below) + (uint32_t)__popc(pm & (odd ? (below << 1) | 1u : below));
+            if (live && pos < cap) list[pos] = (uint16_t)(word + 2 * k + odd);
+            m &= m - 1;
+        }
+        cnt += (uint32_t)__popc(rm) + (uint32_t)__popc(pm);
+    }
+    if (live && !odd) rej_cnt[b] = cnt;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -721,7 +889,21 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     // all SM sub-partitions (131072-item config D leaves 16384 items = 512 warps per GPU for 592 sub-partitions).
     // knobs.uniform_coop = 0/1 forces either (tests, A/B measurements).
     const bool coop = knobs.uniform_coop >= 0 ? knobs.uniform_coop != 0 : batch <= SEB_UNIFORM_COOP_MAX_BATCH;
-    if (coop)
+    // Between the two: two lanes per sponge (bit-interleaved halves).  Both kernels are latency machines at these
+    // sizes: a launch takes as long as the most loaded SM sub-partition, kt = ceil(warps / sub-partitions) warps of 32
+    // sponges for the thread kernel, kp for the pair kernel's warps of 16.  A linear fit of the measured chain times
+    // (profiles/r02_ab_uniform_pair.txt: thread 23 / 41 / 85 ms for kt = 1 / 2 / 4 at n = 16384 x 6, pair 15.8 / 25 /
+    // 36.6 / 49 for kp = 1..4) picks the kernel: pair while 12 kp + 3.5 < 21 kt + 2, i.e. up to one pair warp per
+    // sub-partition (9472 items on 148 SMs) and again in the windows where the thread kernel has just spilled into
+    // a second or third warp.  knobs.uniform_pair = 0/1 forces the choice.
+    const int subparts = 4 * (knobs.sms > 0 ? knobs.sms : 148);
+    const int kt       = ((batch + 31) / 32 + subparts - 1) / subparts;
+    const int kp       = ((batch + 15) / 16 + subparts - 1) / subparts;
+    const bool pair    = knobs.uniform_pair >= 0 ? knobs.uniform_pair != 0 : (!coop && 12.0 * kp + 3.5 < 21.0 * kt + 2.0);
+    if (pair)
+        k_uniform_bulk_pair<<<(2 * batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
+                                                                  rej_idx, rej_cnt, rej_cap);
+    else if (coop)
         k_uniform_bulk_coop<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
                                                              rej_idx, rej_cnt, rej_cap);
     else

@@ -171,6 +171,36 @@ def test_sampler_uniform_both_kernels(n, np_, coop, wide, seb, torch_cuda, oracl
         assert ctr[b] == c
 
 
+@pytest.mark.parametrize("batch", [1, 9, 16, 37])
+@pytest.mark.parametrize("n,np_", CONFIGS)
+def test_sampler_uniform_pair_kernel(n, np_, batch, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """The third bulk kernel (k_uniform_bulk_pair, mid-size batches): two lanes per sponge with the Keccak state
+    bit-interleaved (even / odd bits), forced with the "uniform_pair" option.  Same polynomials, reject lists (through
+    the fix-up) and counters as sample_poly_uniform (sample.c:39-57), for batches that fill a warp exactly (16), leave
+    idle pairs in the last warp (1, 9, 37) and span several warps; the counter chain runs on across the primes."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    ctx.set_option("uniform_pair", 1)
+    seeds = oracle_mod.make_seeds(batch, b"uniform-pair-%d" % n)
+    d_seeds = dev(torch, seeds)
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+    try:
+        for p in range(np_):
+            ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("uniform_pair", -1)
+    out = host(d_out, np.uint32).reshape(batch, np_, n)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        c = 0
+        for p, q in enumerate(ctx.primes):
+            exp, c = orc.sample_uniform(n, q, seeds[b], c)
+            assert np.array_equal(out[b, p], exp), (n, batch, b, p)
+        assert ctr[b] == c
+
+
 @pytest.mark.parametrize("n,np_", CONFIGS)
 def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """sample.c:39-57: bulk draw, ordered redraws, counter running on across primes (ckks_sym.c:219)."""
