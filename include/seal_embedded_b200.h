@@ -239,6 +239,20 @@ int seb_encrypt_sym_seedct_host(seb_ctx *ctx, const float *values, size_t vlen,
                                 const uint8_t *shareable_seeds, const uint8_t *seeds, size_t batch,
                                 uint32_t *c0_out);
 
+/* Optional packed wire form of the host-pointer calls: every residue is below 2^30, so a ciphertext's [nprimes][2][n]
+ * words travel as 30 bits per residue — seb_packed30_words(ctx) = 2 * nprimes * n * 15 / 16 words per ciphertext,
+ * residue i of each group of 16 in bits 30i .. 30i+29 (little endian) of the group's 15 words.  The host-pointer path
+ * is bound by the PCIe link (6.25 % fewer bytes = 6.25 % more ciphertexts/s); the full form stays the default.
+ * seb_unpack30 (host, no GPU) / seb_unpack30_device restore the full form bit for bit: `words` = full-form words, a
+ * multiple of 16. */
+size_t seb_packed30_words(const seb_ctx *ctx);
+int seb_encrypt_asym_host_packed30(seb_ctx *ctx, const float *values, size_t vlen, const uint8_t *seeds,
+                                   size_t batch, uint32_t *out_packed);
+int seb_encrypt_sym_host_packed30(seb_ctx *ctx, const float *values, size_t vlen, const uint8_t *shareable_seeds,
+                                  const uint8_t *seeds, size_t batch, uint32_t *out_packed, int ref_quirk);
+int seb_unpack30(const uint32_t *packed, size_t words, uint32_t *out);
+int seb_unpack30_device(seb_ctx *ctx, const uint32_t *d_packed, size_t words, uint32_t *d_out);
+
 /* ---- stage level (device pointers, asynchronous) ---- */
 /* ckks_encode_base: d_pt [batch][n] int64 */
 int seb_encode_device(seb_ctx *ctx, const float *d_values, size_t vlen, size_t batch, int64_t *d_pt);
@@ -267,6 +281,10 @@ int seb_decrypt_decode_device(seb_ctx *ctx, const uint32_t *d_ct, size_t batch, 
  * d_digests[b] = sum_i mix64((i << 32) | word_i) mod 2^64 with the splitmix64 finaliser — 8 bytes per ciphertext
  * to compare a full-size batch with the reference run on the host (tests/, oracle/ref_shim.c: ref_encrypt_digests) */
 int seb_digest_device(seb_ctx *ctx, const uint32_t *d_words, size_t words_per_item, size_t items, uint64_t *d_digests);
+/* The integer-issue ceilings of this device, measured on the spot with register-only loops of the path's two inner
+ * operations: Keccak-f[1600] permutations/s (what bounds the samplers) and lazy NTT butterflies/s (what bounds the
+ * NTT / encrypt kernels beside HBM).  bench.py's roofline denominators for the kernels that are not HBM-bound. */
+int seb_measure_ceilings(seb_ctx *ctx, double *keccak_f_per_s, double *butterflies_per_s);
 /* first 136-byte block of SHAKE256(seed_i || LE64(counter_i)): d_out [count][17] u64 */
 int seb_prng_blocks_device(seb_ctx *ctx, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
                            uint64_t *d_out);

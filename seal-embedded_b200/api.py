@@ -90,7 +90,8 @@ EXPORTED_SYMBOLS = [
     "seb_intt_device", "seb_decrypt_decode_device", "seb_gen_public_key",
     "seb_encrypt_sym_seedct_device", "seb_encrypt_sym_seedct_host", "seb_expand_seedct_device",
     "se_b200_set_sym_seed_ct", "se_encrypt_batch_seedct", "seb_minimal_psi", "seb_uniform_spec_misses",
-    "seb_set_option", "seb_gen_secret_key", "seb_digest_device", "seb_ct_to_seal_layout", "seb_ct_from_seal_layout",
+    "seb_packed30_words", "seb_encrypt_asym_host_packed30", "seb_encrypt_sym_host_packed30", "seb_unpack30",
+    "seb_unpack30_device", "seb_measure_ceilings", "seb_set_option", "seb_gen_secret_key", "seb_digest_device", "seb_ct_to_seal_layout", "seb_ct_from_seal_layout",
 ]
 
 
@@ -113,6 +114,13 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.seb_destroy.argtypes = [vp]
     L.seb_destroy.restype = None
     L.seb_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.seb_measure_ceilings.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.seb_packed30_words.argtypes = [vp]
+    L.seb_packed30_words.restype = sz
+    L.seb_encrypt_asym_host_packed30.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.seb_encrypt_sym_host_packed30.argtypes = [vp, vp, sz, vp, vp, sz, vp, i32]
+    L.seb_unpack30.argtypes = [vp, sz, vp]
+    L.seb_unpack30_device.argtypes = [vp, vp, sz, vp]
     L.seb_gen_secret_key.argtypes = [vp, vp, vp]
     L.seb_digest_device.argtypes = [vp, vp, sz, sz, vp]
     L.seb_ct_to_seal_layout.argtypes = [vp, sz, sz, sz, vp]
@@ -298,6 +306,12 @@ class Context:
         """A/B switches ("uniform_coop", "uniform_fix_wide", "uniform_spec", "uniform_pair", "host_chunk"); < 0 = auto."""
         self._check(self.lib.seb_set_option(self.h, name.encode(), int(value)))
 
+    def measure_ceilings(self) -> tuple[float, float]:
+        """(Keccak-f[1600]/s, lazy butterflies/s) register-only on this device, measured now."""
+        k, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.seb_measure_ceilings(self.h, C.byref(k), C.byref(b)))
+        return k.value, b.value
+
     def digest_device(self, d_words, words_per_item: int, items: int, d_digests) -> None:
         self._check(self.lib.seb_digest_device(self.h, _addr(d_words), words_per_item, items, _addr(d_digests)))
 
@@ -339,6 +353,41 @@ class Context:
         self._check(self.lib.seb_encrypt_sym_host(self.h, _addr(values), vlen, _addr(share_seeds), _addr(seeds),
                                                   batch, _addr(out), int(ref_quirk)))
         return out
+
+    # -- optional packed wire form: 30 bits per residue (15 words per 16 residues)
+    def packed30_words(self) -> int:
+        return int(self.lib.seb_packed30_words(self.h))
+
+    def encrypt_asym_host_packed30_raw(self, values_ptr: int, vlen: int, seeds_ptr: int, batch: int, out_ptr: int) -> None:
+        self._check(self.lib.seb_encrypt_asym_host_packed30(self.h, values_ptr, vlen, seeds_ptr, batch, out_ptr))
+
+    def encrypt_asym_host_packed30(self, values: np.ndarray, seeds: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        batch, vlen = values.shape
+        if out is None:
+            out = np.empty((batch, self.packed30_words()), np.uint32)
+        self.encrypt_asym_host_packed30_raw(_addr(values), vlen, _addr(seeds), batch, _addr(out))
+        return out
+
+    def encrypt_sym_host_packed30(self, values: np.ndarray, share_seeds: np.ndarray, seeds: np.ndarray,
+                                  ref_quirk: bool = False) -> np.ndarray:
+        batch, vlen = values.shape
+        out = np.empty((batch, self.packed30_words()), np.uint32)
+        self._check(self.lib.seb_encrypt_sym_host_packed30(self.h, _addr(values), vlen, _addr(share_seeds), _addr(seeds),
+                                                           batch, _addr(out), int(ref_quirk)))
+        return out
+
+    def unpack30_host(self, packed: np.ndarray) -> np.ndarray:
+        """[batch][packed30_words] -> [batch][nprimes][2][n] on the host (seb_unpack30, no GPU)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        batch = packed.shape[0]
+        out = np.empty((batch, self.nprimes, 2, self.n), np.uint32)
+        rc = self.lib.seb_unpack30(_addr(packed), batch * 2 * self.nprimes * self.n, _addr(out))
+        if rc:
+            raise SebError(f"seb_unpack30: {rc}")
+        return out
+
+    def unpack30_device(self, d_packed, words: int, d_out) -> None:
+        self._check(self.lib.seb_unpack30_device(self.h, _addr(d_packed), words, _addr(d_out)))
 
     # -- seed-compressed symmetric ciphertexts (SURVEY 8f-2): c0 only; c1 = a is rebuilt from the shareable seed
     def encrypt_sym_seedct_device(self, d_values, vlen: int, d_share_seeds, d_seeds, batch: int, d_c0_out) -> None:

@@ -198,6 +198,8 @@ struct Scratch  // per in-flight chunk
     float *d_values  = nullptr;
     uint8_t *d_seeds = nullptr, *d_sseeds = nullptr;
     uint32_t *d_out  = nullptr;
+    uint32_t *d_pack = nullptr;  // packed wire form of d_out (allocated on first use)
+    size_t pack_words = 0;
     int *h_fail      = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done    = nullptr;
@@ -360,6 +362,7 @@ static void free_scratch(Scratch &s, size_t n)
     wipe_free(s.d_seeds, s.io_cap * SEB_SEED_BYTES);
     cudaFree(s.d_sseeds);
     cudaFree(s.d_out);
+    cudaFree(s.d_pack);
     cudaFreeHost(s.h_fail);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -929,6 +932,21 @@ extern "C" int seb_digest_device(seb_ctx *c, const uint32_t *d_words, size_t wor
     return 0;
 }
 
+// The integer-issue ceilings of this device, measured now with register-only loops of the path's two inner operations
+// (seb_verify.cu): Keccak-f[1600] permutations/s (ALU pipe) and lazy NTT butterflies/s (FMA pipe).  Synchronises.
+extern "C" int seb_measure_ceilings(seb_ctx *c, double *keccak_f_per_s, double *butterflies_per_s)
+{
+    if (!c || !keccak_f_per_s || !butterflies_per_s) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(c->device));
+    void *scratch = nullptr;
+    CU(cudaMalloc(&scratch, (size_t)c->sms * 16 * 256 * 8));
+    cudaError_t e = seb_measure_ceilings(c->sms, c->d_roots, c->primes[0], scratch, keccak_f_per_s, butterflies_per_s, c->stream);
+    cudaFree(scratch);
+    c->launches += 8;
+    if (e != cudaSuccess) return fail(SE_ERR_CUDA, "seb_measure_ceilings: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int seb_prng_blocks_device(seb_ctx *c, const uint8_t *d_seeds, const uint64_t *d_counters, size_t count,
                                       uint64_t *d_out)
 {
@@ -1232,7 +1250,8 @@ static int ensure_io(seb_ctx *c, Scratch &s, size_t chunk, bool sym, size_t per_
 }
 
 static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, const uint8_t *sseeds,
-                        const uint8_t *seeds, size_t batch, uint32_t *out, int quirk, bool seedct = false)
+                        const uint8_t *seeds, size_t batch, uint32_t *out, int quirk, bool seedct = false,
+                        bool packed = false)
 {
     if (!c) return fail(SE_ERR_INVALD_ARGUMENT, "null context");
     if (batch == 0) return 0;
@@ -1243,13 +1262,23 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
     if (r) return r;
     CU(cudaSetDevice(c->device));
     const size_t chunk  = host_chunk(c, sym, batch);
-    const size_t per_ct = (seedct ? 1 : 2) * c->np * c->n;  // words of output per ciphertext
+    const size_t per_ct = (seedct ? 1 : 2) * c->np * c->n;  // words of output per ciphertext on the device
+    const size_t per_out = packed ? per_ct / 16 * 15 : per_ct;  // ... and in the caller's buffer
     const bool pin_out  = is_pinned(out);
     const size_t nslots = chunk < batch ? 2 : 1;
     for (size_t k = 0; k < nslots; k++)
     {
         if ((r = ensure_scratch(c, c->hslot[k], chunk))) return r;
         if ((r = ensure_io(c, c->hslot[k], chunk, sym, per_ct))) return r;
+        Scratch &s = c->hslot[k];
+        if (packed && s.pack_words < chunk * per_out)
+        {
+            cudaFree(s.d_pack);
+            s.d_pack     = nullptr;
+            s.pack_words = 0;
+            CU(cudaMalloc(&s.d_pack, chunk * per_out * sizeof(uint32_t)));
+            s.pack_words = chunk * per_out;
+        }
     }
     struct Pending
     {
@@ -1263,8 +1292,8 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
         if (!pend[k].live) return 0;
         Scratch &s = c->hslot[k];
         if (!pin_out)  // blocking copy, ordered after the chunk's kernels on its stream
-            CU(cudaMemcpyAsync(out + pend[k].first * per_ct, s.d_out, pend[k].count * per_ct * sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(out + pend[k].first * per_out, packed ? s.d_pack : s.d_out,
+                               pend[k].count * per_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventSynchronize(s.done));
         for (size_t i = 0; i < pend[k].count; i++) failures += s.h_fail[i] != 0;
         pend[k].live = false;
@@ -1285,9 +1314,14 @@ static int encrypt_host(seb_ctx *c, bool sym, const float *values, size_t vlen, 
         r = sym ? encrypt_sym_on(c, s, s.d_values, vlen, s.d_sseeds, s.d_seeds, count, s.d_out, quirk, seedct, s.stream)
                 : encrypt_asym_on(c, s, s.d_values, vlen, s.d_seeds, count, s.d_out, s.stream);
         if (r) return r;
+        if (packed)
+        {
+            CU(seb_launch_pack30(s.d_out, s.d_pack, count * per_ct, s.stream));
+            c->launches++;
+        }
         if (pin_out)
-            CU(cudaMemcpyAsync(out + first * per_ct, s.d_out, count * per_ct * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                               s.stream));
+            CU(cudaMemcpyAsync(out + first * per_out, packed ? s.d_pack : s.d_out, count * per_out * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_fail, s.fail, count * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
         pend[k].first = first;
@@ -1305,6 +1339,50 @@ extern "C" int seb_encrypt_asym_host(seb_ctx *c, const float *values, size_t vle
                                      size_t batch, uint32_t *out)
 {
     return encrypt_host(c, false, values, vlen, nullptr, seeds, batch, out, 0);
+}
+
+// The optional packed wire form (SURVEY 8f-1 "wire formats"): every residue is below 2^30, so
+// the [nprimes][2][n] words of a ciphertext travel as 15/16 of their size, 30 bits per residue.  out_packed receives
+// seb_packed30_words(ctx) words per ciphertext; seb_unpack30 / seb_unpack30_device restore the full form bit for bit.
+extern "C" size_t seb_packed30_words(const seb_ctx *c) { return c ? 2 * c->np * c->n / 16 * 15 : 0; }
+
+extern "C" int seb_encrypt_asym_host_packed30(seb_ctx *c, const float *values, size_t vlen, const uint8_t *seeds,
+                                              size_t batch, uint32_t *out_packed)
+{
+    return encrypt_host(c, false, values, vlen, nullptr, seeds, batch, out_packed, 0, false, true);
+}
+
+extern "C" int seb_encrypt_sym_host_packed30(seb_ctx *c, const float *values, size_t vlen, const uint8_t *sseeds,
+                                             const uint8_t *seeds, size_t batch, uint32_t *out_packed, int quirk)
+{
+    return encrypt_host(c, true, values, vlen, sseeds, seeds, batch, out_packed, quirk, false, true);
+}
+
+// d_packed [words * 15 / 16] -> d_out [words] (words a multiple of 16), on the context's stream
+extern "C" int seb_unpack30_device(seb_ctx *c, const uint32_t *d_packed, size_t words, uint32_t *d_out)
+{
+    if (!c || !d_packed || !d_out) return fail(SE_ERR_INVALD_ARGUMENT, "null argument");
+    if (words % 16) return fail(SE_ERR_INVALD_ARGUMENT, "words must be a multiple of 16");
+    CU(seb_launch_unpack30(d_packed, d_out, words, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// the same on the host (no GPU involved): packed [words * 15 / 16] -> out [words]
+extern "C" int seb_unpack30(const uint32_t *packed, size_t words, uint32_t *out)
+{
+    if (!packed || !out || words % 16) return SE_ERR_INVALD_ARGUMENT;
+    for (size_t g = 0; g < words / 16; g++)
+    {
+        const uint32_t *w = packed + 15 * g;
+        for (int i = 0; i < 16; i++)
+        {
+            const int k = (30 * i) / 32, sh = 30 * i - 32 * k;
+            const uint64_t two = ((uint64_t)(k < 14 ? w[k + 1] : 0u) << 32) | w[k];
+            out[16 * g + i]    = (uint32_t)(two >> sh) & 0x3FFFFFFFu;
+        }
+    }
+    return 0;
 }
 
 extern "C" int seb_encrypt_sym_host(seb_ctx *c, const float *values, size_t vlen, const uint8_t *sseeds,

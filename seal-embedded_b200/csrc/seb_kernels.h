@@ -98,6 +98,13 @@ cudaError_t seb_encrypt_configure(int logn);
 // ---- verifier: inverse NTT, decrypt + decode, per-item digests (seb_verify.cu) ----
 // digests[b] = sum_i mix64((i << 32) | words[b][i]) mod 2^64 (words_per_item a multiple of 4, rows 16-byte aligned)
 cudaError_t seb_launch_digest(const uint32_t *words, size_t words_per_item, size_t items, uint64_t *digests, cudaStream_t st);
+// packed wire form: `words` full-form words (a multiple of 16, 16-byte aligned) <-> words * 15 / 16 packed words
+cudaError_t seb_launch_pack30(const uint32_t *in, uint32_t *out, size_t words, cudaStream_t st);
+cudaError_t seb_launch_unpack30(const uint32_t *in, uint32_t *out, size_t words, cudaStream_t st);
+// register-only Keccak-f[1600] and lazy-butterfly loops: the integer-issue ceilings of this device, measured now
+// (tw: any valid twiddle table of a 16-coefficient plan; scratch >= sms * 16 * 128 * 8 bytes)
+cudaError_t seb_measure_ceilings(int sms, const seb_oct *tw, uint32_t q, void *scratch, double *keccak_per_s, double *bfly_per_s,
+                                 cudaStream_t st);
 // iroots: per prime n Shoup pairs, iroots[i] = inverse of the forward table's root i; ninvs: n^-1 per prime
 cudaError_t seb_verify_configure(int n);
 cudaError_t seb_launch_intt(uint32_t *polys, const uint2 *iroots, const uint2 *ninvs, const SebModuli &mods, int n,

@@ -171,6 +171,167 @@ cudaError_t seb_launch_digest(const uint32_t *words, size_t words_per_item, size
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// optional packed wire form: residues are < q < 2^30, so 16 of them fit 15 words (30 bits each, little endian:
+// residue i of a group occupies bits 30i .. 30i+29 of the group's 480 bits).  6.25 % fewer bytes on the PCIe link,
+// which is what bounds the host-pointer path (profiles/README.md); the full form stays the default.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack30(const uint4 *__restrict__ in, uint32_t *__restrict__ out, size_t groups)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const uint4 v = seb_ldg_stream(in + 4 * g + k);
+        r[4 * k] = v.x, r[4 * k + 1] = v.y, r[4 * k + 2] = v.z, r[4 * k + 3] = v.w;
+    }
+    uint32_t *dst = out + 15 * g;
+#pragma unroll
+    for (int w = 0; w < 15; w++)
+    {
+        // word w holds bits 32w .. 32w+31: the top of residue i = 32w / 30 and the bottom of residue i + 1
+        const int i = (32 * w) / 30, sh = 32 * w - 30 * i;  // residue i contributes its bits sh .. 29
+        dst[w] = (r[i] >> sh) | (r[i + 1] << (30 - sh));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpack30(const uint32_t *__restrict__ in, uint4 *__restrict__ out, size_t groups)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 15; k++) w[k] = in[15 * g + k];
+    w[15] = 0;
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+    {
+        const int k = (30 * i) / 32, sh = 30 * i - 32 * k;  // residue i starts at bit sh of word k
+        const uint64_t two = ((uint64_t)w[k + (k < 15 ? 1 : 0)] << 32) | w[k];
+        r[i] = (uint32_t)(two >> sh) & 0x3FFFFFFFu;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * g + k] = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+}
+
+cudaError_t seb_launch_pack30(const uint32_t *in, uint32_t *out, size_t words, cudaStream_t st)
+{
+    if (words == 0) return cudaSuccess;
+    if (words % 16) return cudaErrorInvalidValue;
+    const size_t groups = words / 16;
+    k_pack30<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(in), out, groups);
+    return cudaGetLastError();
+}
+
+cudaError_t seb_launch_unpack30(const uint32_t *in, uint32_t *out, size_t words, cudaStream_t st)
+{
+    if (words == 0) return cudaSuccess;
+    if (words % 16) return cudaErrorInvalidValue;
+    const size_t groups = words / 16;
+    k_unpack30<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(in, reinterpret_cast<uint4 *>(out), groups);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// in-run integer-issue ceilings (bench.py's roofline for the kernels that are not HBM-bound)
+// ---------------------------------------------------------------------------------------------
+// Register-only loops of the two inner operations of the path, on enough resident warps to saturate the pipes:
+//   k_ceiling_keccak : Keccak-f[1600] exactly as the samplers run it (seb_keccak.cuh: 180 ALU-pipe operations per round)
+//   k_ceiling_bfly   : Harvey/Shoup lazy butterflies exactly as the NTT passes run them (seb_ntt.cuh: seb_bfly, radix-16
+//                      register groups: IMAD.HI + 2 IMAD on the FMA pipe, 3 operations on the ALU pipe)
+// What they reach IS the ceiling the sampler / NTT kernels are measured against ("frac" of an ALU- or FMA-bound kernel).
+#include "seb_keccak.cuh"
+#include "seb_ntt.cuh"
+
+__global__ void __launch_bounds__(128) k_ceiling_keccak(uint64_t *__restrict__ out, int iters)
+{
+    uint64_t a[25];
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = t * 0x9E3779B97F4A7C15ULL + (uint64_t)i;
+    for (int it = 0; it < iters; it++) seb_keccak_f1600(a);
+    uint64_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 25; i++) x ^= a[i];
+    out[t] = x;
+}
+
+__global__ void __launch_bounds__(256) k_ceiling_bfly(uint32_t *__restrict__ out, const seb_oct *__restrict__ tw, uint32_t q,
+                                                     int iters)
+{
+    uint32_t x[SEB_E];
+    uint2 w[15];
+    const uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t two_q = 2 * q;
+#pragma unroll
+    for (int i = 0; i < SEB_E; i++) x[i] = (t * 2654435761u + (uint32_t)i * 40503u) % q;
+    // 15 roots of a radix-16 register group, fetched once (heap slots 1..15 of the first group of the table)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const seb_oct o = seb_ldg256(tw + k);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (4 * k + c >= 1) w[4 * k + c - 1] = make_uint2(o.v[2 * c], o.v[2 * c + 1]);
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; it++)
+    {
+        // 32 butterflies: the four stages of a radix-16 pass on the thread's 16 registers
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            const int half = 8 >> r;
+#pragma unroll
+            for (int m = 0; m < (1 << r); m++)
+#pragma unroll
+                for (int k = 0; k < half; k++) seb_bfly(x[m * 2 * half + k], x[m * 2 * half + k + half], w[(1 << r) - 1 + m], q, two_q);
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < SEB_E; i++) acc ^= x[i];
+    out[t] = acc;
+}
+
+// keccak_per_s / bfly_per_s: best of 3 timed launches each (CUDA events on `st`); scratch: >= ctas * 256 * 8 bytes
+cudaError_t seb_measure_ceilings(int sms, const seb_oct *tw, uint32_t q, void *scratch, double *keccak_per_s, double *bfly_per_s,
+                                 cudaStream_t st)
+{
+    cudaEvent_t e0, e1;
+    cudaError_t err = cudaEventCreate(&e0);
+    if (err != cudaSuccess) return err;
+    if ((err = cudaEventCreate(&e1)) != cudaSuccess) return err;
+    const int kc = sms * 16, kt = 128, kiters = 64;   // 16 CTAs x 128 threads per SM
+    const int bc = sms * 8, bt = 256, biters = 2048;  // 8 CTAs x 256 threads per SM wanted (registers decide)
+    double best_k = 0, best_b = 0;
+    for (int rep = 0; rep < 4 && err == cudaSuccess; rep++)
+    {
+        float ms = 0;
+        cudaEventRecord(e0, st);
+        k_ceiling_keccak<<<kc, kt, 0, st>>>(static_cast<uint64_t *>(scratch), kiters);
+        cudaEventRecord(e1, st);
+        if ((err = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0) best_k = fmax(best_k, (double)kc * kt * kiters / (ms * 1e-3));
+        cudaEventRecord(e0, st);
+        k_ceiling_bfly<<<bc, bt, 0, st>>>(static_cast<uint32_t *>(scratch), tw, q, biters);
+        cudaEventRecord(e1, st);
+        if ((err = cudaEventSynchronize(e1)) != cudaSuccess) break;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0) best_b = fmax(best_b, (double)bc * bt * biters * 32.0 / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    *keccak_per_s = best_k;
+    *bfly_per_s   = best_b;
+    return err;
+}
+
 cudaError_t seb_verify_configure(int n)
 {
     // The attribute belongs to the kernel, not to a context: contexts of several degrees live in one

@@ -247,3 +247,24 @@ def test_caller_moduli_are_validated(seb):
     assert not create(n, [1000003]) and b"unusable" in lib.seb_last_error()          # prime, but 1000002 % 2048 != 0
     assert not create(n, [3221225473]) and b"unusable" in lib.seb_last_error()       # 3 * 2^30 + 1: a prime >= 2^30
     assert not create(4096, [1053818881, 1053818881]) and b"twice" in lib.seb_last_error()
+
+
+def test_unpack30_host(seb):
+    """seb_unpack30 (host function, no GPU) against a big-integer restatement of the packed wire form: residue i of
+    every group of 16 occupies bits 30i .. 30i+29 of the group's fifteen 32-bit words, little endian."""
+    import numpy as np
+
+    lib = seb.load_library()
+    rng = np.random.default_rng(5)
+    res = rng.integers(0, 1 << 30, (37, 16), dtype=np.uint32)
+    res[0] = (1 << 30) - 1
+    res[1] = 0
+    res[2, ::2] = (1 << 30) - 1
+    packed = np.zeros((37, 15), np.uint32)
+    for g in range(37):
+        v = sum(int(r) << (30 * i) for i, r in enumerate(res[g]))
+        packed[g] = [(v >> (32 * w)) & 0xFFFFFFFF for w in range(15)]
+    out = np.zeros_like(res)
+    assert lib.seb_unpack30(packed.ctypes.data, res.size, out.ctypes.data) == 0
+    assert np.array_equal(out, res)
+    assert lib.seb_unpack30(packed.ctypes.data, 17, out.ctypes.data) != 0  # not a multiple of 16

@@ -434,3 +434,72 @@ def test_host_call_after_unsynchronised_device_call(seb, torch_cuda, oracle_mod,
             assert np.array_equal(hout[b], exp), b
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# optional packed wire form and the in-run ceilings
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,np_,asym", [(4096, 3, True), (1024, 1, False), (16384, 6, False)])
+def test_packed30_wire_form(n, np_, asym, seb, torch_cuda, oracle_mod, orc):
+    """seb_encrypt_*_host_packed30: 30 bits per residue, 15 words per 16 residues.  Parity = unpacking (on the host,
+    seb_unpack30, and on the device, seb_unpack30_device) gives the full form bit for bit — which is itself compared
+    with the oracle — across several chunks of the host pipeline and for pageable and pinned output buffers."""
+    torch = torch_cuda
+    ctx = seb.Context(n, np_, asym, device=0)
+    try:
+        sk, pk0, pk1 = keys_for(oracle_mod, orc, n, np_)
+        if asym:
+            ctx.set_public_key(pk0, pk1)
+        else:
+            ctx.set_secret_key(sk)
+        batch = 70
+        ctx.set_option("host_chunk", 32)  # 3 chunks: 24 / 23 / 23 items
+        vals = oracle_mod.make_values(batch, n // 2, seed=12)
+        seeds, sseeds = oracle_mod.make_seeds(batch, b"p30"), oracle_mod.make_seeds(batch, b"p30-s")
+        if asym:
+            full = ctx.encrypt_asym_host(vals, seeds)
+            packed = ctx.encrypt_asym_host_packed30(vals, seeds)
+        else:
+            full = ctx.encrypt_sym_host(vals, sseeds, seeds)
+            packed = ctx.encrypt_sym_host_packed30(vals, sseeds, seeds)
+        pw = ctx.packed30_words()
+        assert pw == 2 * np_ * n * 15 // 16 and packed.shape == (batch, pw)
+        assert np.array_equal(ctx.unpack30_host(packed), full)
+        d_pk = dev(torch, packed)
+        d_full = torch.zeros((batch, np_, 2, n), dtype=torch.int32, device="cuda")
+        ctx.unpack30_device(d_pk, batch * 2 * np_ * n, d_full)
+        torch.cuda.synchronize()
+        assert np.array_equal(host(d_full, np.uint32), full)
+        if asym:  # pinned output buffer: the asynchronous copy path
+            po = torch.empty((batch, pw), dtype=torch.int32).pin_memory()
+            ctx.encrypt_asym_host_packed30_raw(vals.ctypes.data, n // 2, seeds.ctypes.data, batch, po.data_ptr())
+            assert np.array_equal(po.numpy().view(np.uint32), packed)
+        for b in (0, 23, 24, 69):
+            if asym:
+                _, exp = orc.encrypt_asym(n, np_, vals[b], seeds[b], pk0, pk1)
+            else:
+                _, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
+            assert np.array_equal(full[b], exp), b
+        # the packing itself, restated in numpy: residue i of a group of 16 at bits 30i .. 30i+29, little endian
+        grp = full[0].reshape(-1, 16).astype(object)
+        big = [sum(int(r) << (30 * i) for i, r in enumerate(g)) for g in grp[:8]]
+        expw = np.array([[(v >> (32 * w)) & 0xFFFFFFFF for w in range(15)] for v in big], dtype=np.uint32)
+        assert np.array_equal(packed[0].reshape(-1, 15)[:8], expw)
+    finally:
+        ctx.close()
+
+
+def test_measured_ceilings_are_plausible(seb, torch_cuda):
+    """seb_measure_ceilings: register-only Keccak-f and lazy-butterfly rates of this device.  Sanity bounds from the
+    pipe widths (64 ALU lanes and 64 FMA lanes per clock per SM): a Keccak-f is 24 x 180 ALU operations, a butterfly
+    at least 3 FMA-pipe operations — and a lower bound a factor of four below that."""
+    torch = torch_cuda
+    ctx = seb.Context(4096, 3, True, device=0)
+    try:
+        k, b = ctx.measure_ceilings()
+        props = torch.cuda.get_device_properties(0)
+        lanes_per_s = props.multi_processor_count * 64 * 2.2e9  # generous clock
+        assert lanes_per_s / (24 * 180) / 4 < k < lanes_per_s / (24 * 180) * 1.05
+        assert lanes_per_s / 3 / 8 < b < lanes_per_s / 3 * 1.05
+    finally:
+        ctx.close()

@@ -11,5 +11,5 @@ timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke.log 
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --batch 16384 > $OUT/bench_under_ncu.log 2>&1; echo "ncu rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-other --batch 16384 > $OUT/bench_under_ncu.log 2>&1; echo "ncu rc=$?"
 tail -5 $OUT/pytest_gpu.log; cat $OUT/smoke.log | tail -3; cat $OUT/bench.json; cat $OUT/bench_ref.json

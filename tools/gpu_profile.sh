@@ -11,7 +11,7 @@ if [ -x tools/ubench/ubench ]; then tools/ubench/ubench > $OUT/ubench.txt 2>&1; 
 for spec in k_encode:3 k_sample_ternary:3 k_sample_cbd:4 k_encrypt_asym:3 k_ntt_forward:3; do
   K=${spec%%:*}; S=${spec##*:}
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^(void )?$K" -s $S -c 1 -f \
-      -o $OUT/hot_$K python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --batch ${NCU_BATCH:-16384} \
+      -o $OUT/hot_$K python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-other --batch ${NCU_BATCH:-65536} \
       > $OUT/ncu_$K.log 2>&1
   echo "ncu $K rc=$?"
 done

@@ -16,7 +16,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NCU_BATCH = int(os.environ.get("NCU_BATCH", "16384"))  # ciphertexts per launch in the captured run (tools/gpu_profile.sh)
+NCU_BATCH = int(os.environ.get("NCU_BATCH", "65536"))  # ciphertexts per launch in the captured run (tools/gpu_profile.sh)
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
