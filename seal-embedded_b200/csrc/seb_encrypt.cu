@@ -75,7 +75,10 @@ __device__ __forceinline__ size_t seb_item() { return (size_t)blockIdx.z * gridD
 // 512-thread CTAs per SM and measures 46.4 % against 48.0 % (profiles/r02_ubench_ntt_plans.txt).  The
 // three-polynomial asymmetric kernel keeps 16 everywhere (3 x 32 values do not fit the register file at any useful
 // occupancy).
-#define SEB_KEY1(logn) ((logn) == 13 ? SEB_NTT_KEY32(13) : (logn))
+#define SEB_KEY1(logn) ((logn) >= 13 ? SEB_NTT_KEY32(logn) : (logn))
+// ... and at n = 16384 the 512 threads of that plan run as a CLUSTER of two 256-thread CTAs, each holding half of the
+// polynomial in its shared memory (seb_ntt.cuh, "two-CTA cluster form"): four resident CTAs per SM instead of two.
+#define SEB_CLUSTER1(logn) ((logn) == 14)
 
 // resident CTAs per SM the NTT-only kernel is compiled for, per plan: the best of the sweeps in
 // profiles/r01_ubench_ntt_occupancy.txt (48 registers for n <= 4096) and profiles/r02_ubench_ntt_plans.txt (64
@@ -87,23 +90,31 @@ struct NttOcc
                                 : K == SEB_NTT_KEY32(13) ? 4 : 2;
 };
 
-template <int K>
-__global__ void __launch_bounds__(NttCfg<K>::T, NttOcc<K>::MINB)
+// CL = 2: a cluster of two CTAs per polynomial, grid.x = 2 * prime + cluster rank (launched with the cluster attribute)
+template <int K, int CL>
+__global__ void __launch_bounds__(NttCfg<K>::T / CL, CL == 2 ? 4 : NttOcc<K>::MINB)
     k_ntt_forward(uint32_t *__restrict__ polys, const seb_oct *__restrict__ roots,
                   const __grid_constant__ SebModuli mods, int np, size_t items)
 {
     constexpr int N = 1 << NttCfg<K>::LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
-    const int t         = threadIdx.x;
+    const int t         = seb_ntt_thread<K, CL>();
     const size_t b      = seb_item();
-    if (b >= items) return;
-    const int p         = (int)blockIdx.x;
+    if (b >= items)  // uniform over a cluster: both CTAs leave together
+    {
+        if (CL == 2) seb_cluster_wait();
+        return;
+    }
+    const int p         = (int)(blockIdx.x / CL);
     const SebModulus &m = mods.m[p];
     uint32_t *data      = polys + (b * np + p) * N;
 
     uint32_t x[1][NttCfg<K>::E];
     LoadPlain ld{data};
-    seb_ntt_forward<K, 1>(x, smem, t, roots + (size_t)p * NttTwSize<K>::OCTS, m.q, m.two_q, ld);
+    if constexpr (CL == 2)
+        seb_ntt_forward_cluster2<K>(x, smem, t, roots + (size_t)p * NttTwSize<K>::OCTS, m.q, m.two_q, ld);
+    else
+        seb_ntt_forward<K, 1>(x, smem, t, roots + (size_t)p * NttTwSize<K>::OCTS, m.q, m.two_q, ld);
 
     using O = NttOut<K>;
 #pragma unroll
@@ -257,8 +268,8 @@ struct LoadSym
 // a / c0 are addressed as base + b*ct_stride + p*p_stride (words): the full layout has a in the c1 slot
 // of the output (a = out + n, c0 = out, strides 2*np*n and 2n); the seed-compressed layout keeps a in
 // scratch and writes c0 only ([batch][np][n], strides np*n and n).
-template <int K>
-__global__ void __launch_bounds__(NttCfg<K>::T, (K == SEB_NTT_KEY32(13) ? 3 : K == SEB_NTT_KEY32(14) ? 2 : 0))
+template <int K, int CL>
+__global__ void __launch_bounds__(NttCfg<K>::T / CL, (K == SEB_NTT_KEY32(13) ? 3 : CL == 2 ? 3 : 0))
     k_encrypt_sym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
                   const seb_oct *__restrict__ roots,
                   const seb_oct *__restrict__ ntt_s, const __grid_constant__ SebModuli mods, uint32_t *a_base,
@@ -266,25 +277,29 @@ __global__ void __launch_bounds__(NttCfg<K>::T, (K == SEB_NTT_KEY32(13) ? 3 : K 
 {
     constexpr int N = 1 << NttCfg<K>::LOGN;
     extern __shared__ __align__(16) uint32_t smem[];
-    const int t        = threadIdx.x;
+    const int t        = seb_ntt_thread<K, CL>();
     const size_t b     = seb_item();
-    if (b >= batch) return;
-    const int p        = (int)blockIdx.x;
+    if (b >= batch)  // uniform over a cluster
+    {
+        if (CL == 2) seb_cluster_wait();
+        return;
+    }
+    const int p        = (int)(blockIdx.x / CL);
     const SebModulus m = mods.m[p];
 
     const seb_oct *tw = roots + (size_t)p * NttTwSize<K>::OCTS;
     uint32_t x[1][NttCfg<K>::E];
-    if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // CTA-uniform, see k_encrypt_asym
+    if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // uniform over the ciphertext, see k_encrypt_asym
     {
         LoadSym<true> ld{e + b * N, pt + b * N, m};
-        seb_ntt_first<K, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+        seb_ntt_first<K, 1, LoadSym<true>, CL>(x, smem, t, tw, m.q, m.two_q, ld);
     }
     else
     {
         LoadSym<false> ld{e + b * N, pt + b * N, m};
-        seb_ntt_first<K, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+        seb_ntt_first<K, 1, LoadSym<false>, CL>(x, smem, t, tw, m.q, m.two_q, ld);
     }
-    seb_ntt_rest<K, 1>(x, smem, t, tw, m.q, m.two_q);
+    seb_ntt_rest<K, 1, CL>(x, smem, t, tw, m.q, m.two_q);
 
     using O           = NttOut<K>;
     uint32_t *c0      = c0_base + b * ct_stride + (size_t)p * p_stride;
@@ -379,21 +394,46 @@ void seb_host_build_epi(int key, const uint2 *natural, seb_oct *out)
 #undef BUILD
 }
 
+// shared memory of one CTA of a one-polynomial kernel
+template <int K, int CL>
+static constexpr size_t seb_smem1() { return 4 * (size_t)(CL == 2 ? NttSmemHalf<K>::WORDS : NttSmem<K>::WORDS); }
+
 cudaError_t seb_encrypt_configure(int logn)
 {
     cudaError_t err = cudaSuccess;
 #define CFG(L)                                                                                                    \
     {                                                                                                             \
-        constexpr int K1 = SEB_KEY1(L);                                                                           \
-        err = cudaFuncSetAttribute(k_ntt_forward<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<K1>::WORDS);      \
+        constexpr int K1 = SEB_KEY1(L), C1 = SEB_CLUSTER1(L) ? 2 : 1;                                             \
+        err = cudaFuncSetAttribute(k_ntt_forward<K1, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seb_smem1<K1, C1>()); \
         if (err == cudaSuccess)                                                                                   \
             err = cudaFuncSetAttribute(k_encrypt_asym<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * NttSmem<L>::WORDS);  \
         if (err == cudaSuccess)                                                                                   \
-            err = cudaFuncSetAttribute(k_encrypt_sym<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NttSmem<K1>::WORDS);  \
+            err = cudaFuncSetAttribute(k_encrypt_sym<K1, C1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seb_smem1<K1, C1>()); \
     }
     SEB_DISPATCH_LOGN(logn, CFG)
 #undef CFG
     return err;
+}
+
+// launch of a one-polynomial kernel over (np primes x items): plain, or as 2-CTA clusters along x
+template <int K, int CL, class Kern, class... Args>
+static cudaError_t seb_launch1(Kern kern, int np, size_t items, cudaStream_t st, Args... args)
+{
+    dim3 grid = seb_grid(np, items);
+    grid.x *= CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = dim3(NttCfg<K>::T / CL);
+    cfg.dynamicSmemBytes   = seb_smem1<K, CL>();
+    cfg.stream             = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs                = attr;
+    cfg.numAttrs             = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // roots: the table of plan seb_ntt_key1(logn)
@@ -402,12 +442,15 @@ cudaError_t seb_launch_ntt(int logn, uint32_t *polys, const seb_oct *roots, cons
 {
     if (npolys_total == 0) return cudaSuccess;
     const size_t items = npolys_total / (size_t)np;
-#define RUN(L)                                                                                                       \
-    k_ntt_forward<SEB_KEY1(L)><<<seb_grid(np, items), NttCfg<SEB_KEY1(L)>::T, 4 * NttSmem<SEB_KEY1(L)>::WORDS, st>>>( \
-        polys, roots, mods, np, items)
+    cudaError_t err    = cudaSuccess;
+#define RUN(L)                                                                                              \
+    {                                                                                                       \
+        constexpr int K1 = SEB_KEY1(L), C1 = SEB_CLUSTER1(L) ? 2 : 1;                                       \
+        err = seb_launch1<K1, C1>(k_ntt_forward<K1, C1>, np, items, st, polys, roots, mods, np, items);     \
+    }
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
-    return cudaGetLastError();
+    return err;
 }
 
 cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const uint8_t *u,
@@ -429,10 +472,14 @@ cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *
                                    size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
+    cudaError_t err = cudaSuccess;
 #define RUN(L)                                                                                                       \
-    k_encrypt_sym<SEB_KEY1(L)><<<seb_grid(np, (size_t)batch), NttCfg<SEB_KEY1(L)>::T, 4 * NttSmem<SEB_KEY1(L)>::WORDS, st>>>( \
-        pt, mag, e, roots, ntt_s, mods, a, c0, ct_stride, p_stride, quirk, (size_t)batch)
+    {                                                                                                                \
+        constexpr int K1 = SEB_KEY1(L), C1 = SEB_CLUSTER1(L) ? 2 : 1;                                                \
+        err = seb_launch1<K1, C1>(k_encrypt_sym<K1, C1>, np, (size_t)batch, st, pt, mag, e, roots, ntt_s, mods, a, c0, ct_stride, \
+                                  p_stride, quirk, (size_t)batch);                                                   \
+    }
     SEB_DISPATCH_LOGN(logn, RUN)
 #undef RUN
-    return cudaGetLastError();
+    return err;
 }

@@ -338,14 +338,55 @@ __device__ __forceinline__ void seb_ntt_sync(const int t)
         __syncthreads();
 }
 
+// ---- two-CTA cluster form (CL = 2): one polynomial over a pair of CTAs, each holding HALF of it in its shared memory.
+// Thread t of the polynomial is thread t % (T/2) of CTA t / (T/2).  Only pass 0 crosses the halves: its groups stride
+// over the whole polynomial, so a thread stores the elements with the top index bit clear into rank 0's shared memory
+// and the others into rank 1's (one of the two is remote: st.shared::cluster); a cluster barrier replaces the CTA
+// barrier after pass 0, and every later pass stays inside the CTA's own half (true for plan SEB_NTT_KEY32(14): its
+// pass-1 blocks are 512 coefficients and threads [256 r, 256 r + 256) own blocks [16 r, 16 r + 16)).
+// Why: the same 512 threads as ONE CTA leave two resident CTAs per SM, too few to hide the input loads (46 % of the
+// HBM peak); as 256-thread CTAs, four are resident (profiles/r02_ubench_ntt_plans.txt).
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t seb_cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `p` (a shared-memory pointer of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t seb_cluster_map(const void *p, uint32_t rank)
+{
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(p), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void seb_cluster_st(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void seb_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// nothing to publish yet (kernel entry): no fence
+__device__ __forceinline__ void seb_cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void seb_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+#else
+static inline uint32_t seb_cluster_rank() { return 0; }
+static inline uint32_t seb_cluster_map(const void *, uint32_t) { return 0; }
+static inline void seb_cluster_st(uint32_t, uint32_t) {}
+static inline void seb_cluster_arrive() {}
+static inline void seb_cluster_arrive_relaxed() {}
+static inline void seb_cluster_wait() {}
+#endif
+
 // One pass P of the plan.  FIRST: inputs come from load(p, pos); otherwise from smem.  LAST:
 // outputs stay in registers (x[p][i*2^R + j] = coefficient (g_i << R) + j, lazy [0,4q)) and the
 // caller finishes; otherwise they are written back to smem (same slots this thread read).
-template <int K, int P, int NPOLY, class Loader>
+// CL = 2: `smem` is this CTA's half, `t` the thread index within the POLYNOMIAL (rank * T/2 + threadIdx.x).
+template <int K, int P, int NPOLY, class Loader, int CL = 1>
 __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                              Loader &load)
 {
+    static_assert(CL == 1 || (CL == 2 && NPOLY == 1 && K == SEB_NTT_KEY32(14)), "cluster form: plan {5,5,4} at n = 16384");
     constexpr int LOGN  = NttCfg<K>::LOGN;
     constexpr int E     = NttCfg<K>::E;
     constexpr int R     = NttPlan<K>::R[P];
@@ -355,12 +396,16 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E],
     constexpr bool LAST = (P == NttPlan<K>::NPASS - 1);
 
     constexpr uint32_t WORDS = NttSmem<K>::WORDS;
+    constexpr uint32_t HALF  = 1u << (LOGN - 1);
+    // CL = 2: this CTA's shared memory starts at coefficient rank * n/2 (seb_pad is additive over disjoint bit fields)
+    const uint32_t rank = CL == 2 ? (uint32_t)t / (uint32_t)(NttCfg<K>::T / 2) : 0u;
+    uint32_t *own       = CL == 2 ? smem - (rank ? seb_pad<K>(HALF) : 0u) : smem;
 #pragma unroll
     for (int i = 0; i < GP; i++)
     {
         const uint32_t blk  = seb_ntt_group<K, P>((uint32_t)t, (uint32_t)i) >> LS;
         const uint32_t base = seb_ntt_group_base<K, P>((uint32_t)t, (uint32_t)i);
-        uint32_t *sp        = smem + seb_pad<K>(base);  // element j lives at sp[seb_pad(j << LS)]
+        uint32_t *sp        = own + seb_pad<K>(base);  // element j lives at sp[seb_pad(j << LS)]
         if (P == 0)
         {
 #pragma unroll
@@ -392,7 +437,24 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E],
                     x[p][i * (1 << R) + j] = sp[p * WORDS + seb_pad<K>((uint32_t)j << LS)];
         }
         seb_radix_regs<R, NPOLY, E>(x, i * (1 << R), tw + NttTw<K, P>::OFF + blk, NttTw<K, P>::NB, q, two_q);
-        if (!LAST)
+        if constexpr (!LAST && CL == 2 && P == 0)
+        {
+            // elements with the top index bit clear belong to rank 0's half, the others to rank 1's
+            static_assert(LS + R == LOGN, "pass 0 of the cluster form spans the polynomial");
+            const uint32_t a0 = seb_cluster_map(smem, 0u) + 4u * seb_pad<K>(base);
+            const uint32_t a1 = seb_cluster_map(smem, 1u) + 4u * seb_pad<K>(base);
+            seb_cluster_wait();  // the partner CTA is running (arrive: at kernel entry): its shared memory may be written
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++)
+            {
+                const uint32_t idx = (uint32_t)j << LS;
+                if (idx < HALF)
+                    seb_cluster_st(a0 + 4u * seb_pad<K>(idx), x[0][i * (1 << R) + j]);
+                else
+                    seb_cluster_st(a1 + 4u * seb_pad<K>(idx - HALF), x[0][i * (1 << R) + j]);
+            }
+        }
+        else if constexpr (!LAST)
         {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++)
@@ -403,20 +465,54 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E],
     }
 }
 
-template <int K, int P, int NPOLY, class Loader>
+template <int K, int P, int NPOLY, class Loader, int CL = 1>
 struct SebNttRun
 {
     __device__ __forceinline__ static void run(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                                const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                                Loader &load)
     {
-        seb_ntt_pass<K, P, NPOLY>(x, smem, t, tw, q, two_q, load);
+        seb_ntt_pass<K, P, NPOLY, Loader, CL>(x, smem, t, tw, q, two_q, load);
         if (P + 1 < NttPlan<K>::NPASS)
         {
-            seb_ntt_sync<NttSync<K, P>::value, NttSync<K, P>::GROUP, NttCfg<K>::T>(t);
-            SebNttRun<K, (P + 1 < NttPlan<K>::NPASS ? P + 1 : P), NPOLY, Loader>::run(x, smem, t, tw, q, two_q, load);
+            if (CL == 2 && P == 0)
+            {
+                // publishes both CTAs' pass-0 stores (release / acquire at cluster scope)
+                seb_cluster_arrive();
+                seb_cluster_wait();
+            }
+            else
+                seb_ntt_sync<NttSync<K, P>::value, NttSync<K, P>::GROUP, NttCfg<K>::T>(t);
+            SebNttRun<K, (P + 1 < NttPlan<K>::NPASS ? P + 1 : P), NPOLY, Loader, CL>::run(x, smem, t, tw, q, two_q, load);
         }
     }
+};
+
+// The cluster form of seb_ntt_forward: called by all T/2 threads of BOTH CTAs of a 2-CTA cluster with
+// t = cluster rank * T/2 + threadIdx.x and `smem` = NttSmem<K>::WORDS / 2 (+ padding slack) words of the CTA's own
+// shared memory.  The caller must have executed seb_cluster_arrive() once at kernel entry.
+template <int K, class Loader>
+__device__ __forceinline__ void seb_ntt_forward_cluster2(uint32_t (&x)[1][NttCfg<K>::E], uint32_t *smem, const int t,
+                                                         const seb_oct *__restrict__ tw, const uint32_t q,
+                                                         const uint32_t two_q, Loader &load)
+{
+    SebNttRun<K, 0, 1, Loader, 2>::run(x, smem, t, tw, q, two_q, load);
+}
+#ifdef __CUDACC__
+// thread index within the polynomial and the entry protocol of a kernel that may run in cluster form
+template <int K, int CL>
+__device__ __forceinline__ int seb_ntt_thread()
+{
+    if (CL == 1) return (int)threadIdx.x;
+    seb_cluster_arrive_relaxed();  // "this CTA runs": paired with the wait in front of pass 0's remote stores
+    return (int)seb_cluster_rank() * (NttCfg<K>::T / 2) + (int)threadIdx.x;
+}
+#endif
+// words of shared memory one CTA of the pair needs
+template <int K>
+struct NttSmemHalf
+{
+    static constexpr uint32_t WORDS = (seb_pad<K>((1u << (NttCfg<K>::LOGN - 1)) - 1u) + 4u) & ~3u;
 };
 
 // Full forward NTT of NPOLY polynomials sharing one modulus, executed by the T = n/E threads
@@ -440,21 +536,27 @@ struct SebNoLoad
 {
     __device__ __forceinline__ uint32_t operator()(int, uint32_t) const { return 0u; }
 };
-template <int K, int NPOLY, class Loader>
+template <int K, int NPOLY, class Loader, int CL = 1>
 __device__ __forceinline__ void seb_ntt_first(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                               const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q,
                                               Loader &load)
 {
-    seb_ntt_pass<K, 0, NPOLY>(x, smem, t, tw, q, two_q, load);
-    __syncthreads();
+    seb_ntt_pass<K, 0, NPOLY, Loader, CL>(x, smem, t, tw, q, two_q, load);
+    if (CL == 2)
+    {
+        seb_cluster_arrive();
+        seb_cluster_wait();
+    }
+    else
+        __syncthreads();
 }
-template <int K, int NPOLY>
+template <int K, int NPOLY, int CL = 1>
 __device__ __forceinline__ void seb_ntt_rest(uint32_t (&x)[NPOLY][NttCfg<K>::E], uint32_t *smem, const int t,
                                              const seb_oct *__restrict__ tw, const uint32_t q, const uint32_t two_q)
 {
     static_assert(NttPlan<K>::NPASS >= 2, "plan with a single pass");
     SebNoLoad none;
-    SebNttRun<K, 1, NPOLY, SebNoLoad>::run(x, smem, t, tw, q, two_q, none);
+    SebNttRun<K, 1, NPOLY, SebNoLoad, CL>::run(x, smem, t, tw, q, two_q, none);
 }
 
 template <int K>

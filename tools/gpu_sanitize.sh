@@ -5,7 +5,7 @@
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-SEL="test_ntt or test_encode or test_encrypt_asym or test_encrypt_sym or test_samplers or test_sampler_uniform or test_decrypt"
+SEL="test_ntt or test_encode or test_encrypt_asym or test_encrypt_sym or test_samplers or test_sampler_uniform or test_decrypt or test_gen_public_key"
 for tool in memcheck racecheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" \
       > $OUT/sanitizer_$tool.log 2>&1

@@ -17,6 +17,35 @@ struct LoadPlain
     __device__ __forceinline__ uint32_t operator()(int, uint32_t pos) const { return seb_ldg_stream(src + pos); }
 };
 
+// the 2-CTA cluster form of plan 30 (n = 16384, 32 coefficients per thread): 256-thread CTAs
+template <int LOGN, int MINB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<LOGN>::T / 2, MINB)
+    k_ntt_c2(uint32_t *__restrict__ polys, const seb_oct *__restrict__ roots, uint32_t q)
+{
+    constexpr int N = 1 << NttCfg<LOGN>::LOGN;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t        = seb_ntt_thread<LOGN, 2>();
+    uint32_t *data     = polys + (size_t)(blockIdx.x >> 1) * N;
+    const uint32_t two_q = 2 * q;
+    uint32_t x[1][NttCfg<LOGN>::E];
+    LoadPlain ld{data};
+    seb_ntt_forward_cluster2<LOGN>(x, smem, t, roots, q, two_q, ld);
+    using O = NttOut<LOGN>;
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+    {
+        seb_oct *dst = reinterpret_cast<seb_oct *>(data + O::pos(t, i));
+#pragma unroll
+        for (int k = 0; k < O::RUN / 8; k++)
+        {
+            seb_oct v;
+#pragma unroll
+            for (int c = 0; c < 8; c++) v.v[c] = seb_final_reduce(x[0][i * O::RUN + 8 * k + c], q, two_q);
+            seb_stg256_stream(dst + k, v);
+        }
+    }
+}
+
 template <int LOGN, int MINB>
 __global__ void __launch_bounds__(NttCfg<LOGN>::T, MINB)
     k_ntt(uint32_t *__restrict__ polys, const seb_oct *__restrict__ roots, uint32_t q)
@@ -85,6 +114,39 @@ static void run(uint32_t *d_polys, const uint32_t *d_init, size_t npoly, const s
            (unsigned long long)dg);
 }
 
+template <int LOGN, int MINB>
+static void run_c2(uint32_t *d_polys, const uint32_t *d_init, size_t npoly, const seb_oct *d_tw, uint32_t q, double peak)
+{
+    constexpr int N = 1 << NttCfg<LOGN>::LOGN;
+    const size_t smem = 4 * NttSmemHalf<LOGN>::WORDS;
+    CK(cudaFuncSetAttribute(k_ntt_c2<LOGN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_ntt_c2<LOGN, MINB>);
+    CK(cudaMemcpy(d_polys, d_init, npoly * N * 4, cudaMemcpyDeviceToDevice));
+    for (int i = 0; i < 2; i++) k_ntt_c2<LOGN, MINB><<<(unsigned)(2 * npoly), NttCfg<LOGN>::T / 2, smem>>>(d_polys, d_tw, q);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int i = 0; i < reps; i++) k_ntt_c2<LOGN, MINB><<<(unsigned)(2 * npoly), NttCfg<LOGN>::T / 2, smem>>>(d_polys, d_tw, q);
+    cudaEventRecord(e1);
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= reps;
+    const double gbs = 8.0 * N * npoly / (ms * 1e-3) / 1e9;
+    CK(cudaMemcpy(d_polys, d_init, (size_t)N * 4, cudaMemcpyDeviceToDevice));
+    k_ntt_c2<LOGN, MINB><<<2, NttCfg<LOGN>::T / 2, smem>>>(d_polys, d_tw, q);
+    std::vector<uint32_t> h(N);
+    CK(cudaMemcpy(h.data(), d_polys, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    uint64_t dg = 1469598103934665603ULL;
+    for (uint32_t v : h) dg = (dg ^ v) * 1099511628211ULL;
+    printf("n=%5d E=%d 2-CTA cluster minb=%d regs=%3d spill=%zu: %.3f ms  %.0f GB/s  %.1f%% of %.0f  digest %016llx\n", N,
+           NttCfg<LOGN>::E, MINB, fa.numRegs, (size_t)fa.localSizeBytes, ms, gbs, 100 * gbs / peak, peak, (unsigned long long)dg);
+}
+
 template <int LOGN>
 static seb_oct *make_tw(uint32_t q)
 {
@@ -135,6 +197,7 @@ int main(int argc, char **argv)
     SWEEP(13, R(13, 1) R(13, 2) R(13, 3) R(13, 4))
     SWEEP(29, R(29, 1) R(29, 2) R(29, 3) R(29, 4) R(29, 5))
     SWEEP(14, R(14, 1) R(14, 2))
-    SWEEP(30, R(30, 1) R(30, 2))
+    SWEEP(30, R(30, 1) R(30, 2) run_c2<30, 2>(d_polys, d_init, npoly, d_tw, q, peak); run_c2<30, 3>(d_polys, d_init, npoly, d_tw, q, peak);
+              run_c2<30, 4>(d_polys, d_init, npoly, d_tw, q, peak);)
     return 0;
 }
