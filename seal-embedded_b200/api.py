@@ -100,7 +100,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    # SEB_LIBRARY_PATH: load another build of the same library (A/B measurements of compile-time variants)
+    p = path or os.environ.get("SEB_LIBRARY_PATH") or LIB_PATH
     if not os.path.exists(p):
         raise SebError(f"{p} is missing: build it with `python seal-embedded_b200/build.py` "
                        "(the CUDA extension is the only implementation; there is no CPU path)")

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
     constexpr int T     = NL / ENC_E;
     constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
     constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
-    extern __shared__ double esm[];
+    extern __shared__ __align__(16) double esm[];
     double *sre   = esm;
     double *sim   = esm + NL;
     float *svals  = reinterpret_cast<float *>(esm + 2 * NL);  // the message, zero padded, skewed (enc_vskew)
@@ -99,8 +99,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
             for (int j = 0; j < (1 << RL); j++)
             {
                 const uint32_t pos = base | ((uint32_t)j << LSL);
-                sre[enc_swz(pos)]  = xr[i * (1 << RL) + j];
-                sim[enc_swz(pos)]  = xi[i * (1 << RL) + j];
+                enc_st(sre, sim, pos, xr[i * (1 << RL) + j], xi[i * (1 << RL) + j]);
             }
         }
         cluster.sync();
@@ -109,8 +108,10 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
         const double2 s   = __ldg(tw + 1);
         for (uint32_t k = t; k < (uint32_t)NL; k += T)
         {
-            const uint32_t sk = enc_swz(k);
-            const double re = enc_cross_re(rank, sre[sk], sim[sk], ore[sk], rank ? oim[sk] : 0.0, s);
+            double ar, ai, br, bi;
+            enc_ld(sre, sim, k, ar, ai);
+            enc_ld(ore, oim, k, br, bi);
+            const double re = enc_cross_re(rank, ar, ai, br, bi, s);
             dst[pos0 + k] = enc_finish(re, n_inv, bad, mx);
         }
         cluster.sync();  // partner may still be reading our shared memory

@@ -17,10 +17,43 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 __host__ __device__ constexpr int enc_npass(int lognl) { return (lognl + 2) / 3; }
 __host__ __device__ constexpr int enc_r(int lognl, int p) { return (lognl - 3 * p) >= 3 ? 3 : (lognl - 3 * p); }
 
-// bank swizzle for the double-precision re[]/im[] arrays (index in elements)
+// The complex vector in shared memory: two arrays of doubles, re[] and im[], with an XOR swizzle (ENC_C2 = 0, the
+// product).  ENC_C2 = 1 is the measured alternative: ONE array of (re, im) pairs read and written with 128-bit accesses
+// (half the shared-memory instructions; swizzle i ^ ((i >> 3) & 7)) - no faster at n = 4096 (1.782 vs 1.789 ms per 65536
+// messages) and slower above (2.51 vs 2.45 ms at n = 8192, 4.15 vs 3.35 ms at n = 16384): profiles/README.md, round 2.
+#ifndef ENC_C2
+#define ENC_C2 0
+#endif
 __device__ __forceinline__ uint32_t enc_swz(uint32_t i)
 {
+#if ENC_C2
+    return i ^ ((i >> 3) & 7u);
+#else
     return i ^ ((i >> 4) & 7u) ^ (((i >> 6) & 1u) << 3);
+#endif
+}
+// element `pos` of the vector whose storage starts at sre (ENC_C2: 2*NL doubles as NL pairs; else sre[NL], sim[NL])
+__device__ __forceinline__ void enc_ld(const double *sre, const double *sim, uint32_t pos, double &re, double &im)
+{
+#if ENC_C2
+    (void)sim;
+    const double2 v = reinterpret_cast<const double2 *>(sre)[enc_swz(pos)];
+    re = v.x;
+    im = v.y;
+#else
+    re = sre[enc_swz(pos)];
+    im = sim[enc_swz(pos)];
+#endif
+}
+__device__ __forceinline__ void enc_st(double *sre, double *sim, uint32_t pos, double re, double im)
+{
+#if ENC_C2
+    (void)sim;
+    reinterpret_cast<double2 *>(sre)[enc_swz(pos)] = make_double2(re, im);
+#else
+    sre[enc_swz(pos)] = re;
+    sim[enc_swz(pos)] = im;
+#endif
 }
 
 // Layout of the staged message in shared memory.  Pass 0 gathers values[src_map[pos]] for 8 consecutive
@@ -104,9 +137,8 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
 #pragma unroll
             for (int j = 0; j < (1 << R); j++)
             {
-                const uint32_t pos   = base | ((uint32_t)j << LS);
-                xr[i * (1 << R) + j] = sre[enc_swz(pos)];
-                xi[i * (1 << R) + j] = sim[enc_swz(pos)];
+                const uint32_t pos = base | ((uint32_t)j << LS);
+                enc_ld(sre, sim, pos, xr[i * (1 << R) + j], xi[i * (1 << R) + j]);
             }
         }
 #pragma unroll
@@ -142,8 +174,7 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
             for (int j = 0; j < (1 << R); j++)
             {
                 const uint32_t pos = base | ((uint32_t)j << LS);
-                sre[enc_swz(pos)]  = xr[i * (1 << R) + j];
-                sim[enc_swz(pos)]  = xi[i * (1 << R) + j];
+                enc_st(sre, sim, pos, xr[i * (1 << R) + j], xi[i * (1 << R) + j]);
             }
         }
     }

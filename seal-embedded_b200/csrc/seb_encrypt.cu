@@ -194,10 +194,13 @@ __device__ __forceinline__ void asym_store8(const uint32_t (&xu)[8], const uint3
     seb_stg256_stream(reinterpret_cast<seb_oct *>(c1 + pos), v1);
 }
 
+#ifndef SEB_ASYM12_MINB
+#define SEB_ASYM12_MINB 3
+#endif
 // Three polynomials at once (registers permitting): every twiddle fetched once for all three.
 template <int LOGN>
 __global__ void __launch_bounds__((1 << LOGN) / SEB_E,
-                                  (LOGN == 10 ? 12 : LOGN == 11 ? 6 : LOGN == 12 ? 3 : LOGN == 13 ? 2 : 1))
+                                  (LOGN == 10 ? 12 : LOGN == 11 ? 6 : LOGN == 12 ? SEB_ASYM12_MINB : LOGN == 13 ? 2 : 1))
     k_encrypt_asym(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
                    const uint8_t *__restrict__ u,
                    const seb_oct *__restrict__ roots, const seb_oct *__restrict__ pk0s,

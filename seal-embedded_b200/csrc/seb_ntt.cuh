@@ -44,6 +44,12 @@ struct NttCfg
 #define SEB_E 16  // the default (and the only value the three-polynomial asymmetric kernel uses)
 #define SEB_NTT_KEY32(logn) (16 + (logn))
 
+// Three polynomials per CTA (the asymmetric kernel): fetch a pass' roots stage by stage (at most two octs live) instead of
+// all at once (four octs = 32 registers beside the 48 coefficient registers) - A/B switch, see profiles/README.md
+#ifndef SEB_STAGED_TW_NPOLY3
+#define SEB_STAGED_TW_NPOLY3 0
+#endif
+
 // How a twiddle oct is fetched: a 256-bit read-only global load of the L1/L2-resident table.  (tools/ubench/
 // ubench_ntt_tma.cu overrides it to measure a table staged in shared memory by cp.async.bulk.)
 #ifndef SEB_TW_LOAD
@@ -239,7 +245,7 @@ __device__ __forceinline__ void seb_radix_regs(uint32_t (&x)[NPOLY][E], const in
                                                const uint32_t two_q)
 {
     constexpr int NOCT = (1 << R) / 4;
-    if constexpr (R <= 4)
+    if constexpr (R <= 4 && !(SEB_STAGED_TW_NPOLY3 && NPOLY >= 3))
     {
         seb_oct w[NOCT];
 #pragma unroll

@@ -145,6 +145,158 @@ __global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// the same sampler, TWO ciphertexts per warp sharing the last wave (n = 4096)
+// ---------------------------------------------------------------------------------------------
+// At n = 4096 a ciphertext consumes 43 blocks + 32.25 +- 5.7 redraws = 75 PRNG counters: three waves of 32 compute 96
+// permutations for it, and the kernel is ALU-pipe bound (95 %), so a fifth of its time is spent on counters nobody
+// reads.  Here a warp owns ciphertexts 2w and 2w+1: two full waves each (counters 0..63), then ONE wave shared by
+// both from counter 64, its lanes split by what each still owes; whoever is not done afterwards gets full waves
+// of its own.  ~2.55 waves per ciphertext instead of 3.  Same walk, same bytes, same counters as k_sample_ternary.
+struct SebTernWalk
+{
+    int j = 0;      // next block index
+    int need = 0;   // redraws still owed to the current block
+    int cur = 0;    // current block index
+    uint32_t cm0 = 0, cm1 = 0, cm2 = 0;  // unresolved rejected positions of the current block
+    uint32_t consumed = 0;
+};
+
+// walk the counters held by lanes [lo, hi) of this wave, in order (the loop body of k_sample_ternary)
+__device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, const int hi, const int lane, const int n,
+                                              const int nblocks, uint32_t *usm, const uint32_t (&packed)[6],
+                                              const uint32_t m0, const uint32_t m1, const uint32_t m2, const uint32_t b0)
+{
+    uint8_t *usm8 = reinterpret_cast<uint8_t *>(usm);
+    for (int i = lo; i < hi; i++)
+    {
+        if (w.need > 0)
+        {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, b0, i);
+            if (v < 0xFEu)
+            {
+                int pos;
+                if (w.cm0)
+                {
+                    pos = __ffs(w.cm0) - 1;
+                    w.cm0 &= w.cm0 - 1;
+                }
+                else if (w.cm1)
+                {
+                    pos = 32 + __ffs(w.cm1) - 1;
+                    w.cm1 &= w.cm1 - 1;
+                }
+                else
+                {
+                    pos = 64 + __ffs(w.cm2) - 1;
+                    w.cm2 &= w.cm2 - 1;
+                }
+                if (lane == 0) usm8[w.cur * 24 + (pos >> 2)] |= (uint8_t)((v % 3u) << (6 - 2 * (pos & 3)));
+                w.need--;
+            }
+        }
+        else if (w.j < nblocks)
+        {
+            const int valid = min(96, n - 96 * w.j);  // multiple of 32 for every legal n
+            if (lane == i)
+            {
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    if (k * 16 < valid) usm[w.j * 6 + k] = packed[k];
+            }
+            w.cm0  = __shfl_sync(0xFFFFFFFFu, m0, i);
+            w.cm1  = valid > 32 ? __shfl_sync(0xFFFFFFFFu, m1, i) : 0u;
+            w.cm2  = valid > 64 ? __shfl_sync(0xFFFFFFFFu, m2, i) : 0u;
+            w.need = __popc(w.cm0) + __popc(w.cm1) + __popc(w.cm2);
+            w.cur  = w.j;
+            w.j++;
+            __syncwarp();
+        }
+        else
+            break;
+        w.consumed++;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sample_ternary_pair(const uint8_t *__restrict__ seeds, uint8_t *__restrict__ u_out,
+                                                             uint32_t *__restrict__ ctr_out, int n, int batch)
+{
+    extern __shared__ uint32_t usm_all[];
+    const int lane      = threadIdx.x & 31;
+    const int warp      = threadIdx.x >> 5;
+    const int pair      = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int words_per = n / 16;  // n/4 bytes
+    if (2 * pair >= batch) return;
+    const int nct       = 2 * pair + 1 < batch ? 2 : 1;  // an odd batch leaves the last warp one ciphertext
+    const int nblocks   = (n + 95) / 96;
+    uint32_t *usm0      = usm_all + (2 * warp) * words_per, *usm1 = usm0 + words_per;
+    SebTernWalk w0, w1;  // two named states, no run-time indexed array: they stay in registers
+
+    // The schedule is a loop with ONE instance of the wave body (Keccak + block extraction + walk): four inlined
+    // copies fell out of the instruction cache and ran 25 % slower than the unpaired kernel.
+    // A wave serves ciphertext c0 on lanes [0, split) from counter base0 and ciphertext c1 on lanes [split, 32) from base1.
+    constexpr uint32_t FULL = 64;  // counters every ciphertext gets from full waves of its own
+    uint32_t next0 = 0, next1 = 0;  // next counter of each ciphertext
+    bool tail_done = nct == 1;
+    uint64_t seed[8];
+    int seed_of = -1;  // whose seed this lane holds
+    for (;;)
+    {
+        const bool open0 = w0.j < nblocks || w0.need > 0;
+        const bool open1 = nct == 2 && (w1.j < nblocks || w1.need > 0);
+        int first, split;  // ciphertext on lanes [0, split); lanes [split, 32) serve the other one
+        if (open0 && (next0 < FULL || tail_done))
+            first = 0, split = 32;
+        else if (open1 && (next1 < FULL || tail_done))
+            first = 1, split = 32;
+        else if (!tail_done && (open0 || open1))
+        {
+            // The shared wave.  What each ciphertext still owes is known up to the redraws to come: blocks left + redraws
+            // owed now + 3/4 redraw per block left (96 bytes x 2/256) + 1; the spare lanes are split evenly.  If the two
+            // estimates do not fit 32 lanes the wave is cut in the middle.
+            const int rem0 = nblocks - w0.j, rem1 = nblocks - w1.j;
+            const int est0 = open0 ? rem0 + w0.need + (3 * rem0 + 3) / 4 + 1 : 0;
+            const int est1 = open1 ? rem1 + w1.need + (3 * rem1 + 3) / 4 + 1 : 0;
+            split          = est0 + est1 <= 32 ? est0 + (32 - est0 - est1) / 2 : 16;
+            first = 0, tail_done = true;
+        }
+        else
+            break;
+        const int mine       = lane < split ? first : 1;
+        const uint32_t count = (mine ? next1 : next0) + (uint32_t)(lane < split ? lane : lane - split);
+        uint64_t a[25];
+        if (seed_of != mine)  // only the lanes that change ciphertext reload (L1-resident 64 bytes)
+        {
+            load_seed(seeds, (size_t)(2 * pair + mine), seed);
+            seed_of = mine;
+        }
+        seb_prng_init(a, seed, (uint64_t)count);
+        seb_keccak_f1600<12>(a);  // 96 bytes (or 1) are read from each call
+        uint32_t m0, m1, m2, packed[6];
+        seb_ternary_block(a, packed, m0, m1, m2);
+        const uint32_t b0 = (uint32_t)a[0] & 0xFFu;  // value if this counter was a 1-byte redraw
+        if (first == 0)
+        {
+            seb_tern_walk(w0, 0, split, lane, n, nblocks, usm0, packed, m0, m1, m2, b0);
+            next0 += (uint32_t)split;
+        }
+        if (first == 1 || split < 32)
+        {
+            seb_tern_walk(w1, first == 1 ? 0 : split, 32, lane, n, nblocks, usm1, packed, m0, m1, m2, b0);
+            next1 += (uint32_t)(first == 1 ? 32 : 32 - split);
+        }
+    }
+
+    __syncwarp();
+    for (int c = 0; c < nct; c++)
+    {
+        uint32_t *dst       = reinterpret_cast<uint32_t *>(u_out + (size_t)(2 * pair + c) * (n / 4));
+        const uint32_t *src = c ? usm1 : usm0;
+        for (int k = lane; k < words_per; k += 32) dst[k] = src[k];
+        if (lane == 0) ctr_out[2 * pair + c] = c ? w1.consumed : w0.consumed;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // centered binomial (k=21): one thread per 96-byte PRNG call = 16 samples
 // ---------------------------------------------------------------------------------------------
 // e_out: [batch][npoly][n] int8; polynomial k of ciphertext b uses counters
@@ -794,6 +946,14 @@ void seb_launch_sample_ternary(const uint8_t *seeds, uint8_t *u_out, uint32_t *c
 {
     if (batch <= 0) return;
     const int warps = 4;
+    if (n == 4096 && batch >= 2)
+    {
+        // two ciphertexts per warp sharing their third wave (the degree where a third of the last wave is unused)
+        const int pairs = (batch + 1) / 2;
+        k_sample_ternary_pair<<<(pairs + warps - 1) / warps, warps * 32, (size_t)2 * warps * (n / 4), st>>>(seeds, u_out, ctr_out, n,
+                                                                                                       batch);
+        return;
+    }
     const size_t sm = (size_t)warps * (n / 4);
     k_sample_ternary<<<(batch + warps - 1) / warps, warps * 32, sm, st>>>(seeds, u_out, ctr_out, n, batch);
 }

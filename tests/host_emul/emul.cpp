@@ -233,15 +233,16 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
     constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
     int bad             = 0;
     g_emul_mag          = 0;
-    std::vector<double> sre[2], sim[2];
+    std::vector<double> sre[2];  // 2*NL doubles per CTA, like the kernel's shared memory: re[NL] im[NL] or NL (re, im) pairs
     std::vector<float> svals(EncVals<LOGN>::WORDS, 0.0f);  // the kernel's staged, zero-padded, skewed message
     for (int i = 0; i < vlen && i < N / 2; i++) svals[enc_vskew<LOGN>((uint32_t)i)] = vals[i];
     for (int rank = 0; rank < CL; rank++)
     {
-        sre[rank].assign(NL, 1e300);
-        sim[rank].assign(NL, 1e300);
+        sre[rank].assign(2 * NL + 2, 1e300);
+        double *re0 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sre[rank].data()) + 15) & ~uintptr_t(15));
+        double *im0 = re0 + NL;
         std::vector<std::array<double, 2 * ENC_E>> regs(T);
-        enc_passes<LOGN, LOGNL, 0>(regs, sre[rank].data(), sim[rank].data(), rank * NL, svals.data(), src_map, tw);
+        enc_passes<LOGN, LOGNL, 0>(regs, re0, im0, rank * NL, svals.data(), src_map, tw);
         for (int t = 0; t < T; t++)
             for (int i = 0; i < (ENC_E >> RL); i++)
             {
@@ -254,10 +255,7 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
                     if (CL == 1)
                         out[pos] = enc_finish(regs[t][i * (1 << RL) + j], n_inv, bad, g_emul_mag);
                     else
-                    {
-                        sre[rank][enc_swz(pos)] = regs[t][i * (1 << RL) + j];
-                        sim[rank][enc_swz(pos)] = regs[t][ENC_E + i * (1 << RL) + j];
-                    }
+                        enc_st(re0, im0, pos, regs[t][i * (1 << RL) + j], regs[t][ENC_E + i * (1 << RL) + j]);
                 }
             }
     }
@@ -265,9 +263,13 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
         for (uint32_t rank = 0; rank < 2; rank++)
             for (uint32_t k = 0; k < (uint32_t)NL; k++)
             {
-                const uint32_t sk = enc_swz(k);
-                const double re   = enc_cross_re(rank, sre[rank][sk], sim[rank][sk], sre[rank ^ 1][sk],
-                                                 sim[rank ^ 1][sk], tw[1]);
+                auto base = [&](uint32_t r) {
+                    return reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sre[r].data()) + 15) & ~uintptr_t(15));
+                };
+                double ar, ai, br, bi;
+                enc_ld(base(rank), base(rank) + NL, k, ar, ai);
+                enc_ld(base(rank ^ 1), base(rank ^ 1) + NL, k, br, bi);
+                const double re    = enc_cross_re(rank, ar, ai, br, bi, tw[1]);
                 out[rank * NL + k] = enc_finish(re, n_inv, bad, g_emul_mag);
             }
     return bad;

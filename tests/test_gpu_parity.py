@@ -136,6 +136,30 @@ def test_samplers_asym(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert np.array_equal(e[b, 0], e0) and np.array_equal(e[b, 1], e1), (n, b)
 
 
+@pytest.mark.parametrize("batch", [1, 2, 7, 601])
+def test_sampler_ternary_paired_warps(batch, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """n = 4096 runs the ternary sampler with TWO ciphertexts per warp sharing their third wave of PRNG counters
+    (k_sample_ternary_pair): lone / odd batches leave a warp with one ciphertext, and over 601 items every branch is taken
+    — ciphertexts done inside the shared wave (counter < 80), ciphertexts that need further waves of their own (the
+    counter after u is checked to cover both).  Packed u and the PRNG counter equal sample.c:218-242 item by item."""
+    torch = torch_cuda
+    n, np_ = 4096, 3
+    ctx = ctxs(n, np_, True)
+    seeds = oracle_mod.make_seeds(batch, b"ternary-pair-%d" % batch)
+    d_u = torch.zeros(batch * n // 4, dtype=torch.uint8, device="cuda")
+    d_e = torch.zeros(batch * 2 * n, dtype=torch.int8, device="cuda")
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    ctx.sample_asym_device(dev(torch, seeds), batch, d_u, d_e, d_ctr)
+    torch.cuda.synchronize()
+    u = d_u.cpu().numpy().reshape(batch, n // 4)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        eu, c = orc.sample_ternary_small(n, seeds[b])
+        assert ctr[b] == c and np.array_equal(u[b], eu), (batch, b, ctr[b], c)
+    if batch > 500:
+        assert ctr.min() < 80 <= ctr.max()  # both kinds of ciphertext occurred
+
+
 @pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("coop", ["0", "1"])
 @pytest.mark.parametrize("n,np_", CONFIGS)
