@@ -10,7 +10,7 @@
 //     complex multiplication on x86-64 without -ffast-math;
 //   * twiddles are the host libm's cos/sin (table built once in seb_api.cu with the reference's own
 //     expression, fft.c:27-45), not CUDA's;
-//   * radix-8 passes are three fused radix-2 stages, never a re-associated butterfly;
+//   * radix-16 passes are four fused radix-2 stages (radix-8 / three with ENC_E = 8), never a re-associated butterfly;
 //   * C round() (half away from zero) and the x86 cvttsd2si result for out-of-range values.
 #include <cooperative_groups.h>
 
@@ -22,11 +22,17 @@ namespace cg = cooperative_groups;
 
 // resident CTAs per SM the kernel is compiled for: 64 registers per thread at every degree (two
 // 512-thread CTAs per SM for n = 4096)
+#ifndef ENC_THREADS_PER_SM
+#define ENC_THREADS_PER_SM (ENC_E == 16 ? 512 : 1024)
+#endif
 template <int LOGN, int CL>
 struct EncOcc
 {
     static constexpr int T    = (1 << LOGN) / CL / ENC_E;
-    static constexpr int MINB = T >= 1024 ? 1 : 1024 / T;
+    // 8 values per thread: 64 registers, 1024 threads per SM; 16 per thread: 128 registers, 512 threads per SM
+    // (ENC_THREADS_PER_SM: A/B switch)
+    static constexpr int TPS  = ENC_THREADS_PER_SM;
+    static constexpr int MINB = T >= TPS ? 1 : TPS / T;
 };
 
 template <int LOGN, int CL>
@@ -40,7 +46,7 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
     constexpr int LOGNL = (CL == 2) ? LOGN - 1 : LOGN;
     constexpr int T     = NL / ENC_E;
     constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
-    constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
+    constexpr int LSL   = ENC_LR * (enc_npass(LOGNL) - 1);
     extern __shared__ __align__(16) double esm[];
     double *sre   = esm;
     double *sim   = esm + NL;

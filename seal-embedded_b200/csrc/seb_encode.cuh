@@ -12,10 +12,16 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 #endif
 
-#define ENC_E 8  // complex values per thread
+// complex values per thread: 8 (radix-8 passes of three fused radix-2 stages) or 16 (radix-16 passes of four: one
+// shared-memory round trip fewer at n >= 2048; a compile-time choice for the whole library, see profiles/README.md)
+#ifndef ENC_E
+#define ENC_E 16
+#endif
+#define ENC_LR (ENC_E == 16 ? 4 : 3)  // stages per full pass
+static_assert(ENC_E == 8 || ENC_E == 16, "ENC_E: 8 or 16 values per thread");
 
-__host__ __device__ constexpr int enc_npass(int lognl) { return (lognl + 2) / 3; }
-__host__ __device__ constexpr int enc_r(int lognl, int p) { return (lognl - 3 * p) >= 3 ? 3 : (lognl - 3 * p); }
+__host__ __device__ constexpr int enc_npass(int lognl) { return (lognl + ENC_LR - 1) / ENC_LR; }
+__host__ __device__ constexpr int enc_r(int lognl, int p) { return (lognl - ENC_LR * p) >= ENC_LR ? ENC_LR : (lognl - ENC_LR * p); }
 
 // The complex vector in shared memory: two arrays of doubles, re[] and im[], with an XOR swizzle (ENC_C2 = 0, the
 // product).  ENC_C2 = 1 is the measured alternative: ONE array of (re, im) pairs read and written with 128-bit accesses
@@ -28,6 +34,10 @@ __device__ __forceinline__ uint32_t enc_swz(uint32_t i)
 {
 #if ENC_C2
     return i ^ ((i >> 3) & 7u);
+#elif ENC_E == 16
+    // pass 0: lane l holds elements 16 l + j -> low four bits j ^ l, distinct over a half-warp; later passes: lanes on
+    // consecutive elements with (i >> 4) & 15 constant over a half-warp
+    return i ^ ((i >> 4) & 15u);
 #else
     return i ^ ((i >> 4) & 7u) ^ (((i >> 6) & 1u) << 3);
 #endif
@@ -64,7 +74,8 @@ __device__ __forceinline__ void enc_st(double *sre, double *sim, uint32_t pos, d
 template <int LOGN>
 __host__ __device__ __forceinline__ constexpr uint32_t enc_vskew(uint32_t s)
 {
-    return s + (s >> (LOGN - 9));
+    // 8 positions per thread: shift log2(n) - 9; 16 per thread: log2(n) - 10 (n = 1024: 1, two-way at worst)
+    return s + (s >> (LOGN - 6 - ENC_LR > 0 ? LOGN - 6 - ENC_LR : 1));
 }
 // floats of shared memory the staged message occupies
 template <int LOGN>
@@ -80,18 +91,19 @@ struct EncVals
 // (tw[n + slot*(n/8) + g], slot = 0..3 for r = 0, 4..5 for r = 1, 6 for r = 2) so that the lanes of a warp read
 // consecutive 16-byte entries.  Later passes share each root between >= 8 consecutive threads and use
 // the natural table.
-#define ENC_TW0_SLOTS 7
-__host__ __device__ __forceinline__ constexpr int enc_tw0_slot(int r, int m) { return r == 0 ? m : r == 1 ? 4 + m : 6; }
-// entries of the whole table: n natural + 7 * n/8 pass-0 copies
-__host__ __device__ __forceinline__ constexpr size_t enc_tw_entries(size_t n) { return n + ENC_TW0_SLOTS * (n / 8); }
+#define ENC_TW0_SLOTS (ENC_E - 1)
+// slot of root m of stage r: stage 0's E/2 roots first, then stage 1's E/4, ...
+__host__ __device__ __forceinline__ constexpr int enc_tw0_slot(int r, int m) { return ENC_E - (ENC_E >> r) + m; }
+// entries of the whole table: n natural + (E - 1) * n/E pass-0 copies
+__host__ __device__ __forceinline__ constexpr size_t enc_tw_entries(size_t n) { return n + ENC_TW0_SLOTS * (n / ENC_E); }
 template <class D2>
 inline void enc_build_tw0(size_t n, D2 *tw)  // tw[0..n) filled; appends the pass-0 copies
 {
-    const size_t G = n / 8;
+    const size_t G = n / ENC_E;
     for (size_t g = 0; g < G; g++)
-        for (int r = 0; r < 3; r++)
-            for (int m = 0; m < (1 << (2 - r)); m++)
-                tw[n + (size_t)enc_tw0_slot(r, m) * G + g] = tw[(n >> (r + 1)) + (g << (2 - r)) + m];
+        for (int r = 0; r < ENC_LR; r++)
+            for (int m = 0; m < (1 << (ENC_LR - 1 - r)); m++)
+                tw[n + (size_t)enc_tw0_slot(r, m) * G + g] = tw[(n >> (r + 1)) + (g << (ENC_LR - 1 - r)) + m];
 }
 
 // one pass = R fused Gentleman-Sande stages starting at butterfly distance S = 2^LS
@@ -106,7 +118,7 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
     constexpr int NL   = 1 << LOGNL;
     constexpr int T    = NL / ENC_E;
     constexpr int R    = enc_r(LOGNL, P);
-    constexpr int LS   = 3 * P;
+    constexpr int LS   = ENC_LR * P;
     constexpr int GP   = ENC_E >> R;
     constexpr bool LAST = (P == enc_npass(LOGNL) - 1);
 
@@ -119,17 +131,22 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
         const uint32_t base = (blk << (LS + R)) | off;  // local position of element j = 0
         if (P == 0)
         {
-            // pass 0 works on 8 consecutive positions (LS = 0, R = 3): their 8 map entries are one
-            // 128-bit load; both conjugate slots of value i receive values[i]
-            static_assert(P != 0 || (LS == 0 && R == 3), "pass 0 is expected to be radix-8 on contiguous data");
-            const uint4 mp = __ldg(reinterpret_cast<const uint4 *>(src_map + cta_pos0 + base));
-            const uint32_t mw[4] = {mp.x, mp.y, mp.z, mp.w};
+            // pass 0 works on E consecutive positions (LS = 0, R = log2 E): their map entries are one or two
+            // 128-bit loads; both conjugate slots of value i receive values[i]
+            static_assert(P != 0 || (LS == 0 && R == ENC_LR), "pass 0 is expected to be a full pass on contiguous data");
+            uint32_t mw[ENC_E / 2];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
+            for (int k = 0; k < ENC_E / 8; k++)
+            {
+                const uint4 mp = __ldg(reinterpret_cast<const uint4 *>(src_map + cta_pos0 + base) + k);
+                mw[4 * k] = mp.x, mw[4 * k + 1] = mp.y, mw[4 * k + 2] = mp.z, mw[4 * k + 3] = mp.w;
+            }
+#pragma unroll
+            for (int j = 0; j < ENC_E; j++)
             {
                 const uint32_t slot = (mw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                xr[i * 8 + j]       = (double)svals[enc_vskew<LOGN>(slot)];
-                xi[i * 8 + j]       = 0.0;
+                xr[i * ENC_E + j]   = (double)svals[enc_vskew<LOGN>(slot)];
+                xi[i * ENC_E + j]   = 0.0;
             }
         }
         else
@@ -151,8 +168,8 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
             for (int m = 0; m < (1 << (R - r - 1)); m++)
             {
                 // pass 0: this thread's own roots, from the lane-contiguous copy behind the natural table
-                const double2 s = (P == 0) ? __ldg(tw + (1u << LOGN) + (uint32_t)enc_tw0_slot(r, m) * ((1u << LOGN) / 8) +
-                                                   (cta_pos0 >> 3) + g)
+                const double2 s = (P == 0) ? __ldg(tw + (1u << LOGN) + (uint32_t)enc_tw0_slot(r, m) * ((1u << LOGN) / ENC_E) +
+                                                   (cta_pos0 >> ENC_LR) + g)
                                            : __ldg(tw + h + jbase + m);
 #pragma unroll
                 for (int k = 0; k < (1 << r); k++)
@@ -186,8 +203,11 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
 // named barrier (1 + group; CTAs of 1024 threads use groups of 128 to stay within hardware barriers 1..15).
 // Later boundaries span 512 threads or the CTA.  Returns 0 for a CTA-wide barrier, else the unit's width.
 // Checked exhaustively by tests/test_host_logic.py::test_encode_barrier_scopes.
+// With 16 values per thread: pass 1 reads what the sixteen threads 16*(t/16) .. +15 wrote (warp-local), pass 2 what
+// threads 256*(t/256) .. +255 wrote: a named barrier over 256 threads when the CTA has more, else the CTA barrier.
 __host__ __device__ __forceinline__ constexpr int enc_sync_width(int lognl, int p)
 {
+    if (ENC_E == 16) return p == 0 ? 32 : (p == 1 && ((1 << lognl) / ENC_E) > 256) ? 256 : 0;
     return p == 0 ? 32 : p == 1 ? (((1 << lognl) / ENC_E) > 960 ? 128 : 64) : 0;
 }
 template <int LOGNL, int P>

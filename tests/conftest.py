@@ -55,8 +55,10 @@ def emul():
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", csrc, "-I", cuda_inc,
-                        src, "-o", out], check=True)
+        # SEB_ENC_E=16 compiles the emulation for the encode's 16-values-per-thread variant (A/B builds)
+        extra = [f"-DENC_E={os.environ['SEB_ENC_E']}"] if os.environ.get("SEB_ENC_E") else []
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", csrc, "-I", cuda_inc] + extra +
+                       [src, "-o", out], check=True)
     return ctypes.CDLL(out)
 
 

@@ -230,7 +230,7 @@ static int enc_emul(const float *vals, int vlen, const uint16_t *src_map, const 
     constexpr int LOGNL = (CL == 2) ? LOGN - 1 : LOGN;
     constexpr int T     = NL / ENC_E;
     constexpr int RL    = enc_r(LOGNL, enc_npass(LOGNL) - 1);
-    constexpr int LSL   = 3 * (enc_npass(LOGNL) - 1);
+    constexpr int LSL   = ENC_LR * (enc_npass(LOGNL) - 1);
     int bad             = 0;
     g_emul_mag          = 0;
     std::vector<double> sre[2];  // 2*NL doubles per CTA, like the kernel's shared memory: re[NL] im[NL] or NL (re, im) pairs
@@ -300,13 +300,14 @@ extern "C" int emul_encode(int logn, const float *vals, int vlen, const uint16_t
 extern "C" int64_t emul_enc_pos(int lognl, int pass, uint32_t t, uint32_t i, uint32_t j)
 {
     if (pass >= enc_npass(lognl)) return -1;
-    const int R = enc_r(lognl, pass), LS = 3 * pass;
+    const int R = enc_r(lognl, pass), LS = ENC_LR * pass;
     const uint32_t T = (1u << lognl) / ENC_E;
     if (i >= (uint32_t)(ENC_E >> R) || j >= (1u << R) || t >= T) return -1;
     const uint32_t g = t + i * T, off = g & ((1u << LS) - 1u), blk = g >> LS;
     return (int64_t)(((blk << (LS + R)) | off) | (j << LS));
 }
 extern "C" int emul_enc_sync_width(int lognl, int pass) { return enc_sync_width(lognl, pass); }
+extern "C" int emul_enc_e(void) { return ENC_E; }
 
 // physical word of message slot s in the staged (skewed) layout, and the size of that buffer
 extern "C" uint32_t emul_enc_vskew(int logn, uint32_t slot)
