@@ -447,17 +447,27 @@ __device__ __forceinline__ void seb_ntt_pass(uint32_t (&x)[NPOLY][NttCfg<K>::E],
         {
             // elements with the top index bit clear belong to rank 0's half, the others to rank 1's
             static_assert(LS + R == LOGN, "pass 0 of the cluster form spans the polynomial");
-            const uint32_t a0 = seb_cluster_map(smem, 0u) + 4u * seb_pad<K>(base);
-            const uint32_t a1 = seb_cluster_map(smem, 1u) + 4u * seb_pad<K>(base);
+            // the partner's half first (remote stores have the longer way to go), then the own half with plain
+            // shared-memory stores
+            const uint32_t peer = seb_cluster_map(smem, rank ^ 1u) + 4u * seb_pad<K>(base);
+            uint32_t *mine      = smem + seb_pad<K>(base);
             seb_cluster_wait();  // the partner CTA is running (arrive: at kernel entry): its shared memory may be written
-#pragma unroll
-            for (int j = 0; j < (1 << R); j++)
+            if (rank == 0)
             {
-                const uint32_t idx = (uint32_t)j << LS;
-                if (idx < HALF)
-                    seb_cluster_st(a0 + 4u * seb_pad<K>(idx), x[0][i * (1 << R) + j]);
-                else
-                    seb_cluster_st(a1 + 4u * seb_pad<K>(idx - HALF), x[0][i * (1 << R) + j]);
+#pragma unroll
+                for (int j = (1 << R) / 2; j < (1 << R); j++)
+                    seb_cluster_st(peer + 4u * seb_pad<K>(((uint32_t)j << LS) - HALF), x[0][i * (1 << R) + j]);
+#pragma unroll
+                for (int j = 0; j < (1 << R) / 2; j++) mine[seb_pad<K>((uint32_t)j << LS)] = x[0][i * (1 << R) + j];
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < (1 << R) / 2; j++)
+                    seb_cluster_st(peer + 4u * seb_pad<K>((uint32_t)j << LS), x[0][i * (1 << R) + j]);
+#pragma unroll
+                for (int j = (1 << R) / 2; j < (1 << R); j++)
+                    mine[seb_pad<K>(((uint32_t)j << LS) - HALF)] = x[0][i * (1 << R) + j];
             }
         }
         else if constexpr (!LAST)
