@@ -11,7 +11,7 @@ batch is fixed).  Prints ONE JSON line (rank 0).
 
 Beside the headline (config B) the same line carries `other_configs`: BASELINE.json's configs C and D as ONE GLOBAL
 BATCH sharded over the N ranks with shard_range ("strong" scaling), B in symmetric mode, and the NTT-only sweep
-(config E: n x primes 1..8 x batch 1..2^20) per rank — each timed like the headline (barrier, CUDA events, max over
+(config E: n in {1024, 4096, 16384} x primes 1..8 x batch 1..2^20, plus n = 2048 / 8192 at their largest batch) per rank — each timed like the headline (barrier, CUDA events, max over
 ranks) — and, at N = 1, the reference's CPU path on bounded samples of A, C and D.
 """
 from __future__ import annotations
@@ -369,6 +369,24 @@ def run_ntt_sweep(seb, torch, D: Dist, stream, local: int, peak: float, cap_byte
                 e1.record(stream)
                 e1.synchronize()
                 points.append((n, np_, lb, e0.elapsed_time(e1) / reps))
+            ctx.close()
+    # the two degrees between them, at their largest batch under the cap (the plan changes at n = 8192)
+    for n in (2048, 8192):
+        for np_ in (1, 4):
+            ctx = seb.Context(n, np_, asym=False, device=local, primes=PRIMES30[:np_])
+            ctx.set_stream(stream.cuda_stream)
+            lb = 0
+            while (2 << lb) * np_ * n * 4 <= cap_bytes and lb < 20:
+                lb += 1
+            batch = 1 << lb
+            ctx.ntt_device(buf, batch)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                ctx.ntt_device(buf, batch)
+            e1.record(stream)
+            e1.synchronize()
+            points.append((n, np_, lb, e0.elapsed_time(e1) / 5))
             ctx.close()
     ms = D.max_ms([p[3] for p in points])
     out = {}

@@ -872,6 +872,66 @@ __global__ void __launch_bounds__(128) k_uniform_fix(const uint8_t *__restrict__
     seb_uniform_fix_warp(b, lane, seeds, ctr, out, ct_stride, n, mod, max_multiple, rej_idx, rej_cnt, cap);
 }
 
+// The same fix-up with L lanes per ciphertext (32/L ciphertexts per warp), for parameter sets that reject a handful of
+// words: a wave of 32 candidates per ciphertext computes 32 permutations for the ~1.5 rejections of n = 1024 under a
+// 27-bit prime - the fix-up cost as much as the whole squeeze of configuration A.  Candidates of ciphertext b are still LE32(X(seed, c0+1+t, 4)), t = 0, 1, ... in order; a group
+// draws L of them per wave and stops when its list is served.  Ciphertexts whose reject list overflowed (cnt > cap)
+// are handed, one after the other, to the scanning path of seb_uniform_fix_warp by the whole warp.
+template <int L>
+__global__ void __launch_bounds__(128) k_uniform_fix_sub(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
+                                                         uint32_t *__restrict__ out, size_t ct_stride, int n, SebModulus mod,
+                                                         uint32_t max_multiple, int batch,
+                                                         const uint16_t *__restrict__ rej_idx,
+                                                         const uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    constexpr int G   = 32 / L;  // ciphertexts per warp
+    const int lane    = threadIdx.x & 31;
+    const int group   = lane / L, sub = lane % L;
+    const int warp    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int b0      = warp * G;
+    if (b0 >= batch) return;
+    const int b       = b0 + group;
+    const bool live   = b < batch;
+    const uint32_t cnt = live ? rej_cnt[b] : 0u;
+    const bool scan    = cnt > cap;  // list overflow: the one-warp scanning path below
+    const uint32_t gmask = (L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u)) << (group * L);
+    const uint32_t below = gmask & ((1u << lane) - 1u);
+
+    uint64_t s[8];
+    load_seed(seeds, (size_t)(live ? b : b0), s);
+    const uint64_t c0    = live ? (uint64_t)ctr[b] : 0ull;
+    uint64_t wave_base   = c0 + 1;  // counter of this group's first candidate in the next wave
+    uint64_t last_used   = c0;
+    const uint32_t want  = scan ? 0u : cnt;  // rejected words this group's waves serve
+    const uint16_t *list = rej_idx + (size_t)(live ? b : b0) * cap;
+    uint32_t *row        = out + (size_t)(live ? b : b0) * ct_stride;
+    uint32_t done        = 0;
+    while (__any_sync(0xFFFFFFFFu, done < want))
+    {
+        uint64_t a[25];
+        seb_prng_init(a, s, wave_base + (uint64_t)sub);
+        seb_keccak_f1600<12>(a);  // 4 bytes per call
+        const uint32_t cand  = (uint32_t)a[0];
+        const bool ok        = done < want && cand < max_multiple;
+        const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
+        const uint32_t rank  = done + (uint32_t)__popc(avail & below);  // this candidate's turn within its ciphertext
+        const bool used      = ok && rank < want;
+        if (used) row[list[rank]] = seb_barrett32(cand, mod);
+        const uint32_t um = __ballot_sync(0xFFFFFFFFu, used) & gmask;
+        if (um) last_used = wave_base + (uint64_t)(31 - __clz(um) - group * L);
+        if (done < want) wave_base += L;
+        done += (uint32_t)__popc(um);
+    }
+    if (live && !scan && sub == 0) ctr[b] = (uint32_t)(last_used + 1);
+    // overflowed lists (never with SHAKE output and cap = n/8, but it must stay correct): whole warp, one at a time
+    const uint32_t scans = __ballot_sync(0xFFFFFFFFu, scan && sub == 0);
+    for (uint32_t m = scans; m; m &= m - 1)
+    {
+        const int g = (__ffs(m) - 1) / L;
+        seb_uniform_fix_warp(b0 + g, lane, seeds, ctr, out, ct_stride, n, mod, max_multiple, rej_idx, rej_cnt, cap);
+    }
+}
+
 // The fix-up for a handful of ciphertexts: one CTA per ciphertext, every thread one candidate, so that the ~n/50
 // candidates a polynomial needs come out of ONE round of permutations instead of n/1600 dependent 32-candidate
 // waves (10 at n = 16384: 69 us of a lone call's 85 us per prime).  Ranks are counted across the CTA (ballot per
@@ -983,8 +1043,24 @@ static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t
                                                       rej_cap);
     }
     else
-        k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
-                                                       rej_cnt, rej_cap);
+    {
+        // Lanes per ciphertext by the expected number of rejected words, n x the prime's rejection rate: 1.5 and 3 at
+        // n = 1024 / 2048 under the 27-bit prime (a wave of 32 would compute 32 permutations for them), 76 and more
+        // under 30-bit primes at n >= 4096.  A warp of G groups runs until its slowest group is served, which costs about
+        // mean + z_G sd + L/2 permutations per ciphertext: at 76 +- 9 every L lands on 91-94, so only the small
+        // expectations leave the full-warp form.  knobs.uniform_fix_lanes forces 4 / 8 / 32.
+        const double expect = (double)n * (4294967296.0 - (double)max_multiple) / 4294967296.0;
+        const int lanes     = knobs.uniform_fix_lanes > 0 ? knobs.uniform_fix_lanes : expect < 2.5 ? 4 : expect < 7.0 ? 8 : 32;
+        if (lanes == 4)
+            k_uniform_fix_sub<4><<<(batch + 31) / 32, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                                    rej_cnt, rej_cap);
+        else if (lanes == 8)
+            k_uniform_fix_sub<8><<<(batch + 15) / 16, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                                    rej_cnt, rej_cap);
+        else
+            k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                           rej_cnt, rej_cap);
+    }
 }
 
 // Speculation windows for a parameter set (host, once per context).  sigmas: half-width in standard deviations.

@@ -225,6 +225,39 @@ def test_sampler_uniform_pair_kernel(n, np_, batch, seb, torch_cuda, oracle_mod,
         assert ctr[b] == c
 
 
+@pytest.mark.parametrize("lanes", [4, 8, 32])
+@pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3)])
+def test_sampler_uniform_fixup_lanes(n, np_, lanes, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """The fix-up with 4 / 8 / 32 lanes per ciphertext (k_uniform_fix_sub / k_uniform_fix, forced with the
+    "uniform_fix_lanes" option): same polynomials and counters as sample_poly_uniform (sample.c:39-57) whether a
+    ciphertext's rejected words are served in one wave (n = 1024: ~1.5 of them) or in twenty (n = 4096 with 4 lanes),
+    for a batch that leaves the last warp partly empty."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    batch = 45
+    seeds = oracle_mod.make_seeds(batch, b"uniform-lanes-%d" % n)
+    d_seeds = dev(torch, seeds)
+    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+    ctx.set_option("uniform_fix_lanes", lanes)
+    ctx.set_option("uniform_fix_wide", 0)
+    try:
+        for p in range(np_):
+            ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_option("uniform_fix_lanes", -1)
+        ctx.set_option("uniform_fix_wide", -1)
+    out = host(d_out, np.uint32).reshape(batch, np_, n)
+    ctr = host(d_ctr, np.uint32)
+    for b in range(batch):
+        c = 0
+        for p, q in enumerate(ctx.primes):
+            exp, c = orc.sample_uniform(n, q, seeds[b], c)
+            assert np.array_equal(out[b, p], exp), (n, lanes, b, p)
+        assert ctr[b] == c
+
+
 @pytest.mark.parametrize("n,np_", CONFIGS)
 def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
     """sample.c:39-57: bulk draw, ordered redraws, counter running on across primes (ckks_sym.c:219)."""
