@@ -623,7 +623,8 @@ def run_b200_arm(args) -> None:
         "sample_cbd": 64 + 4 + 2 * n,
         "encrypt": 8 * n + 2 * n + n // 4 + 8 * n * np_,
     }
-    sym_of = {"encode": "k_encode", "sample_ternary": "k_sample_ternary", "sample_cbd": "k_sample_cbd", "encrypt": "k_encrypt_asym"}
+    sym_of = {"encode": "k_encode", "sample_ternary": "k_sample_ternary_pair" if n == 4096 else "k_sample_ternary",
+              "sample_cbd": "k_sample_cbd", "encrypt": "k_encrypt_asym"}
     # what binds each kernel and the unit its ceiling is measured in: Keccak-f/s for the samplers (ALU pipe), lazy
     # butterflies/s for the fused encrypt (FMA pipe); the encode is FP64/shared-memory bound and is only given its
     # HBM view.  Units of work per ciphertext:

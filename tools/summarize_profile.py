@@ -59,7 +59,7 @@ def launches(tag: str, rnd: str) -> None:
                 agg.setdefault(k, []).append(ns)
     # the step = the four kernels of the asymmetric full path, at the bench's grid (setup-time launches of
     # the same kernels with tiny grids — key generation, ntt(s) — and the verifier are listed but not counted)
-    hot = ("k_encode", "k_sample_ternary", "k_sample_cbd", "k_encrypt_asym")
+    hot = ("k_encode", "k_sample_ternary", "k_sample_ternary_pair", "k_sample_cbd", "k_encrypt_asym")
     means = {}
     for k, v in agg.items():
         big = [x for x in v if x >= 0.5 * max(v)]
