@@ -52,6 +52,131 @@ __global__ void k_prng_blocks(const uint8_t *__restrict__ seeds, const uint64_t 
 // depends on how many redraws blocks <= j needed), but X(seed,c,96) and X(seed,c,1) are the same
 // SHAKE stream, so the warp computes 32 consecutive counters' streams per wave and then walks
 // them in order, deciding per counter whether it was a 96-byte block or a 1-byte redraw.
+// ---------------------------------------------------------------------------------------------
+// the same sampler, TWO ciphertexts per warp sharing the last wave (n = 4096)
+// ---------------------------------------------------------------------------------------------
+// At n = 4096 a ciphertext consumes 43 blocks + 32.25 +- 5.7 redraws = 75 PRNG counters: three waves of 32 compute 96
+// permutations for it, and the kernel is ALU-pipe bound (95 %), so a fifth of its time is spent on counters nobody
+// reads.  Here a warp owns ciphertexts 2w and 2w+1: two full waves each (counters 0..63), then ONE wave shared by
+// both from counter 64, its lanes split by what each still owes; whoever is not done afterwards gets full waves
+// of its own.  ~2.55 waves per ciphertext instead of 3.  Same walk, same bytes, same counters as k_sample_ternary.
+struct SebTernWalk
+{
+    int j = 0;       // next block index
+    int need = 0;    // redraws still owed to the current block
+    int cur = 0;     // current block index
+    int served = 0;  // redraws already served to the current block
+    uint32_t cm0 = 0, cm1 = 0, cm2 = 0;  // reject masks of the current block (all of them: served ones included)
+    uint32_t consumed = 0;
+};
+
+// position of the ord-th (0-based) set bit of the 96-bit mask (a0, a1, a2)
+__device__ __forceinline__ uint32_t seb_nth_set96(uint32_t a0, uint32_t a1, uint32_t a2, int ord)
+{
+    const int c0 = __popc(a0), c1 = __popc(a1);
+    uint32_t word = a0, base = 0;
+    if (ord >= c0 + c1)
+        word = a2, base = 64u, ord -= c0 + c1;
+    else if (ord >= c0)
+        word = a1, base = 32u, ord -= c0;
+    for (; ord > 0; ord--) word &= word - 1u;  // a block has a handful of rejected bytes (2 in 256): a short loop
+    return base + (uint32_t)__ffs(word) - 1u;
+}
+
+// Walk the counters held by lanes [lo, hi) of this wave, in order (sample.c:223-241: a counter is a 96-byte block, or a
+// 1-byte redraw owed to the block before it).  The in-order part is a lean, warp-uniform loop that only ASSIGNS roles -
+// "lane i is block j" / "lane i is the k-th redraw of block j" - from a ballot of the acceptable redraw bytes and one
+// shuffle per block (its number of rejected bytes); the data moves afterwards in parallel: block lanes store their 24
+// packed bytes, redraw lanes look up the k-th rejected position in their block's masks and OR their two bits in.
+// (Round 1 did both in the loop: a shared-memory byte update by lane 0 per redraw, three shuffles and six predicated
+// stores per block - a quarter of the kernel's instructions.)
+__device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, const int hi, const int lane, const int n,
+                                              const int nblocks, uint32_t *usm, const uint32_t (&packed)[6],
+                                              const uint32_t m0, const uint32_t m1, const uint32_t m2, const uint32_t b0)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t acc  = __ballot_sync(FULL, b0 < 0xFEu);  // counters whose first byte is acceptable as a redraw
+    const int vlast     = n - 96 * (nblocks - 1);           // bytes of the last block that are used: 32, 64 or 96
+    const int need_full = __popc(m0) + __popc(m1) + __popc(m2);
+    const int need_last = __popc(m0) + (vlast > 32 ? __popc(m1) : 0) + (vlast > 64 ? __popc(m2) : 0);
+    const uint32_t e0 = w.cm0, e1 = w.cm1, e2 = w.cm2;  // masks of the block carried over from the previous wave
+    const int j_in = w.j, cur_in = w.cur, served_in = w.served;
+    // the in-order part only builds two masks: which lanes are blocks, which are redraws that were accepted.
+    // (Stepping from event to event instead - runs of reject-free blocks from a ballot, all redraws of a block with one
+    // __fns - was measured slower, 1.755 vs 1.630 ms: __fns is a software loop.)
+    uint32_t is_blk = 0, is_red = 0;
+    int owner = -1;  // lane of this wave that holds the current block (-1: carried over)
+    for (int i = lo; i < hi; i++)
+    {
+        const uint32_t bit = 1u << i;
+        if (w.need > 0)
+        {
+            if (acc & bit)
+            {
+                is_red |= bit;
+                w.served++;
+                w.need--;
+            }
+        }
+        else if (w.j < nblocks)
+        {
+            w.need   = __shfl_sync(FULL, w.j == nblocks - 1 ? need_last : need_full, i);
+            is_blk |= bit;
+            owner    = i;
+            w.cur    = w.j;
+            w.served = 0;
+            w.j++;
+        }
+        else
+            break;
+        w.consumed++;
+    }
+    // every lane derives its role from the masks: block lanes count the blocks below them; redraw lanes belong to the
+    // nearest block below them (or to the carried block) and count the redraws in between
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t bb    = is_blk & below;
+    const int my_owner   = bb ? 31 - __clz(bb) : -1;
+    int kind = 0, blk = 0, ord = 0;  // 1 = block `blk`, 2 = redraw number `ord` of block `blk`
+    if ((is_blk >> lane) & 1u)
+        kind = 1, blk = j_in + __popc(bb);
+    else if ((is_red >> lane) & 1u)
+    {
+        kind = 2;
+        if (my_owner >= 0)
+            blk = j_in + __popc(bb) - 1, ord = __popc(is_red & below & ~((2u << my_owner) - 1u));
+        else
+            blk = cur_in, ord = served_in + __popc(is_red & below);
+    }
+    const int valid = min(96, n - 96 * blk);  // multiple of 32 for every legal n
+    if (kind == 1)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (k * 16 < valid) usm[blk * 6 + k] = packed[k];
+    }
+    __syncwarp();
+    {
+        const int src = my_owner < 0 ? lane : my_owner;
+        uint32_t a0 = __shfl_sync(FULL, m0, src), a1 = __shfl_sync(FULL, m1, src), a2 = __shfl_sync(FULL, m2, src);
+        if (kind == 2)
+        {
+            if (my_owner < 0) a0 = e0, a1 = e1, a2 = e2;
+            if (valid <= 32) a1 = 0u;
+            if (valid <= 64) a2 = 0u;
+            const uint32_t pos  = seb_nth_set96(a0, a1, a2, ord);
+            const uint32_t byte = (uint32_t)blk * 24u + (pos >> 2);
+            atomicOr(usm + (byte >> 2), (b0 % 3u) << (8u * (byte & 3u) + 6u - 2u * (pos & 3u)));
+        }
+    }
+    if (w.need > 0 && owner >= 0)  // warp-uniform: the block that continues into the next wave started in this one
+    {
+        w.cm0 = __shfl_sync(FULL, m0, owner);
+        w.cm1 = __shfl_sync(FULL, m1, owner);
+        w.cm2 = __shfl_sync(FULL, m2, owner);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restrict__ seeds,
                                                         uint8_t *__restrict__ u_out,
                                                         uint32_t *__restrict__ ctr_out, int n, int batch)
@@ -63,158 +188,24 @@ __global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restric
     const int words_per = n / 16;  // n/4 bytes
     uint32_t *usm       = usm_all + warp * words_per;
     if (b >= batch) return;
-    uint8_t *usm8 = reinterpret_cast<uint8_t *>(usm);
 
     uint64_t seed[8];
     load_seed(seeds, (size_t)b, seed);
-
     const int nblocks = (n + 95) / 96;
-    int j             = 0;  // next block index
-    int need          = 0;  // redraws still owed to the current block
-    int cur           = 0;  // current block index
-    uint32_t cm0 = 0, cm1 = 0, cm2 = 0;  // unresolved rejected positions of the current block
-    uint32_t consumed = 0;
-    uint64_t cbase    = 0;
-
-    while (j < nblocks || need > 0)
+    SebTernWalk w;
+    for (uint64_t cbase = 0; w.j < nblocks || w.need > 0; cbase += 32)
     {
         uint64_t a[25];
         seb_prng_init(a, seed, cbase + (uint64_t)lane);
         seb_keccak_f1600<12>(a);  // 96 bytes (or 1) are read from each call
-
-        uint32_t m0, m1, m2;
-        uint32_t packed[6];
+        uint32_t m0, m1, m2, packed[6];
         seb_ternary_block(a, packed, m0, m1, m2);
         const uint32_t b0 = (uint32_t)a[0] & 0xFFu;  // value if this counter was a 1-byte redraw
-
-        for (int i = 0; i < 32; i++)
-        {
-            if (need > 0)
-            {
-                const uint32_t v = __shfl_sync(0xFFFFFFFFu, b0, i);
-                if (v < 0xFEu)
-                {
-                    int pos;
-                    if (cm0)
-                    {
-                        pos = __ffs(cm0) - 1;
-                        cm0 &= cm0 - 1;
-                    }
-                    else if (cm1)
-                    {
-                        pos = 32 + __ffs(cm1) - 1;
-                        cm1 &= cm1 - 1;
-                    }
-                    else
-                    {
-                        pos = 64 + __ffs(cm2) - 1;
-                        cm2 &= cm2 - 1;
-                    }
-                    if (lane == 0)
-                        usm8[cur * 24 + (pos >> 2)] |= (uint8_t)((v % 3u) << (6 - 2 * (pos & 3)));
-                    need--;
-                }
-            }
-            else if (j < nblocks)
-            {
-                const int valid = min(96, n - 96 * j);  // multiple of 32 for every legal n
-                if (lane == i)
-                {
-#pragma unroll
-                    for (int k = 0; k < 6; k++)
-                        if (k * 16 < valid) usm[j * 6 + k] = packed[k];
-                }
-                cm0  = __shfl_sync(0xFFFFFFFFu, m0, i);
-                cm1  = valid > 32 ? __shfl_sync(0xFFFFFFFFu, m1, i) : 0u;
-                cm2  = valid > 64 ? __shfl_sync(0xFFFFFFFFu, m2, i) : 0u;
-                need = __popc(cm0) + __popc(cm1) + __popc(cm2);
-                cur  = j;
-                j++;
-                __syncwarp();
-            }
-            else
-                break;
-            consumed++;
-        }
-        cbase += 32;
+        seb_tern_walk(w, 0, 32, lane, n, nblocks, usm, packed, m0, m1, m2, b0);
     }
-    __syncwarp();
     uint32_t *dst = reinterpret_cast<uint32_t *>(u_out + (size_t)b * (n / 4));
     for (int k = lane; k < words_per; k += 32) dst[k] = usm[k];
-    if (lane == 0) ctr_out[b] = consumed;
-}
-
-// ---------------------------------------------------------------------------------------------
-// the same sampler, TWO ciphertexts per warp sharing the last wave (n = 4096)
-// ---------------------------------------------------------------------------------------------
-// At n = 4096 a ciphertext consumes 43 blocks + 32.25 +- 5.7 redraws = 75 PRNG counters: three waves of 32 compute 96
-// permutations for it, and the kernel is ALU-pipe bound (95 %), so a fifth of its time is spent on counters nobody
-// reads.  Here a warp owns ciphertexts 2w and 2w+1: two full waves each (counters 0..63), then ONE wave shared by
-// both from counter 64, its lanes split by what each still owes; whoever is not done afterwards gets full waves
-// of its own.  ~2.55 waves per ciphertext instead of 3.  Same walk, same bytes, same counters as k_sample_ternary.
-struct SebTernWalk
-{
-    int j = 0;      // next block index
-    int need = 0;   // redraws still owed to the current block
-    int cur = 0;    // current block index
-    uint32_t cm0 = 0, cm1 = 0, cm2 = 0;  // unresolved rejected positions of the current block
-    uint32_t consumed = 0;
-};
-
-// walk the counters held by lanes [lo, hi) of this wave, in order (the loop body of k_sample_ternary)
-__device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, const int hi, const int lane, const int n,
-                                              const int nblocks, uint32_t *usm, const uint32_t (&packed)[6],
-                                              const uint32_t m0, const uint32_t m1, const uint32_t m2, const uint32_t b0)
-{
-    uint8_t *usm8 = reinterpret_cast<uint8_t *>(usm);
-    for (int i = lo; i < hi; i++)
-    {
-        if (w.need > 0)
-        {
-            const uint32_t v = __shfl_sync(0xFFFFFFFFu, b0, i);
-            if (v < 0xFEu)
-            {
-                int pos;
-                if (w.cm0)
-                {
-                    pos = __ffs(w.cm0) - 1;
-                    w.cm0 &= w.cm0 - 1;
-                }
-                else if (w.cm1)
-                {
-                    pos = 32 + __ffs(w.cm1) - 1;
-                    w.cm1 &= w.cm1 - 1;
-                }
-                else
-                {
-                    pos = 64 + __ffs(w.cm2) - 1;
-                    w.cm2 &= w.cm2 - 1;
-                }
-                if (lane == 0) usm8[w.cur * 24 + (pos >> 2)] |= (uint8_t)((v % 3u) << (6 - 2 * (pos & 3)));
-                w.need--;
-            }
-        }
-        else if (w.j < nblocks)
-        {
-            const int valid = min(96, n - 96 * w.j);  // multiple of 32 for every legal n
-            if (lane == i)
-            {
-#pragma unroll
-                for (int k = 0; k < 6; k++)
-                    if (k * 16 < valid) usm[w.j * 6 + k] = packed[k];
-            }
-            w.cm0  = __shfl_sync(0xFFFFFFFFu, m0, i);
-            w.cm1  = valid > 32 ? __shfl_sync(0xFFFFFFFFu, m1, i) : 0u;
-            w.cm2  = valid > 64 ? __shfl_sync(0xFFFFFFFFu, m2, i) : 0u;
-            w.need = __popc(w.cm0) + __popc(w.cm1) + __popc(w.cm2);
-            w.cur  = w.j;
-            w.j++;
-            __syncwarp();
-        }
-        else
-            break;
-        w.consumed++;
-    }
+    if (lane == 0) ctr_out[b] = w.consumed;
 }
 
 __global__ void __launch_bounds__(128) k_sample_ternary_pair(const uint8_t *__restrict__ seeds, uint8_t *__restrict__ u_out,
