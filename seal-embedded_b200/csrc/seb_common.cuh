@@ -24,6 +24,13 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s)
     s &= 31;
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)  // selector nibbles 0..7 only
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r       = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+}
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline uint32_t __vcmpgeu4(uint32_t a, uint32_t b)

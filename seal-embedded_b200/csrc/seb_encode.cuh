@@ -176,6 +176,21 @@ __device__ __forceinline__ void enc_pass(double (&xr)[ENC_E], double (&xi)[ENC_E
                 {
                     const int ia    = i * (1 << R) + (m << (r + 1)) + k;
                     const int ib    = ia + (1 << r);
+                    if (P == 0 && k == 0)
+                    {
+                        // The message is real (ckks_common.c:139-153 stores values[i] in both conjugate slots, imaginary
+                        // parts 0), and after r stages the elements whose low r position bits are 0 still are: u and v
+                        // are both real here.  di = 0 - 0 = +0, so the reference's dr*s.x - di*s.y and dr*s.y + di*s.x
+                        // equal dr*s.x and dr*s.y up to the SIGN OF A ZERO result, which no later operation turns into a
+                        // different non-zero value and the final round-to-int64 maps to 0 either way: 4 FP64
+                        // operations instead of 10 for 30 of the 64 butterflies of this pass.
+                        const double ur = xr[ia], vr = xr[ib];
+                        const double dr = __dsub_rn(ur, vr);
+                        xr[ia]          = __dadd_rn(ur, vr);
+                        xr[ib]          = __dmul_rn(dr, s.x);
+                        xi[ib]          = __dmul_rn(dr, s.y);
+                        continue;
+                    }
                     const double ur = xr[ia], ui = xi[ia], vr = xr[ib], vi = xi[ib];
                     const double dr = __dsub_rn(ur, vr), di = __dsub_rn(ui, vi);
                     xr[ia]          = __dadd_rn(ur, vr);

@@ -165,7 +165,9 @@ __device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, cons
             if (valid <= 64) a2 = 0u;
             const uint32_t pos  = seb_nth_set96(a0, a1, a2, ord);
             const uint32_t byte = (uint32_t)blk * 24u + (pos >> 2);
-            atomicOr(usm + (byte >> 2), (b0 % 3u) << (8u * (byte & 3u) + 6u - 2u * (pos & 3u)));
+            const uint32_t sh   = 8u * (byte & 3u) + 6u - 2u * (pos & 3u);
+            atomicAnd(usm + (byte >> 2), ~(3u << sh));  // the block left a don't-care value in a rejected field
+            atomicOr(usm + (byte >> 2), (b0 % 3u) << sh);
         }
     }
     if (w.need > 0 && owner >= 0)  // warp-uniform: the block that continues into the next wave started in this one

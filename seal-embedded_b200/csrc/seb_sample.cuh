@@ -16,30 +16,47 @@ __device__ __forceinline__ uint32_t seb_mod3_bytes(uint32_t x)
     return r - (three | (three << 1));
 }
 
-// One 96-byte PRNG block as a ternary block (sample.c:223-241): packed[6] = the 24 output bytes
-// (MSB-first 2-bit fields, rejected slots left 0), m0..m2 = bit i set when byte i >= 0xFE.
+// One 96-byte PRNG block as a ternary block (sample.c:223-241): packed[6] = the 24 output bytes (MSB-first 2-bit
+// fields), m0..m2 = bit i set when byte i >= 0xFE (rejected).  The fields of rejected bytes hold a DON'T-CARE value (their
+// byte mod 3): the walk overwrites them with the redraws.
+//
+// The samplers are bound by the ALU pipe (LOP3/SHF/PRMT/IADD: Keccak-f keeps it 98 % busy) while the FMA pipe idles, so
+// this is written to put its arithmetic into IMADs - 9 ALU + 9 IMAD instructions per four bytes instead of ~30 ALU:
+//  * rejected flags: z = ~w & 0xFE..FE has a zero byte exactly where w has 0xFE/0xFF; z's bytes are even, so the borrow
+//    of (z - 0x01..01) never produces a false positive and (z - 0x01..01) & ~z & 0x80..80 is exact; one multiplication
+//    gathers the four flags (bits 7, 15, 23, 31) into bits 28..31 and a funnel shift appends them to the mask;
+//  * x mod 3 for two bytes per word (16-bit fields): x * 171 = 512 floor(x / 3) + l (exact for x < 256), so
+//    x * 512 - 3 * (x * 171 & 0xFE00) = 512 (x mod 3) - also when the fields' partial products overflow into each other,
+//    the identity holds modulo 2^32;
+//  * the four 2-bit results (bits 9-10 and 25-26 of two words) are moved to one byte by two more multiplications whose
+//    partial products do not collide, and a byte permute drops it into the output word.
 __device__ __forceinline__ void seb_ternary_block(const uint64_t (&a)[25], uint32_t (&packed)[6], uint32_t &m0,
                                                   uint32_t &m1, uint32_t &m2)
 {
     m0 = m1 = m2 = 0;
 #pragma unroll
-    for (int k = 0; k < 24; k++)
+    for (int g = 0; g < 6; g++) packed[g] = 0;
+#pragma unroll
+    for (int k = 23; k >= 0; k--)  // downwards: the funnel shift pushes earlier words towards the high nibbles
     {
-        const uint32_t w  = (k & 1) ? (uint32_t)(a[k >> 1] >> 32) : (uint32_t)a[k >> 1];
-        const uint32_t ge = __vcmpgeu4(w, 0xFEFEFEFEu);
-        const uint32_t nb = ((ge & 0x01010101u) * 0x01020408u) >> 24;  // bit i = byte i rejected
+        const uint32_t w    = (k & 1) ? (uint32_t)(a[k >> 1] >> 32) : (uint32_t)a[k >> 1];
+        const uint32_t z    = ~w & 0xFEFEFEFEu;
+        const uint32_t ge   = (z - 0x01010101u) & ~z & 0x80808080u;  // bit 8i+7: byte i rejected
+        const uint32_t nib  = ge * 0x00204081u;                       // ... gathered in bits 28 + i
         if (k < 8)
-            m0 |= nb << (4 * k);
+            m0 = __funnelshift_l(nib, m0, 4);
         else if (k < 16)
-            m1 |= nb << (4 * (k - 8));
+            m1 = __funnelshift_l(nib, m1, 4);
         else
-            m2 |= nb << (4 * (k - 16));
-        const uint32_t r    = seb_mod3_bytes(w) & ~ge;      // rejected slots stay 0 for now
-        const uint32_t byte = (r * 0x40100401u) >> 24;      // v0<<6 | v1<<4 | v2<<2 | v3
-        if ((k & 3) == 0)
-            packed[k >> 2] = byte;
-        else
-            packed[k >> 2] |= byte << (8 * (k & 3));
+            m2 = __funnelshift_l(nib, m2, 4);
+        const uint32_t e  = __byte_perm(w, 0u, 0x4240);  // byte 0 | byte 2 << 16
+        const uint32_t o  = __byte_perm(w, 0u, 0x4143);  // byte 3 | byte 1 << 16
+        const uint32_t re = e * 512u - 3u * ((e * 171u) & 0xFE00FE00u);  // v0 at bits 9-10, v2 at bits 25-26
+        const uint32_t ro = o * 512u - 3u * ((o * 171u) & 0xFE00FE00u);  // v3 at bits 9-10, v1 at bits 25-26
+        // re * (2^21 + 2): v0 -> bits 30-31, v2 -> 26-27 (and v0 -> 10-11); ro * (2^15 + 2^3): v3 -> 24-25, v1 -> 28-29
+        // (and v3 -> 12-13): the top byte is v0 << 6 | v1 << 4 | v2 << 2 | v3
+        const uint32_t sum = re * 0x00200002u + ro * 0x00008008u;
+        packed[k >> 2] = __byte_perm(packed[k >> 2], sum, (0x3210u & ~(0xFu << (4 * (k & 3)))) | (7u << (4 * (k & 3))));
     }
 }
 

@@ -367,6 +367,16 @@ extern "C" void emul_ternary_block(const uint8_t *seed, uint64_t ctr, uint32_t *
     memcpy(packed6, p, sizeof p);
 }
 
+// the same on a caller-supplied 96-byte block (exhaustive byte-value checks)
+extern "C" void emul_ternary_block_raw(const uint8_t *bytes96, uint32_t *packed6, uint32_t *mask3)
+{
+    uint64_t a[25] = {0};
+    memcpy(a, bytes96, 96);
+    uint32_t p[6];
+    seb_ternary_block(a, p, mask3[0], mask3[1], mask3[2]);
+    memcpy(packed6, p, sizeof p);
+}
+
 extern "C" void emul_cbd_block(const uint8_t *seed, uint64_t ctr, uint32_t *out4)
 {
     uint64_t s[8], a[25];

@@ -63,6 +63,7 @@ def E(emul):
     emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint32)]
     emul.emul_cbd_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
+    emul.emul_ternary_block_raw.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     emul.emul_mod3_bytes.argtypes = [C.c_uint32]
     emul.emul_mod3_bytes.restype = C.c_uint32
     return emul
@@ -343,6 +344,28 @@ def test_mod3_bytes_exhaustive(E):
             assert (r >> (8 * k)) & 0xFF == ((x >> (8 * k)) & 0xFF) % 3
 
 
+def test_ternary_block_every_byte_value(E):
+    """The multiply-based mod 3 / flag gathering of seb_ternary_block on every byte value at every position of a word,
+    beside neighbours that make the 16-bit partial products overflow into each other (0xFF) or not (0x00)."""
+    rng = np.random.default_rng(5)
+    for fill in (0x00, 0xFF, 0xFD, None):
+        for lane in range(4):
+            for base in range(0, 256, 24):
+                blk = np.full(96, fill, np.uint8) if fill is not None else rng.integers(0, 256, 96, dtype=np.uint8)
+                vals = [(base + i) & 0xFF for i in range(24)]
+                for i, v in enumerate(vals):
+                    blk[4 * i + lane] = v
+                packed = np.zeros(6, np.uint32)
+                mask = np.zeros(3, np.uint32)
+                E.emul_ternary_block_raw(_p(blk, C.c_uint8), _p(packed, C.c_uint32), _p(mask, C.c_uint32))
+                pb = packed.tobytes()
+                for pos in range(96):
+                    rej = int(blk[pos]) >= 0xFE
+                    assert ((int(mask[pos // 32]) >> (pos % 32)) & 1) == int(rej)
+                    if not rej:
+                        assert (pb[pos // 4] >> (6 - 2 * (pos % 4))) & 3 == int(blk[pos]) % 3
+
+
 def test_ternary_and_cbd_blocks(E, oracle_mod):
     """One 96-byte PRNG call as a ternary block (packed fields + rejection masks, sample.c:223-241) and as
     16 CBD samples (sample.c:263-321)."""
@@ -359,7 +382,7 @@ def test_ternary_and_cbd_blocks(E, oracle_mod):
             rej = buf[pos] >= 0xFE
             assert ((int(mask[pos // 32]) >> (pos % 32)) & 1) == int(rej)
             field = (pb[pos // 4] >> (6 - 2 * (pos % 4))) & 3
-            assert field == (0 if rej else buf[pos] % 3)
+            assert rej or field == buf[pos] % 3  # a rejected field is a don't-care: the walk overwrites it
             seen_reject += rej
         o = np.zeros(4, np.uint32)
         E.emul_cbd_block(_p(seeds[i], C.c_uint8), ctr, _p(o, C.c_uint32))
