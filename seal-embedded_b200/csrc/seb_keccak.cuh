@@ -133,6 +133,133 @@ __device__ __forceinline__ void seb_keccak_f1600(uint64_t (&a)[25])
     for (int i = 0; i < (PRUNE ? 12 : 25); i++) a[i] = ((uint64_t)hi[i] << 32) | lo[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same permutation on a BIT-INTERLEAVED state: lane = (e, o), e bit i = lane bit 2i, o bit i = lane bit 2i + 1.
+// A 64-bit rotation by an even amount R is two 32-bit rotations by R/2; by an odd amount it swaps the halves and
+// rotates them by (R+1)/2 and (R-1)/2 - so the rotation by 1 of theta's five column parities costs ONE funnel shift
+// instead of two, and so does rho's offset 1: 174 ALU operations per round instead of 180 (3.3 % of a kernel that is
+// bound by exactly that).  It pays where the squeezed bits can be consumed without de-interleaving them: the
+// centered-binomial sampler only counts bits (seb_sample.cuh, seb_cbd_block_il).
+// ---------------------------------------------------------------------------------------------
+SEB_CONSTANT uint32_t c_keccak_rc_even[24] = {
+    0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
+    0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
+    0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000000u};
+SEB_CONSTANT uint32_t c_keccak_rc_odd[24] = {
+    0x00000000u, 0x00000089u, 0x8000008bu, 0x80008080u, 0x0000008bu, 0x00008000u, 0x80008088u, 0x80000082u,
+    0x0000000bu, 0x0000000au, 0x00008082u, 0x00008003u, 0x0000808bu, 0x8000000bu, 0x8000008au, 0x80000081u,
+    0x80000081u, 0x80000008u, 0x00000083u, 0x80008003u, 0x80008088u, 0x80000088u, 0x00008000u, 0x80008082u};
+
+__device__ __forceinline__ uint32_t seb_rotl32(uint32_t x, const int r)  // r: compile-time after inlining
+{
+    return (r & 31) ? __funnelshift_l(x, x, r & 31) : x;
+}
+template <int R>
+__device__ __forceinline__ void seb_rotl64_il(uint32_t e, uint32_t o, uint32_t &oe, uint32_t &oo)
+{
+    if constexpr ((R & 1) == 0)
+    {
+        oe = seb_rotl32(e, R / 2);
+        oo = seb_rotl32(o, R / 2);
+    }
+    else
+    {
+        oe = seb_rotl32(o, (R + 1) / 2);
+        oo = seb_rotl32(e, (R - 1) / 2);
+    }
+}
+
+#define SEB_KECCAK_RP_IL(SRC, DST, ROT)                                                               \
+    if (!PRUNE || (DST) < 14)                                                                         \
+    {                                                                                                 \
+        const uint32_t te_ = X3(e[SRC], ce[((SRC) % 5 + 4) % 5], re[((SRC) % 5 + 1) % 5]);           \
+        const uint32_t to_ = X3(o[SRC], co[((SRC) % 5 + 4) % 5], ce[((SRC) % 5 + 1) % 5]);           \
+        seb_rotl64_il<ROT>(te_, to_, be[DST], bo[DST]);                                               \
+    }
+
+// FIRST: round 0 of a freshly initialised sponge, inlined outside the round loop.  Thirteen of its 25 lanes are zero and
+// two are constants; written with plain operators instead of the opaque LOP3s, the compiler folds them (column parities
+// of two inputs, one theta word for the three empty lanes of a column).
+template <bool PRUNE, bool FIRST = false>
+__device__ __forceinline__ void seb_keccak_round_il(uint32_t (&e)[25], uint32_t (&o)[25], const int round)
+{
+    auto X3 = [](uint32_t a, uint32_t b, uint32_t c) { return FIRST ? (a ^ b ^ c) : seb_xor3(a, b, c); };
+    uint32_t ce[5], co[5], re[5], be[25], bo[25];
+#pragma unroll
+    for (int x = 0; x < 5; x++)
+    {
+        ce[x] = X3(X3(e[x], e[x + 5], e[x + 10]), e[x + 15], e[x + 20]);
+        co[x] = X3(X3(o[x], o[x + 5], o[x + 10]), o[x + 15], o[x + 20]);
+    }
+    // rotl64(C, 1): even half = rotl32(co, 1), odd half = ce (a rename: SEB_KECCAK_RP_IL reads ce there)
+#pragma unroll
+    for (int x = 0; x < 5; x++) re[x] = seb_rotl32(co[x], 1);
+    SEB_KECCAK_RP_IL(0, 0, 0) SEB_KECCAK_RP_IL(1, 10, 1) SEB_KECCAK_RP_IL(2, 20, 62) SEB_KECCAK_RP_IL(3, 5, 28)
+    SEB_KECCAK_RP_IL(4, 15, 27) SEB_KECCAK_RP_IL(5, 16, 36) SEB_KECCAK_RP_IL(6, 1, 44) SEB_KECCAK_RP_IL(7, 11, 6)
+    SEB_KECCAK_RP_IL(8, 21, 55) SEB_KECCAK_RP_IL(9, 6, 20) SEB_KECCAK_RP_IL(10, 7, 3) SEB_KECCAK_RP_IL(11, 17, 10)
+    SEB_KECCAK_RP_IL(12, 2, 43) SEB_KECCAK_RP_IL(13, 12, 25) SEB_KECCAK_RP_IL(14, 22, 39) SEB_KECCAK_RP_IL(15, 23, 41)
+    SEB_KECCAK_RP_IL(16, 8, 45) SEB_KECCAK_RP_IL(17, 18, 15) SEB_KECCAK_RP_IL(18, 3, 21) SEB_KECCAK_RP_IL(19, 13, 8)
+    SEB_KECCAK_RP_IL(20, 14, 18) SEB_KECCAK_RP_IL(21, 24, 2) SEB_KECCAK_RP_IL(22, 9, 61) SEB_KECCAK_RP_IL(23, 19, 56)
+    SEB_KECCAK_RP_IL(24, 4, 14)
+#pragma unroll
+    for (int y = 0; y < 25; y += 5)
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+            if (!PRUNE || y + x < 12)
+            {
+                e[y + x] = seb_chi(be[y + x], be[y + (x + 1) % 5], be[y + (x + 2) % 5]);
+                o[y + x] = seb_chi(bo[y + x], bo[y + (x + 1) % 5], bo[y + (x + 2) % 5]);
+            }
+    e[0] ^= c_keccak_rc_even[round];
+    o[0] ^= c_keccak_rc_odd[round];
+}
+#undef SEB_KECCAK_RP_IL
+
+// Keccak-f[1600] on the interleaved state; the last round is pruned to output lanes 0..11 (96 bytes)
+__device__ __forceinline__ void seb_keccak_f1600_il12(uint32_t (&e)[25], uint32_t (&o)[25])
+{
+    seb_keccak_round_il<false, true>(e, o, 0);
+#pragma unroll 1
+    for (int round = 1; round < 23; round++) seb_keccak_round_il<false>(e, o, round);
+    seb_keccak_round_il<true>(e, o, 23);
+}
+
+// the even (odd = 0) or odd (odd = 1) bits of a 32-bit word, packed into 16
+__device__ __forceinline__ uint32_t seb_half_bits32(uint32_t w, const int odd)
+{
+    uint32_t t = (w >> odd) & 0x55555555u;
+    t          = (t | (t >> 1)) & 0x33333333u;
+    t          = (t | (t >> 2)) & 0x0F0F0F0Fu;
+    t          = (t | (t >> 4)) & 0x00FF00FFu;
+    t          = (t | (t >> 8)) & 0x0000FFFFu;
+    return t;
+}
+// ... of a 64-bit lane, packed into 32
+__device__ __forceinline__ uint32_t seb_half_bits(uint64_t w, const int odd)
+{
+    return seb_half_bits32((uint32_t)w, odd) | (seb_half_bits32((uint32_t)(w >> 32), odd) << 16);
+}
+
+// interleaved absorb of (seed || LE64(counter)): se/so = the seed's eight lanes already split, counter < 2^33
+__device__ __forceinline__ void seb_prng_init_il(uint32_t (&e)[25], uint32_t (&o)[25], const uint32_t (&se)[8],
+                                                 const uint32_t (&so)[8], uint64_t counter)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = se[i], o[i] = so[i];
+    e[8] = seb_half_bits32((uint32_t)counter, 0);
+    o[8] = seb_half_bits32((uint32_t)counter, 1);
+    if (const uint32_t chi = (uint32_t)(counter >> 32))  // the samplers' counters are small: never taken in practice
+    {
+        e[8] |= seb_half_bits32(chi, 0) << 16;
+        o[8] |= seb_half_bits32(chi, 1) << 16;
+    }
+    e[9] = 0x7u;  // 0x1F: bits 0, 2, 4 | bits 1, 3
+    o[9] = 0x3u;
+#pragma unroll
+    for (int i = 10; i < 25; i++) e[i] = 0u, o[i] = 0u;
+    o[16] = 0x80000000u;  // bit 63
+}
+
 // SHAKE256 absorb of (seed || LE64(counter)): 72 bytes, domain byte 0x1F at offset 72, final bit
 // 0x80 at offset 135 (device/lib/shake256/fips202.c:46-66).  seed8 = the seed as 8 LE words.
 __device__ __forceinline__ void seb_prng_init(uint64_t (&a)[25], const uint64_t (&seed8)[8], uint64_t counter)

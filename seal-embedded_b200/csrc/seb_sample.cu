@@ -294,25 +294,53 @@ __global__ void __launch_bounds__(128) k_sample_ternary_pair(const uint8_t *__re
 // ---------------------------------------------------------------------------------------------
 // e_out: [batch][npoly][n] int8; polynomial k of ciphertext b uses counters
 // ctr_base[b] + k*n/16 + (0 .. n/16)   (ckks_asym.c:199-200: e0 then e1 from the same PRNG)
+//
+// The permutation runs on a bit-interleaved state (seb_keccak.cuh: 174 ALU operations per round instead of 180) because
+// the samples are popcounts and can be taken from the interleaved block as it is.  The 32 threads of a warp serve the
+// same ciphertext (n/16 calls per polynomial is a multiple of 32 for n >= 512), so its seed is split into even and odd
+// bits once per warp - lane i < 8 does seed word i, 16 shuffles hand the halves round - instead of 32 times.
 __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ seeds,
                                                     const uint32_t *__restrict__ ctr_base,
                                                     int8_t *__restrict__ e_out, int n, int npoly, int batch)
 {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
     const size_t per_ct = (size_t)npoly * (n / 16);
+    const size_t total  = per_ct * (size_t)batch;
     const size_t idx    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= per_ct * (size_t)batch) return;
-    const size_t b = idx / per_ct;
-    const size_t r = idx % per_ct;
+    const bool live     = idx < total;
+    const size_t idc    = live ? idx : total - 1;  // a partial last warp computes along: the shuffles need every lane
+    const uint32_t b    = (uint32_t)(idc / per_ct);
+    const size_t r      = idc % per_ct;
+    const int lane      = threadIdx.x & 31;
 
-    uint64_t s[8], a[25];
-    load_seed(seeds, b, s);
-    seb_prng_init(a, s, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
-    seb_keccak_f1600<12>(a);  // 96 bytes per call
+    uint32_t se[8], so[8];
+    if (__all_sync(FULL, b == __shfl_sync(FULL, b, 0)))
+    {
+        // lane = 16 * parity + 8 * (high word) + seed word: every lane compresses ONE 32-bit piece into 16 bits, lane L
+        // and lane L + 8 make a half lane, and lanes 0..7 / 16..23 end up with the even / odd halves of seed word L & 7
+        const uint32_t piece = __ldg(reinterpret_cast<const uint32_t *>(seeds + (size_t)b * SEB_SEED_BYTES) +
+                                     2 * (lane & 7) + ((lane >> 3) & 1));
+        const uint32_t v     = seb_half_bits32(piece, lane >> 4);
+        const uint32_t comb  = __byte_perm(v, __shfl_down_sync(FULL, v, 8), 0x5410);
+#pragma unroll
+        for (int i = 0; i < 8; i++) se[i] = __shfl_sync(FULL, comb, i), so[i] = __shfl_sync(FULL, comb, 16 + i);
+    }
+    else  // a warp across two ciphertexts (degrees below 512): every lane splits its own seed
+    {
+        uint64_t s[8];
+        load_seed(seeds, b, s);
+#pragma unroll
+        for (int i = 0; i < 8; i++) se[i] = seb_half_bits(s[i], 0), so[i] = seb_half_bits(s[i], 1);
+    }
+    uint32_t e[25], o[25];
+    seb_prng_init_il(e, o, se, so, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
+    seb_keccak_f1600_il12(e, o);  // 96 bytes per call
 
-    uint32_t o[4];
-    seb_cbd_block(a, o);
-    uint4 *dst = reinterpret_cast<uint4 *>(e_out + b * (size_t)npoly * n + r * 16);
-    *dst       = make_uint4(o[0], o[1], o[2], o[3]);
+    uint32_t out[4];
+    seb_cbd_block_il(e, o, out);
+    if (!live) return;
+    uint4 *dst = reinterpret_cast<uint4 *>(e_out + (size_t)b * npoly * n + r * 16);
+    *dst       = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,27 +573,6 @@ __global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__rest
 // computes, on twice the warps with half the dependency depth.  The squeezed words are de-interleaved with one more
 // exchange and a 4-step perfect shuffle each (the even lane rebuilds the low 32 bits of every rate word, the odd
 // lane the high 32 bits).  Output, reject lists and counters are exactly those of k_uniform_bulk (sample.c:39-57).
-SEB_CONSTANT uint32_t c_keccak_rc_even[24] = {
-    0x00000001u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
-    0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000001u, 0x00000001u, 0x00000001u,
-    0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000001u, 0x00000000u, 0x00000001u, 0x00000000u};
-SEB_CONSTANT uint32_t c_keccak_rc_odd[24] = {
-    0x00000000u, 0x00000089u, 0x8000008bu, 0x80008080u, 0x0000008bu, 0x00008000u, 0x80008088u, 0x80000082u,
-    0x0000000bu, 0x0000000au, 0x00008082u, 0x00008003u, 0x0000808bu, 0x8000000bu, 0x8000008au, 0x80000081u,
-    0x80000081u, 0x80000008u, 0x00000083u, 0x80008003u, 0x80008088u, 0x80000088u, 0x00008000u, 0x80008082u};
-
-// the even (odd = 0) or odd (odd = 1) bits of w, packed
-__device__ __forceinline__ uint32_t seb_half_bits(uint64_t w, const int odd)
-{
-    uint64_t t = (w >> odd) & 0x5555555555555555ULL;
-    t = (t | (t >> 1)) & 0x3333333333333333ULL;
-    t = (t | (t >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
-    t = (t | (t >> 4)) & 0x00FF00FF00FF00FFULL;
-    t = (t | (t >> 8)) & 0x0000FFFF0000FFFFULL;
-    t = (t | (t >> 16)) & 0x00000000FFFFFFFFULL;
-    return (uint32_t)t;
-}
-
 // v = bytes [a0, b0, a1, b1] of two 16-bit values a, b  ->  bit 2i = a_i, bit 2i+1 = b_i: the last three steps of the
 // 32-bit perfect shuffle (the first, a swap of the two middle bytes, is folded into the byte permute that builds v)
 __device__ __forceinline__ uint32_t seb_interleave_tail(uint32_t v)

@@ -83,3 +83,75 @@ __device__ __forceinline__ void seb_cbd_block(const uint64_t (&a)[25], uint32_t 
                ((uint32_t)(s3 & 0xFF) << 24);
     }
 }
+
+// The same 16 samples from a BIT-INTERLEAVED block (seb_keccak.cuh: e[l] bit i = lane l bit 2i, o[l] bit i = bit 2i + 1).
+// A sample is popcount(21 bits) - popcount(21 bits), and a popcount does not care where its bits sit: the 21-bit ranges
+// [48s, 48s + 21) and [48s + 24, 48s + 45) of the stream become 11 even + 10 odd positions each, in one or two lanes.
+// With popc(x) - popc(y) = popc(x) + popc(~y & mask) - |mask| the positive and the negative bits that share a word are
+// counted by ONE population count of (w ^ neg_mask) & (pos_mask | neg_mask): 12 counts per four samples.
+__host__ __device__ constexpr uint32_t seb_il_mask(int lane, int odd, int b0, int len)  // positions [b0, b0+len) of the stream
+{
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++)
+    {
+        const int pos = 64 * lane + 2 * i + odd;
+        if (pos >= b0 && pos < b0 + len) m |= 1u << i;
+    }
+    return m;
+}
+// (x ^ n) & m with constant n and m as ONE LOP3: an instruction takes one immediate, so the compiler splits the
+// expression into two ALU operations; with m forced into a register the second becomes a move, which goes to the idle
+// FMA pipe.  n = 0 is a plain AND.
+template <uint32_t N, uint32_t M>
+__device__ __forceinline__ uint32_t seb_xor_and(uint32_t x)
+{
+#ifdef __CUDACC__
+    if constexpr (N == 0u)
+        return x & M;
+    else
+    {
+        uint32_t r;
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(r) : "r"(x), "n"(N), "r"(M));
+        return r;
+    }
+#else
+    return (x ^ N) & M;
+#endif
+}
+// Adds the counts of sample S found in lane L to byte S % 4 of acc.  The counts of one sample sum to s + 21 in [0, 42]:
+// no carry between the bytes.  Spelled as multiply-adds so that they issue on the FMA pipe.
+template <int S, int L>
+__device__ __forceinline__ void seb_cbd_il_part(const uint32_t (&e)[25], const uint32_t (&o)[25], uint32_t &acc)
+{
+    constexpr uint32_t pe = seb_il_mask(L, 0, 48 * S, 21), ne = seb_il_mask(L, 0, 48 * S + 24, 21);
+    constexpr uint32_t po = seb_il_mask(L, 1, 48 * S, 21), no = seb_il_mask(L, 1, 48 * S + 24, 21);
+    constexpr uint32_t w  = 1u << (8 * (S & 3));
+    if constexpr ((pe | ne) != 0u) acc = (uint32_t)__popc(seb_xor_and<ne, (pe | ne)>(e[L])) * w + acc;
+    if constexpr ((po | no) != 0u) acc = (uint32_t)__popc(seb_xor_and<no, (po | no)>(o[L])) * w + acc;
+}
+template <int S>
+__device__ __forceinline__ void seb_cbd_il_one(const uint32_t (&e)[25], const uint32_t (&o)[25], uint32_t &acc)
+{
+    constexpr int L0 = (48 * S) / 64, L1 = (48 * S + 44) / 64;
+    seb_cbd_il_part<S, L0>(e, o, acc);
+    if constexpr (L1 != L0) seb_cbd_il_part<S, L1>(e, o, acc);
+}
+// four samples as int8: byte j collects s_j + 21 on top of 0x80 - 21 = 0x6B (bit 7 keeps the per-byte subtraction of
+// the bias from borrowing), and flipping bit 7 afterwards leaves s_j modulo 256
+template <int G>
+__device__ __forceinline__ uint32_t seb_cbd_il_word(const uint32_t (&e)[25], const uint32_t (&o)[25])
+{
+    uint32_t acc = 0x6B6B6B6Bu;
+    seb_cbd_il_one<4 * G>(e, o, acc);
+    seb_cbd_il_one<4 * G + 1>(e, o, acc);
+    seb_cbd_il_one<4 * G + 2>(e, o, acc);
+    seb_cbd_il_one<4 * G + 3>(e, o, acc);
+    return acc ^ 0x80808080u;
+}
+__device__ __forceinline__ void seb_cbd_block_il(const uint32_t (&e)[25], const uint32_t (&o)[25], uint32_t (&out)[4])
+{
+    out[0] = seb_cbd_il_word<0>(e, o);
+    out[1] = seb_cbd_il_word<1>(e, o);
+    out[2] = seb_cbd_il_word<2>(e, o);
+    out[3] = seb_cbd_il_word<3>(e, o);
+}

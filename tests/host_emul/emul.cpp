@@ -377,7 +377,22 @@ extern "C" void emul_ternary_block_raw(const uint8_t *bytes96, uint32_t *packed6
     memcpy(packed6, p, sizeof p);
 }
 
+// the product's form: bit-interleaved state, samples counted in place
 extern "C" void emul_cbd_block(const uint8_t *seed, uint64_t ctr, uint32_t *out4)
+{
+    uint64_t s[8];
+    memcpy(s, seed, 64);
+    uint32_t se[8], so[8], e[25], o[25];
+    for (int i = 0; i < 8; i++) se[i] = seb_half_bits(s[i], 0), so[i] = seb_half_bits(s[i], 1);
+    seb_prng_init_il(e, o, se, so, ctr);
+    seb_keccak_f1600_il12(e, o);
+    uint32_t out[4];
+    seb_cbd_block_il(e, o, out);
+    memcpy(out4, out, sizeof out);
+}
+
+// the plain form (64-bit lanes), kept as a second opinion
+extern "C" void emul_cbd_block_plain(const uint8_t *seed, uint64_t ctr, uint32_t *out4)
 {
     uint64_t s[8], a[25];
     memcpy(s, seed, 64);
@@ -386,6 +401,21 @@ extern "C" void emul_cbd_block(const uint8_t *seed, uint64_t ctr, uint32_t *out4
     uint32_t o[4];
     seb_cbd_block(a, o);
     memcpy(out4, o, sizeof o);
+}
+
+// one full interleaved permutation against the plain one: state in / state out as 64-bit lanes
+extern "C" void emul_keccak_il(uint64_t *a25)
+{
+    uint32_t e[25], o[25];
+    for (int i = 0; i < 25; i++) e[i] = seb_half_bits(a25[i], 0), o[i] = seb_half_bits(a25[i], 1);
+    for (int round = 0; round < 24; round++) seb_keccak_round_il<false>(e, o, round);
+    for (int i = 0; i < 25; i++)
+    {
+        uint64_t w = 0;
+        for (int k = 0; k < 32; k++)
+            w |= ((uint64_t)((e[i] >> k) & 1u) << (2 * k)) | ((uint64_t)((o[i] >> k) & 1u) << (2 * k + 1));
+        a25[i] = w;
+    }
 }
 
 extern "C" uint32_t emul_mod3_bytes(uint32_t x) { return seb_mod3_bytes(x); }

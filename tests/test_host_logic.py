@@ -63,6 +63,8 @@ def E(emul):
     emul.emul_ternary_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint32)]
     emul.emul_cbd_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
+    emul.emul_cbd_block_plain.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
+    emul.emul_keccak_il.argtypes = [C.POINTER(C.c_uint64)]
     emul.emul_ternary_block_raw.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     emul.emul_mod3_bytes.argtypes = [C.c_uint32]
     emul.emul_mod3_bytes.restype = C.c_uint32
@@ -336,6 +338,21 @@ def test_keccak_permutation_and_prng_block(E, oracle_mod):
         assert out.tobytes() == hashlib.shake_256(seeds[i].tobytes() + struct.pack("<Q", ctr)).digest(136)
 
 
+def test_keccak_bit_interleaved(E):
+    """The bit-interleaved round function (even/odd halves, 174 operations) is the same permutation."""
+    st = (C.c_uint64 * 25)()
+    E.emul_keccak_il(st)
+    assert st[0] == 0xF1258F7940E1DDE7 and st[24] == 0xEAF1FF7B5CECA249
+    rng = np.random.default_rng(11)
+    for _ in range(8):
+        v = rng.integers(0, 1 << 64, 25, dtype=np.uint64)
+        a = (C.c_uint64 * 25)(*[int(x) for x in v])
+        b = (C.c_uint64 * 25)(*[int(x) for x in v])
+        E.emul_keccak(a)
+        E.emul_keccak_il(b)
+        assert list(a) == list(b)
+
+
 def test_mod3_bytes_exhaustive(E):
     for b in range(256):
         x = b | ((255 - b) << 8) | (((b * 7) & 0xFF) << 16) | (((b * 13 + 5) & 0xFF) << 24)
@@ -391,4 +408,7 @@ def test_ternary_and_cbd_blocks(E, oracle_mod):
         for s in range(16):
             x = buf[6 * s: 6 * s + 6]
             assert got[s] == hw(x[0]) + hw(x[1]) + hw(x[2] & 0x1F) - hw(x[3]) - hw(x[4]) - hw(x[5] & 0x1F)
+        o2 = np.zeros(4, np.uint32)
+        E.emul_cbd_block_plain(_p(seeds[i], C.c_uint8), ctr, _p(o2, C.c_uint32))
+        assert np.array_equal(o, o2)
     assert seen_reject > 0
