@@ -67,8 +67,8 @@ SEB_CONSTANT uint32_t c_keccak_rc_hi[24] = {
 #define SEB_KECCAK_RP(SRC, DST, ROT)                                                                  \
     if (!PRUNE || (DST) < 14)                                                                         \
     {                                                                                                 \
-        const uint32_t tl_ = seb_xor3(lo[SRC], cl[((SRC) % 5 + 4) % 5], rl[((SRC) % 5 + 1) % 5]);    \
-        const uint32_t th_ = seb_xor3(hi[SRC], ch[((SRC) % 5 + 4) % 5], rh[((SRC) % 5 + 1) % 5]);    \
+        const uint32_t tl_ = X3(lo[SRC], cl[((SRC) % 5 + 4) % 5], rl[((SRC) % 5 + 1) % 5]);          \
+        const uint32_t th_ = X3(hi[SRC], ch[((SRC) % 5 + 4) % 5], rh[((SRC) % 5 + 1) % 5]);          \
         seb_rotl64<ROT>(tl_, th_, bl[DST], bh[DST]);                                                  \
     }
 
@@ -76,15 +76,19 @@ SEB_CONSTANT uint32_t c_keccak_rc_hi[24] = {
 // 10, theta-apply fused into a 3-input XOR 50, rho 48 funnel shifts, chi 50, iota 2.
 // PRUNE: only output lanes 0..11 (the first 96 bytes of the rate) are wanted, which need B lanes
 // 0..13 only: 112 operations.
-template <bool PRUNE>
+// FIRST: round 0 of a freshly initialised sponge (seb_prng_init), inlined outside the round loop.  Thirteen of its 25
+// lanes are zero and two are constants; written with plain operators instead of the opaque LOP3s, the compiler folds
+// them (column parities of two inputs, one theta word for the three empty lanes of a column): ~110 operations.
+template <bool PRUNE, bool FIRST = false>
 __device__ __forceinline__ void seb_keccak_round(uint32_t (&lo)[25], uint32_t (&hi)[25], const int round)
 {
+    auto X3 = [](uint32_t a, uint32_t b, uint32_t c) { return FIRST ? (a ^ b ^ c) : seb_xor3(a, b, c); };
     uint32_t cl[5], ch[5], rl[5], rh[5], bl[25], bh[25];
 #pragma unroll
     for (int x = 0; x < 5; x++)
     {
-        cl[x] = seb_xor3(seb_xor3(lo[x], lo[x + 5], lo[x + 10]), lo[x + 15], lo[x + 20]);
-        ch[x] = seb_xor3(seb_xor3(hi[x], hi[x + 5], hi[x + 10]), hi[x + 15], hi[x + 20]);
+        cl[x] = X3(X3(lo[x], lo[x + 5], lo[x + 10]), lo[x + 15], lo[x + 20]);
+        ch[x] = X3(X3(hi[x], hi[x + 5], hi[x + 10]), hi[x + 15], hi[x + 20]);
     }
 #pragma unroll
     for (int x = 0; x < 5; x++) seb_rotl64<1>(cl[x], ch[x], rl[x], rh[x]);
@@ -115,7 +119,8 @@ __device__ __forceinline__ void seb_keccak_round(uint32_t (&lo)[25], uint32_t (&
 // which case the last round is pruned and lanes >= NOUT of `a` are left unspecified.
 // The round loop stays rolled (one round ~190 instructions) so the kernels stay inside the
 // instruction cache; tools/ubench measured no gain from unrolling by 2.
-template <int NOUT = 25>
+// FRESH: `a` comes straight from seb_prng_init (round 0 is specialised on its constant lanes).
+template <int NOUT = 25, bool FRESH = false>
 __device__ __forceinline__ void seb_keccak_f1600(uint64_t (&a)[25])
 {
     constexpr bool PRUNE = NOUT <= 12;
@@ -126,8 +131,9 @@ __device__ __forceinline__ void seb_keccak_f1600(uint64_t (&a)[25])
         lo[i] = (uint32_t)a[i];
         hi[i] = (uint32_t)(a[i] >> 32);
     }
+    if (FRESH) seb_keccak_round<false, true>(lo, hi, 0);
 #pragma unroll 1
-    for (int round = 0; round < (PRUNE ? 23 : 24); round++) seb_keccak_round<false>(lo, hi, round);
+    for (int round = FRESH ? 1 : 0; round < (PRUNE ? 23 : 24); round++) seb_keccak_round<false>(lo, hi, round);
     if (PRUNE) seb_keccak_round<true>(lo, hi, 23);
 #pragma unroll
     for (int i = 0; i < (PRUNE ? 12 : 25); i++) a[i] = ((uint64_t)hi[i] << 32) | lo[i];

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) k_sample_ternary(const uint8_t *__restric
     {
         uint64_t a[25];
         seb_prng_init(a, seed, cbase + (uint64_t)lane);
-        seb_keccak_f1600<12>(a);  // 96 bytes (or 1) are read from each call
+        seb_keccak_f1600<12, true>(a);  // 96 bytes (or 1) are read from each call
         uint32_t m0, m1, m2, packed[6];
         seb_ternary_block(a, packed, m0, m1, m2);
         const uint32_t b0 = (uint32_t)a[0] & 0xFFu;  // value if this counter was a 1-byte redraw
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128) k_sample_ternary_pair(const uint8_t *__re
             seed_of = mine;
         }
         seb_prng_init(a, seed, (uint64_t)count);
-        seb_keccak_f1600<12>(a);  // 96 bytes (or 1) are read from each call
+        seb_keccak_f1600<12, true>(a);  // 96 bytes (or 1) are read from each call
         uint32_t m0, m1, m2, packed[6];
         seb_ternary_block(a, packed, m0, m1, m2);
         const uint32_t b0 = (uint32_t)a[0] & 0xFFu;  // value if this counter was a 1-byte redraw
@@ -297,27 +297,24 @@ __global__ void __launch_bounds__(128) k_sample_ternary_pair(const uint8_t *__re
 //
 // The permutation runs on a bit-interleaved state (seb_keccak.cuh: 174 ALU operations per round instead of 180) because
 // the samples are popcounts and can be taken from the interleaved block as it is.  The 32 threads of a warp serve the
-// same ciphertext (n/16 calls per polynomial is a multiple of 32 for n >= 512), so its seed is split into even and odd
-// bits once per warp - lane i < 8 does seed word i, 16 shuffles hand the halves round - instead of 32 times.
+// same ciphertext, so its seed is split into even and odd bits once per warp - one 32-bit piece per lane, 17 shuffles hand
+// the halves round - instead of 32 times.
+// Grid: x = ciphertext, y = slice of its calls (blockDim.x calls each; the launcher picks a block size that divides
+// n/16 * npoly), so no index is divided and a warp never straddles two ciphertexts.
 __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ seeds,
                                                     const uint32_t *__restrict__ ctr_base,
                                                     int8_t *__restrict__ e_out, int n, int npoly, int batch)
 {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
-    const size_t per_ct = (size_t)npoly * (n / 16);
-    const size_t total  = per_ct * (size_t)batch;
-    const size_t idx    = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live     = idx < total;
-    const size_t idc    = live ? idx : total - 1;  // a partial last warp computes along: the shuffles need every lane
-    const uint32_t b    = (uint32_t)(idc / per_ct);
-    const size_t r      = idc % per_ct;
-    const int lane      = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x;
+    const uint32_t r = blockIdx.y * blockDim.x + threadIdx.x;
+    const int lane   = threadIdx.x & 31;
+    (void)batch;
 
+    // lane = 16 * parity + 8 * (high word) + seed word: every lane compresses ONE 32-bit piece of the seed into 16 bits,
+    // lane L and lane L + 8 make a half lane, and lanes 0..7 / 16..23 end up with the even / odd halves of seed word L & 7
     uint32_t se[8], so[8];
-    if (__all_sync(FULL, b == __shfl_sync(FULL, b, 0)))
     {
-        // lane = 16 * parity + 8 * (high word) + seed word: every lane compresses ONE 32-bit piece into 16 bits, lane L
-        // and lane L + 8 make a half lane, and lanes 0..7 / 16..23 end up with the even / odd halves of seed word L & 7
         const uint32_t piece = __ldg(reinterpret_cast<const uint32_t *>(seeds + (size_t)b * SEB_SEED_BYTES) +
                                      2 * (lane & 7) + ((lane >> 3) & 1));
         const uint32_t v     = seb_half_bits32(piece, lane >> 4);
@@ -325,21 +322,13 @@ __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; i++) se[i] = __shfl_sync(FULL, comb, i), so[i] = __shfl_sync(FULL, comb, 16 + i);
     }
-    else  // a warp across two ciphertexts (degrees below 512): every lane splits its own seed
-    {
-        uint64_t s[8];
-        load_seed(seeds, b, s);
-#pragma unroll
-        for (int i = 0; i < 8; i++) se[i] = seb_half_bits(s[i], 0), so[i] = seb_half_bits(s[i], 1);
-    }
     uint32_t e[25], o[25];
     seb_prng_init_il(e, o, se, so, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
     seb_keccak_f1600_il12(e, o);  // 96 bytes per call
 
     uint32_t out[4];
     seb_cbd_block_il(e, o, out);
-    if (!live) return;
-    uint4 *dst = reinterpret_cast<uint4 *>(e_out + (size_t)b * npoly * n + r * 16);
+    uint4 *dst = reinterpret_cast<uint4 *>(e_out + (size_t)b * npoly * n + (size_t)r * 16);
     *dst       = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
@@ -1022,8 +1011,10 @@ void seb_launch_sample_cbd(const uint8_t *seeds, const uint32_t *ctr_base, int8_
                            int batch, cudaStream_t st)
 {
     if (batch <= 0) return;
-    const size_t total = (size_t)batch * npoly * (n / 16);
-    k_sample_cbd<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(seeds, ctr_base, e_out, n, npoly, batch);
+    const int per_ct  = npoly * (n / 16);  // a multiple of 32: the degrees are powers of two >= 512
+    const int threads = per_ct % 128 == 0 ? 128 : per_ct % 64 == 0 ? 64 : 32;
+    k_sample_cbd<<<dim3((unsigned)batch, (unsigned)(per_ct / threads)), threads, 0, st>>>(seeds, ctr_base, e_out, n, npoly,
+                                                                                         batch);
 }
 
 // fix-up launch: a CTA per ciphertext with one round of ~n/50 + 32 candidates for a handful of ciphertexts (latency),

@@ -361,7 +361,7 @@ extern "C" void emul_ternary_block(const uint8_t *seed, uint64_t ctr, uint32_t *
     uint64_t s[8], a[25];
     memcpy(s, seed, 64);
     seb_prng_init(a, s, ctr);
-    seb_keccak_f1600<12>(a);  // the pruned permutation the samplers use
+    seb_keccak_f1600<12, true>(a);  // the pruned permutation the ternary sampler uses (round 0 specialised)
     uint32_t p[6];
     seb_ternary_block(a, p, mask3[0], mask3[1], mask3[2]);
     memcpy(packed6, p, sizeof p);
