@@ -669,8 +669,12 @@ def run_b200_arm(args) -> None:
                  "issue_bound": {"pipe": "fma", "achieved": ntt_bf, "peak": bfly_peak, "unit": "butterflies/s",
                                  "frac": ntt_bf / bfly_peak if bfly_peak else None}}
     ceilings = {"keccak_f_per_s": keccak_peak, "butterflies_per_s": bfly_peak, "hbm_GBps": peak, "hbm_source": peak_src,
-                "how": "seb_measure_ceilings: register-only Keccak-f[1600] (24 rounds x 180 ALU-pipe operations) and "
-                       "Harvey/Shoup lazy-butterfly loops, best of 3 launches, CUDA events, in this process"}
+                "how": "seb_measure_ceilings: register-only Keccak-f[1600] (24 full rounds x 174 ALU-pipe operations, the "
+                       "bit-interleaved form) and Harvey/Shoup lazy-butterfly loops, best of 3 launches, CUDA events, in "
+                       "this process.  A sampler call runs a SHORTER permutation (round 0 folded on the sponge's constant "
+                       "lanes, last round pruned to the 96 bytes read: ~3930 operations instead of 4176) plus seed split "
+                       "and extraction, so a fraction near 1.0 means the kernel's whole instruction stream runs at the "
+                       "rate of the bare permutation"}
 
     # ---- CPU baseline: the reference's own path on this host's cores, bounded sample
     cpu = None

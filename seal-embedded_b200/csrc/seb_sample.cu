@@ -79,6 +79,7 @@ __device__ __forceinline__ uint32_t seb_nth_set96(uint32_t a0, uint32_t a1, uint
         word = a2, base = 64u, ord -= c0 + c1;
     else if (ord >= c0)
         word = a1, base = 32u, ord -= c0;
+#pragma unroll 1  // trip counts of 0-2: an unrolled loop only adds prologue work
     for (; ord > 0; ord--) word &= word - 1u;  // a block has a handful of rejected bytes (2 in 256): a short loop
     return base + (uint32_t)__ffs(word) - 1u;
 }
@@ -101,36 +102,91 @@ __device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, cons
     const int need_last = __popc(m0) + (vlast > 32 ? __popc(m1) : 0) + (vlast > 64 ? __popc(m2) : 0);
     const uint32_t e0 = w.cm0, e1 = w.cm1, e2 = w.cm2;  // masks of the block carried over from the previous wave
     const int j_in = w.j, cur_in = w.cur, served_in = w.served;
-    // the in-order part only builds two masks: which lanes are blocks, which are redraws that were accepted.
-    // (Stepping from event to event instead - runs of reject-free blocks from a ballot, all redraws of a block with one
-    // __fns - was measured slower, 1.755 vs 1.630 ms: __fns is a software loop.)
-    uint32_t is_blk = 0, is_red = 0;
-    int owner = -1;  // lane of this wave that holds the current block (-1: carried over)
-    for (int i = lo; i < hi; i++)
+    // Which lanes are blocks and which are accepted redraws, WITHOUT walking the lanes one by one (round 2 did, in a
+    // warp-uniform loop of ~14 instructions per lane: a tenth of the kernel).  Every lane answers "if I were a block,
+    // which lane would the next block be?" - the lane after the need-th acceptable redraw above it, found with a
+    // clear-lowest-bit loop of need - 1 steps (0.75 on average) - and the blocks of this wave are the lanes reachable
+    // from the first one by that map: five rounds of pointer doubling, each one warp OR-reduction and one shuffle.
+    auto below_bits = [](int p) { return p >= 32 ? 0xFFFFFFFFu : (1u << p) - 1u; };
+    const uint32_t A = acc & below_bits(hi) & ~below_bits(lo);  // acceptable redraws among this wave's counters
+    // (1) the block carried over from the previous wave takes the first w.need of them
+    int p0 = lo, need_c = 0;  // first lane that can be a block; what the carried block still owes afterwards
+    if (w.need > 0)
     {
-        const uint32_t bit = 1u << i;
-        if (w.need > 0)
+        const int have = __popc(A);
+        if (have < w.need)
+            p0 = 32, need_c = w.need - have;
+        else
         {
-            if (acc & bit)
+            uint32_t t = A;
+#pragma unroll 1
+            for (int k = 1; k < w.need; k++) t &= t - 1u;
+            p0 = __ffs(t);  // the lane after the last redraw it needed
+        }
+    }
+    // (2) the chain of blocks from p0
+    uint32_t is_blk   = 0;
+    const int avail   = nblocks - w.j;
+    if (p0 < hi && avail > 0)
+    {
+        const uint32_t above = A & ~below_bits(lane + 1);
+        int nxt;
+        if (need_full == 0)
+            nxt = lane + 1;
+        else if (__popc(above) < need_full)
+            nxt = 32;
+        else
+        {
+            uint32_t t = above;
+#pragma unroll 1
+            for (int k = 1; k < need_full; k++) t &= t - 1u;
+            nxt = __ffs(t);
+        }
+        if (nxt >= hi) nxt = 32;  // the next block belongs to the next wave
+        is_blk = 1u << p0;
+#pragma unroll
+        for (int round = 0; round < 5; round++)
+        {
+            is_blk |= __reduce_or_sync(FULL, (((is_blk >> lane) & 1u) && nxt < 32) ? 1u << nxt : 0u);
+            const int far = __shfl_sync(FULL, nxt, nxt & 31);
+            nxt           = nxt < 32 ? far : 32;
+        }
+        if (__popc(is_blk) > avail) is_blk &= (1u << __fns(is_blk, 0, avail + 1)) - 1u;  // the ciphertext ends in this wave
+    }
+    // (3) the state after this wave
+    const int nb = __popc(is_blk);
+    int owner    = -1;  // lane of this wave that holds the current block (-1: carried over)
+    int end      = hi;  // counters of [lo, end) are consumed
+    w.j += nb;
+    if (nb > 0)
+    {
+        owner               = 31 - __clz(is_blk);
+        const int n_b       = __shfl_sync(FULL, w.j == nblocks ? need_last : need_full, owner);
+        const uint32_t rest = A & ~below_bits(owner + 1);
+        const int got       = __popc(rest);
+        w.cur               = w.j - 1;
+        if (got >= n_b)
+        {
+            w.need = 0, w.served = n_b;
+            if (w.j == nblocks)  // that was the last block, and it is complete: the walk ends behind its last redraw
             {
-                is_red |= bit;
-                w.served++;
-                w.need--;
+                uint32_t t = rest;
+#pragma unroll 1
+                for (int k = 1; k < n_b; k++) t &= t - 1u;
+                end = n_b == 0 ? owner + 1 : __ffs(t);
             }
         }
-        else if (w.j < nblocks)
-        {
-            w.need   = __shfl_sync(FULL, w.j == nblocks - 1 ? need_last : need_full, i);
-            is_blk |= bit;
-            owner    = i;
-            w.cur    = w.j;
-            w.served = 0;
-            w.j++;
-        }
         else
-            break;
-        w.consumed++;
+            w.need = n_b - got, w.served = got;
     }
+    else
+    {
+        w.served += __popc(A & below_bits(p0));
+        w.need = need_c;
+        if (need_c == 0 && w.j == nblocks) end = p0;  // only redraws of the last block were left
+    }
+    w.consumed += (uint32_t)(end - lo);
+    const uint32_t is_red = A & ~is_blk & below_bits(end);
     // every lane derives its role from the masks: block lanes count the blocks below them; redraw lanes belong to the
     // nearest block below them (or to the carried block) and count the redraws in between
     const uint32_t below = (1u << lane) - 1u;

@@ -239,7 +239,8 @@ cudaError_t seb_launch_unpack30(const uint32_t *in, uint32_t *out, size_t words,
 // in-run integer-issue ceilings (bench.py's roofline for the kernels that are not HBM-bound)
 // ---------------------------------------------------------------------------------------------
 // Register-only loops of the two inner operations of the path, on enough resident warps to saturate the pipes:
-//   k_ceiling_keccak : Keccak-f[1600] exactly as the samplers run it (seb_keccak.cuh: 180 ALU-pipe operations per round)
+//   k_ceiling_keccak : 24 full rounds of Keccak-f[1600] in the cheapest form the samplers use (seb_keccak.cuh, bit-interleaved
+//                      state: 174 ALU-pipe operations per round; the plain form of the ternary / uniform kernels is 180)
 //   k_ceiling_bfly   : Harvey/Shoup lazy butterflies exactly as the NTT passes run them (seb_ntt.cuh: seb_bfly, radix-16
 //                      register groups: IMAD.HI + 2 IMAD on the FMA pipe, 3 operations on the ALU pipe)
 // What they reach IS the ceiling the sampler / NTT kernels are measured against ("frac" of an ALU- or FMA-bound kernel).
@@ -248,15 +249,19 @@ cudaError_t seb_launch_unpack30(const uint32_t *in, uint32_t *out, size_t words,
 
 __global__ void __launch_bounds__(128) k_ceiling_keccak(uint64_t *__restrict__ out, int iters)
 {
-    uint64_t a[25];
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t e[25], o[25];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 25; i++) a[i] = t * 0x9E3779B97F4A7C15ULL + (uint64_t)i;
-    for (int it = 0; it < iters; it++) seb_keccak_f1600(a);
-    uint64_t x = 0;
+    for (int i = 0; i < 25; i++) e[i] = t * 0x9E3779B9u + (uint32_t)i, o[i] = t * 0x7F4A7C15u - (uint32_t)i;
+    for (int it = 0; it < iters; it++)
+    {
+#pragma unroll 1
+        for (int round = 0; round < 24; round++) seb_keccak_round_il<false>(e, o, round);
+    }
+    uint32_t x = 0, y = 0;
 #pragma unroll
-    for (int i = 0; i < 25; i++) x ^= a[i];
-    out[t] = x;
+    for (int i = 0; i < 25; i++) x ^= e[i], y ^= o[i];
+    out[t] = ((uint64_t)y << 32) | x;
 }
 
 __global__ void __launch_bounds__(256) k_ceiling_bfly(uint32_t *__restrict__ out, const seb_oct *__restrict__ tw, uint32_t q,
