@@ -176,7 +176,7 @@ __device__ __forceinline__ void seb_rotl64_il(uint32_t e, uint32_t o, uint32_t &
 }
 
 #define SEB_KECCAK_RP_IL(SRC, DST, ROT)                                                               \
-    if (!PRUNE || (DST) < 14)                                                                         \
+    if ((DST) < NB)                                                                                   \
     {                                                                                                 \
         const uint32_t te_ = X3(e[SRC], ce[((SRC) % 5 + 4) % 5], re[((SRC) % 5 + 1) % 5]);           \
         const uint32_t to_ = X3(o[SRC], co[((SRC) % 5 + 4) % 5], ce[((SRC) % 5 + 1) % 5]);           \
@@ -186,9 +186,13 @@ __device__ __forceinline__ void seb_rotl64_il(uint32_t e, uint32_t o, uint32_t &
 // FIRST: round 0 of a freshly initialised sponge, inlined outside the round loop.  Thirteen of its 25 lanes are zero and
 // two are constants; written with plain operators instead of the opaque LOP3s, the compiler folds them (column parities
 // of two inputs, one theta word for the three empty lanes of a column).
-template <bool PRUNE, bool FIRST = false>
+// KEEP: how many leading lanes of the result are wanted - 25 (a full round), 12 (the last round of a 96-byte call: B lanes
+// 0..13 suffice, 106 operations) or 1 (the last round of a 4-byte call: B lanes 0..2, 37 operations).
+template <int KEEP = 25, bool FIRST = false>
 __device__ __forceinline__ void seb_keccak_round_il(uint32_t (&e)[25], uint32_t (&o)[25], const int round)
 {
+    static_assert(KEEP == 25 || KEEP == 12 || KEEP == 1, "supported prunings");
+    constexpr int NB = KEEP == 25 ? 25 : KEEP == 12 ? 14 : 3;  // B lanes the wanted outputs read
     auto X3 = [](uint32_t a, uint32_t b, uint32_t c) { return FIRST ? (a ^ b ^ c) : seb_xor3(a, b, c); };
     uint32_t ce[5], co[5], re[5], be[25], bo[25];
 #pragma unroll
@@ -211,7 +215,7 @@ __device__ __forceinline__ void seb_keccak_round_il(uint32_t (&e)[25], uint32_t 
     for (int y = 0; y < 25; y += 5)
 #pragma unroll
         for (int x = 0; x < 5; x++)
-            if (!PRUNE || y + x < 12)
+            if (y + x < KEEP)
             {
                 e[y + x] = seb_chi(be[y + x], be[y + (x + 1) % 5], be[y + (x + 2) % 5]);
                 o[y + x] = seb_chi(bo[y + x], bo[y + (x + 1) % 5], bo[y + (x + 2) % 5]);
@@ -224,10 +228,10 @@ __device__ __forceinline__ void seb_keccak_round_il(uint32_t (&e)[25], uint32_t 
 // Keccak-f[1600] on the interleaved state; the last round is pruned to output lanes 0..11 (96 bytes)
 __device__ __forceinline__ void seb_keccak_f1600_il12(uint32_t (&e)[25], uint32_t (&o)[25])
 {
-    seb_keccak_round_il<false, true>(e, o, 0);
+    seb_keccak_round_il<25, true>(e, o, 0);
 #pragma unroll 1
-    for (int round = 1; round < 23; round++) seb_keccak_round_il<false>(e, o, round);
-    seb_keccak_round_il<true>(e, o, 23);
+    for (int round = 1; round < 23; round++) seb_keccak_round_il<25>(e, o, round);
+    seb_keccak_round_il<12>(e, o, 23);
 }
 
 // the even (odd = 0) or odd (odd = 1) bits of a 32-bit word, packed into 16
@@ -264,6 +268,44 @@ __device__ __forceinline__ void seb_prng_init_il(uint32_t (&e)[25], uint32_t (&o
 #pragma unroll
     for (int i = 10; i < 25; i++) e[i] = 0u, o[i] = 0u;
     o[16] = 0x80000000u;  // bit 63
+}
+
+// v = bytes [a0, b0, a1, b1] of two 16-bit values a, b  ->  bit 2i = a_i, bit 2i+1 = b_i: the last three steps of the
+// 32-bit perfect shuffle (the first, a swap of the two middle bytes, is folded into the byte permute that builds v)
+__device__ __forceinline__ uint32_t seb_interleave_tail(uint32_t v)
+{
+    uint32_t t;
+    t = (v ^ (v >> 4)) & 0x00F000F0u;
+    v ^= t ^ (t << 4);
+    t = (v ^ (v >> 2)) & 0x0C0C0C0Cu;
+    v ^= t ^ (t << 2);
+    t = (v ^ (v >> 1)) & 0x22222222u;
+    v ^= t ^ (t << 1);
+    return v;
+}
+
+// LE32 of the first four bytes of SHAKE256(seed || LE64(counter)) - a redraw of the uniform sampler (sample.c:39-57) -
+// from a fresh interleaved sponge: round 0 folded, 22 full rounds, the last one pruned to the one word that is read
+__device__ __forceinline__ uint32_t seb_prng_word_il(const uint32_t (&se)[8], const uint32_t (&so)[8], uint64_t counter)
+{
+    uint32_t e[25], o[25];
+    seb_prng_init_il(e, o, se, so, counter);
+    seb_keccak_round_il<25, true>(e, o, 0);
+#pragma unroll 1
+    for (int round = 1; round < 23; round++) seb_keccak_round_il<25>(e, o, round);
+    seb_keccak_round_il<1>(e, o, 23);
+    return seb_interleave_tail(__byte_perm(e[0], o[0], 0x5140));
+}
+// the seed's eight lanes split into even and odd bits by one thread
+__device__ __forceinline__ void seb_seed_split(const uint8_t *seeds, size_t b, uint32_t (&se)[8], uint32_t (&so)[8])
+{
+    const uint64_t *p = reinterpret_cast<const uint64_t *>(seeds + b * SEB_SEED_BYTES);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        const uint64_t w = __ldg(p + i);
+        se[i] = seb_half_bits(w, 0), so[i] = seb_half_bits(w, 1);
+    }
 }
 
 // SHAKE256 absorb of (seed || LE64(counter)): 72 bytes, domain byte 0x1F at offset 72, final bit

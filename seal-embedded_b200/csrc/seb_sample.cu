@@ -29,6 +29,22 @@ __device__ __forceinline__ void load_seed(const uint8_t *seeds, size_t b, uint64
     for (int i = 0; i < 8; i++) s[i] = __ldg(p + i);
 }
 
+// The seed of ciphertext b split into even and odd bits (seb_keccak.cuh, interleaved state) by a whole warp that serves
+// this one ciphertext: lane = 16 * parity + 8 * (high word) + seed word, every lane compresses ONE 32-bit piece into 16
+// bits, lane L and lane L + 8 make a half lane, lanes 0..7 / 16..23 end up with the even / odd halves of seed word L & 7,
+// and 16 shuffles hand them round.  All 32 lanes must call it.
+__device__ __forceinline__ void seb_seed_split_warp(const uint8_t *seeds, size_t b, const int lane, uint32_t (&se)[8],
+                                                    uint32_t (&so)[8])
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t piece    = __ldg(reinterpret_cast<const uint32_t *>(seeds + b * SEB_SEED_BYTES) + 2 * (lane & 7) +
+                                    ((lane >> 3) & 1));
+    const uint32_t v        = seb_half_bits32(piece, lane >> 4);
+    const uint32_t comb     = __byte_perm(v, __shfl_down_sync(FULL, v, 8), 0x5410);
+#pragma unroll
+    for (int i = 0; i < 8; i++) se[i] = __shfl_sync(FULL, comb, i), so[i] = __shfl_sync(FULL, comb, 16 + i);
+}
+
 // ---------------------------------------------------------------------------------------------
 // raw blocks: out[i][0..136) = first rate block of SHAKE256(seed[b_i] || LE64(ctr_i))
 // ---------------------------------------------------------------------------------------------
@@ -367,17 +383,8 @@ __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ 
     const int lane   = threadIdx.x & 31;
     (void)batch;
 
-    // lane = 16 * parity + 8 * (high word) + seed word: every lane compresses ONE 32-bit piece of the seed into 16 bits,
-    // lane L and lane L + 8 make a half lane, and lanes 0..7 / 16..23 end up with the even / odd halves of seed word L & 7
     uint32_t se[8], so[8];
-    {
-        const uint32_t piece = __ldg(reinterpret_cast<const uint32_t *>(seeds + (size_t)b * SEB_SEED_BYTES) +
-                                     2 * (lane & 7) + ((lane >> 3) & 1));
-        const uint32_t v     = seb_half_bits32(piece, lane >> 4);
-        const uint32_t comb  = __byte_perm(v, __shfl_down_sync(FULL, v, 8), 0x5410);
-#pragma unroll
-        for (int i = 0; i < 8; i++) se[i] = __shfl_sync(FULL, comb, i), so[i] = __shfl_sync(FULL, comb, 16 + i);
-    }
+    seb_seed_split_warp(seeds, (size_t)b, lane, se, so);
     uint32_t e[25], o[25];
     seb_prng_init_il(e, o, se, so, (uint64_t)(ctr_base ? ctr_base[b] : 0u) + r);
     seb_keccak_f1600_il12(e, o);  // 96 bytes per call
@@ -618,19 +625,6 @@ __global__ void __launch_bounds__(128) k_uniform_bulk_coop(const uint8_t *__rest
 // computes, on twice the warps with half the dependency depth.  The squeezed words are de-interleaved with one more
 // exchange and a 4-step perfect shuffle each (the even lane rebuilds the low 32 bits of every rate word, the odd
 // lane the high 32 bits).  Output, reject lists and counters are exactly those of k_uniform_bulk (sample.c:39-57).
-// v = bytes [a0, b0, a1, b1] of two 16-bit values a, b  ->  bit 2i = a_i, bit 2i+1 = b_i: the last three steps of the
-// 32-bit perfect shuffle (the first, a swap of the two middle bytes, is folded into the byte permute that builds v)
-__device__ __forceinline__ uint32_t seb_interleave_tail(uint32_t v)
-{
-    uint32_t t;
-    t = (v ^ (v >> 4)) & 0x00F000F0u;
-    v = v ^ t ^ (t << 4);
-    t = (v ^ (v >> 2)) & 0x0C0C0C0Cu;
-    v = v ^ t ^ (t << 2);
-    t = (v ^ (v >> 1)) & 0x22222222u;
-    v = v ^ t ^ (t << 1);
-    return v;
-}
 
 // theta + rho + pi of word SRC on this lane's half; e = 1 on the even lane, 0 on the odd lane
 #define SEB_PAIR_RP(SRC, DST, ROT)                                                               \
@@ -842,8 +836,8 @@ __device__ __forceinline__ void seb_uniform_fix_warp(const int b, const int lane
                                                      const uint32_t *__restrict__ rej_cnt, uint32_t cap)
 {
     uint32_t *row = out + (size_t)b * ct_stride;
-    uint64_t s[8];
-    load_seed(seeds, (size_t)b, s);
+    uint32_t se[8], so[8];  // every candidate is one permutation on the bit-interleaved state (seb_prng_word_il)
+    seb_seed_split_warp(seeds, (size_t)b, lane, se, so);
 
     const uint64_t c0  = (uint64_t)ctr[b];
     uint64_t wave_base = c0 + 1;  // counter of lane 0's candidate in the next wave to generate
@@ -856,10 +850,7 @@ __device__ __forceinline__ void seb_uniform_fix_warp(const int b, const int lane
         uint32_t done        = 0;  // rejected words already replaced
         while (done < cnt)
         {
-            uint64_t a[25];
-            seb_prng_init(a, s, wave_base + (uint64_t)lane);
-            seb_keccak_f1600<12>(a);  // 4 bytes per call
-            const uint32_t cand  = (uint32_t)a[0];
+            const uint32_t cand  = seb_prng_word_il(se, so, wave_base + (uint64_t)lane);  // 4 bytes per call
             const bool ok        = cand < max_multiple;
             const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
             const uint32_t rank  = done + (uint32_t)__popc(avail & ((1u << lane) - 1u));  // this candidate's turn
@@ -884,10 +875,7 @@ __device__ __forceinline__ void seb_uniform_fix_warp(const int b, const int lane
             {
                 while (avail == 0)
                 {
-                    uint64_t a[25];
-                    seb_prng_init(a, s, wave_base + (uint64_t)lane);
-                    seb_keccak_f1600<12>(a);
-                    cand     = (uint32_t)a[0];
+                    cand     = seb_prng_word_il(se, so, wave_base + (uint64_t)lane);
                     avail    = __ballot_sync(0xFFFFFFFFu, cand < max_multiple);
                     cur_base = wave_base;
                     wave_base += 32;
@@ -942,8 +930,8 @@ __global__ void __launch_bounds__(128) k_uniform_fix_sub(const uint8_t *__restri
     const uint32_t gmask = (L == 32 ? 0xFFFFFFFFu : ((1u << L) - 1u)) << (group * L);
     const uint32_t below = gmask & ((1u << lane) - 1u);
 
-    uint64_t s[8];
-    load_seed(seeds, (size_t)(live ? b : b0), s);
+    uint32_t se[8], so[8];
+    seb_seed_split(seeds, (size_t)(live ? b : b0), se, so);
     const uint64_t c0    = live ? (uint64_t)ctr[b] : 0ull;
     uint64_t wave_base   = c0 + 1;  // counter of this group's first candidate in the next wave
     uint64_t last_used   = c0;
@@ -953,10 +941,7 @@ __global__ void __launch_bounds__(128) k_uniform_fix_sub(const uint8_t *__restri
     uint32_t done        = 0;
     while (__any_sync(0xFFFFFFFFu, done < want))
     {
-        uint64_t a[25];
-        seb_prng_init(a, s, wave_base + (uint64_t)sub);
-        seb_keccak_f1600<12>(a);  // 4 bytes per call
-        const uint32_t cand  = (uint32_t)a[0];
+        const uint32_t cand  = seb_prng_word_il(se, so, wave_base + (uint64_t)sub);  // 4 bytes per call
         const bool ok        = done < want && cand < max_multiple;
         const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
         const uint32_t rank  = done + (uint32_t)__popc(avail & below);  // this candidate's turn within its ciphertext
@@ -1000,8 +985,8 @@ __global__ void __launch_bounds__(512) k_uniform_fix_wide(const uint8_t *__restr
     }
     uint32_t *row        = out + (size_t)b * ct_stride;
     const uint16_t *list = rej_idx + (size_t)b * cap;
-    uint64_t s[8];
-    load_seed(seeds, (size_t)b, s);
+    uint32_t se[8], so[8];
+    seb_seed_split_warp(seeds, (size_t)b, lane, se, so);
     const uint32_t c0  = ctr[b];
     uint32_t wave_base = c0 + 1;  // counter of thread 0's candidate in the next round
     uint32_t done      = 0;
@@ -1009,10 +994,7 @@ __global__ void __launch_bounds__(512) k_uniform_fix_wide(const uint8_t *__restr
     __syncthreads();  // ctr[b] is read by everybody before thread 0 overwrites it at the end
     while (done < cnt)
     {
-        uint64_t a[25];
-        seb_prng_init(a, s, (uint64_t)wave_base + (uint64_t)tid);
-        seb_keccak_f1600<12>(a);  // 4 bytes per call
-        const uint32_t cand  = (uint32_t)a[0];
+        const uint32_t cand  = seb_prng_word_il(se, so, (uint64_t)wave_base + (uint64_t)tid);  // 4 bytes per call
         const bool ok        = cand < max_multiple;
         const uint32_t avail = __ballot_sync(0xFFFFFFFFu, ok);
         if (lane == 0) s_count[warp] = (uint32_t)__popc(avail);

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) k_ceiling_keccak(uint64_t *__restrict__ o
     for (int it = 0; it < iters; it++)
     {
 #pragma unroll 1
-        for (int round = 0; round < 24; round++) seb_keccak_round_il<false>(e, o, round);
+        for (int round = 0; round < 24; round++) seb_keccak_round_il<25>(e, o, round);
     }
     uint32_t x = 0, y = 0;
 #pragma unroll

@@ -403,12 +403,22 @@ extern "C" void emul_cbd_block_plain(const uint8_t *seed, uint64_t ctr, uint32_t
     memcpy(out4, o, sizeof o);
 }
 
+// a 4-byte redraw of the uniform sampler the way the fix-up kernels compute it
+extern "C" uint32_t emul_prng_word_il(const uint8_t *seed, uint64_t ctr)
+{
+    uint64_t s[8];
+    memcpy(s, seed, 64);
+    uint32_t se[8], so[8];
+    for (int i = 0; i < 8; i++) se[i] = seb_half_bits(s[i], 0), so[i] = seb_half_bits(s[i], 1);
+    return seb_prng_word_il(se, so, ctr);
+}
+
 // one full interleaved permutation against the plain one: state in / state out as 64-bit lanes
 extern "C" void emul_keccak_il(uint64_t *a25)
 {
     uint32_t e[25], o[25];
     for (int i = 0; i < 25; i++) e[i] = seb_half_bits(a25[i], 0), o[i] = seb_half_bits(a25[i], 1);
-    for (int round = 0; round < 24; round++) seb_keccak_round_il<false>(e, o, round);
+    for (int round = 0; round < 24; round++) seb_keccak_round_il<25>(e, o, round);
     for (int i = 0; i < 25; i++)
     {
         uint64_t w = 0;

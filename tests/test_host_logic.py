@@ -65,6 +65,8 @@ def E(emul):
     emul.emul_cbd_block.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
     emul.emul_cbd_block_plain.argtypes = [C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint32)]
     emul.emul_keccak_il.argtypes = [C.POINTER(C.c_uint64)]
+    emul.emul_prng_word_il.argtypes = [C.POINTER(C.c_uint8), C.c_uint64]
+    emul.emul_prng_word_il.restype = C.c_uint32
     emul.emul_ternary_block_raw.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     emul.emul_mod3_bytes.argtypes = [C.c_uint32]
     emul.emul_mod3_bytes.restype = C.c_uint32
@@ -351,6 +353,15 @@ def test_keccak_bit_interleaved(E):
         E.emul_keccak(a)
         E.emul_keccak_il(b)
         assert list(a) == list(b)
+
+
+def test_prng_word_interleaved(E, oracle_mod):
+    """A 4-byte PRNG call through the interleaved sponge with round 0 folded and the last round pruned to one word."""
+    seeds = oracle_mod.make_seeds(16, b"w0")
+    for i in range(16):
+        for ctr in (0, 1, 77 + i, 0xFFFF, 0x12345678, 0xFFFFFFFF, (1 << 32) + 5, (1 << 63) + 12345):
+            want = struct.unpack("<I", hashlib.shake_256(seeds[i].tobytes() + struct.pack("<Q", ctr)).digest(4))[0]
+            assert E.emul_prng_word_il(_p(seeds[i], C.c_uint8), ctr) == want
 
 
 def test_mod3_bytes_exhaustive(E):
