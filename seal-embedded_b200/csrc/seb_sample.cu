@@ -402,6 +402,82 @@ __global__ void __launch_bounds__(128) k_sample_cbd(const uint8_t *__restrict__ 
 // stored already reduced mod q (< q <= max_multiple); rejected words are stored raw
 // (>= max_multiple) and their indices appended, in ascending order, to the ciphertext's reject list
 // (rej_idx[b][0..cap), rej_cnt[b] = how many there were, which may exceed cap).
+// A value the compiler must keep in a register: it otherwise re-reads the modulus constants from the parameter bank in
+// front of every use (68 LDC per block of 34 words), and at the batch sizes where this kernel runs ONE in-order warp per
+// SM sub-partition every instruction is an issue slot of the sequential sponge.
+__device__ __forceinline__ uint32_t seb_pin(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
+// One word of the squeeze in six instructions: v = x >= max_multiple ? x (raw, for the fix-up) : x mod q, and the word's
+// bit ORed into the reject mask under the same predicate.  Spelled in PTX because the compiler turns the predicated OR
+// into a select and an add, and `x - hi * q` into a negation and a multiply-add (negq = -q avoids it).
+template <uint32_t BIT>
+__device__ __forceinline__ uint32_t seb_uniform_word(const uint32_t x, const uint32_t negq, const uint32_t q,
+                                                     const uint32_t ratio, const uint32_t max_multiple, uint32_t &mask)
+{
+    const uint32_t red = seb_csub(__umulhi(x, ratio) * negq + x, q);  // seb_barrett32
+    uint32_t v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %2, %3;\n\t@p or.b32 %0, %0, %5;\n\tselp.b32 %1, %2, %4, p;\n\t}"
+        : "+r"(mask), "=r"(v)
+        : "r"(x), "r"(max_multiple), "r"(red), "n"(BIT));
+    return v;
+}
+template <int K>
+struct SebUniformLanes  // rate lanes K..16 of a full block, unrolled by recursion (BIT must be a constant expression)
+{
+    __device__ __forceinline__ static void run(const uint32_t (&lo)[25], const uint32_t (&hi)[25], uint2 *__restrict__ dst,
+                                               const uint32_t negq, const uint32_t q, const uint32_t ratio,
+                                               const uint32_t mm, uint32_t &m0, uint32_t &m1)
+    {
+        uint32_t &m       = K < 16 ? m0 : m1;
+        constexpr int sh  = K < 16 ? 2 * K : 0;
+        const uint32_t vl = seb_uniform_word<(1u << sh)>(lo[K], negq, q, ratio, mm, m);
+        const uint32_t vh = seb_uniform_word<(2u << sh)>(hi[K], negq, q, ratio, mm, m);
+        dst[K]            = make_uint2(vl, vh);
+        if constexpr (K < 16) SebUniformLanes<K + 1>::run(lo, hi, dst, negq, q, ratio, mm, m0, m1);
+    }
+};
+
+// the 34 words of one rate block (m0 bit 2k / 2k+1: low / high word of rate lane k rejected; m1: lane 16): a full block
+// without per-lane bound checks, or the tail of nk < 17 lanes in plain C
+template <bool FULL_BLOCK>
+__device__ __forceinline__ void seb_uniform_block(const uint32_t (&lo)[25], const uint32_t (&hi)[25], const int nk,
+                                                  uint2 *__restrict__ dst, const uint32_t negq, const uint32_t q,
+                                                  const uint32_t ratio, const uint32_t max_multiple, uint32_t &m0,
+                                                  uint32_t &m1)
+{
+    // Branch-free over the 17 rate lanes (rejections are 2 % of the words: a branch per word costs more than the
+    // work it skips); the rejected words of the block are collected in a bit mask and listed afterwards.
+    m0 = 0, m1 = 0;
+    if constexpr (FULL_BLOCK)
+        SebUniformLanes<0>::run(lo, hi, dst, negq, q, ratio, max_multiple, m0, m1);
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 17; k++)
+        {
+            const bool in = k < nk;
+            const bool rl = in && lo[k] >= max_multiple, rh = in && hi[k] >= max_multiple;
+            if (k < 16)
+            {
+                if (rl) m0 |= 1u << (2 * k);
+                if (rh) m0 |= 2u << (2 * k);
+            }
+            else
+            {
+                if (rl) m1 |= 1u;
+                if (rh) m1 |= 2u;
+            }
+            const uint32_t tl = __umulhi(lo[k], ratio) * negq + lo[k], th = __umulhi(hi[k], ratio) * negq + hi[k];
+            const uint32_t vl = rl ? lo[k] : seb_csub(tl, q), vh = rh ? hi[k] : seb_csub(th, q);
+            if (in) dst[k] = make_uint2(vl, vh);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__ seeds,
                                                       const uint32_t *__restrict__ ctr, uint32_t *__restrict__ out,
                                                       size_t ct_stride, int n, SebModulus mod,
@@ -411,9 +487,15 @@ __global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
-    uint64_t s[8], a[25];
-    load_seed(seeds, (size_t)b, s);
-    seb_prng_init(a, s, (uint64_t)ctr[b]);
+    uint32_t lo[25], hi[25];  // the state as 32-bit halves throughout: no repacking between permutation and squeeze
+    {
+        uint64_t s[8], a[25];
+        load_seed(seeds, (size_t)b, s);
+        seb_prng_init(a, s, (uint64_t)ctr[b]);
+#pragma unroll
+        for (int i = 0; i < 25; i++) lo[i] = (uint32_t)a[i], hi[i] = (uint32_t)(a[i] >> 32);
+    }
+    const uint32_t q = seb_pin(mod.q), negq = seb_pin(0u - mod.q), ratio = seb_pin(mod.ratio_hi), mm = seb_pin(max_multiple);
     uint2 *dst     = reinterpret_cast<uint2 *>(out + (size_t)b * ct_stride);
     uint16_t *list = rej_idx + (size_t)b * cap;
     uint32_t cnt   = 0;
@@ -421,25 +503,13 @@ __global__ void __launch_bounds__(32) k_uniform_bulk(const uint8_t *__restrict__
     int left       = n / 2;  // 64-bit lanes still to emit
     while (left > 0)
     {
-        seb_keccak_f1600(a);
-        // Branch-free over the 17 rate lanes (rejections are 2 % of the words: a branch per word costs more than the
-        // work it skips); the rejected words of the block are collected in a bit mask and listed afterwards.
-        const int nk = min(17, left);
-        uint32_t m0 = 0, m1 = 0;  // bit 2k / 2k+1: low / high word of rate lane k rejected (m1: lane 16)
-#pragma unroll
-        for (int k = 0; k < 17; k++)
-        {
-            const uint32_t lo = (uint32_t)a[k], hi = (uint32_t)(a[k] >> 32);
-            const bool in = k < nk;
-            const bool rl = in && lo >= max_multiple, rh = in && hi >= max_multiple;
-            const uint32_t bits = (rl ? 1u : 0u) | (rh ? 2u : 0u);
-            if (k < 16)
-                m0 |= bits << (2 * k);
-            else
-                m1 = bits;
-            const uint32_t vl = rl ? lo : seb_barrett32(lo, mod), vh = rh ? hi : seb_barrett32(hi, mod);
-            if (in) dst[k] = make_uint2(vl, vh);
-        }
+#pragma unroll 1
+        for (int round = 0; round < 24; round++) seb_keccak_round<false>(lo, hi, round);
+        uint32_t m0, m1;
+        if (left >= 17)
+            seb_uniform_block<true>(lo, hi, 17, dst, negq, q, ratio, mm, m0, m1);
+        else
+            seb_uniform_block<false>(lo, hi, left, dst, negq, q, ratio, mm, m0, m1);
         while (m0)
         {
             const int bit = __ffs(m0) - 1;

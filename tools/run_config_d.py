@@ -1,12 +1,13 @@
 """Configuration D's per-GPU shard (n = 16384, 6 primes, symmetric, 16384 items), two calls: the workload of the ncu
-captures of the symmetric path.  argv[1] = 1 forces the two-lane uniform sampler (k_uniform_bulk_pair)."""
+captures of the symmetric path.  argv[1] = 1 forces the two-lane uniform sampler (k_uniform_bulk_pair), -1 leaves the
+choice to the library; argv[2..4] = n, primes, batch of another symmetric configuration (B-sym: 4096 3 65536)."""
 import importlib, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.environ.get("GRAFT_REPO_ROOT", "/root/repo"))
 seb = importlib.import_module("seal-embedded_b200")
-n, np_, batch = 16384, 6, 16384
+n, np_, batch = (int(v) for v in sys.argv[2:5]) if len(sys.argv) >= 5 else (16384, 6, 16384)
 ctx = seb.Context(n, np_, asym=False, device=0)
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and int(sys.argv[1]) >= 0:
     ctx.set_option("uniform_pair", int(sys.argv[1]))
 rng = np.random.default_rng(1)
 t = rng.integers(0, 3, (n // 4, 4), dtype=np.uint8)
