@@ -627,6 +627,7 @@ extern "C" int seb_set_option(seb_ctx *c, const char *name, long value)
     else if (!strcmp(name, "uniform_spec")) c->knobs.uniform_spec = v;
     else if (!strcmp(name, "uniform_pair")) c->knobs.uniform_pair = v;
     else if (!strcmp(name, "uniform_fix_lanes")) c->knobs.uniform_fix_lanes = v;
+    else if (!strcmp(name, "uniform_fix_stream")) c->knobs.uniform_fix_stream = v;
     else if (!strcmp(name, "host_chunk")) c->knobs.host_chunk = value < 0 ? 0 : value;
     else return fail(SE_ERR_INVALD_ARGUMENT, "unknown option '%s'", name);
     return 0;

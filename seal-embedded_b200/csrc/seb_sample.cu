@@ -1032,6 +1032,93 @@ __global__ void __launch_bounds__(128) k_uniform_fix_sub(const uint8_t *__restri
     }
 }
 
+// The fix-up as a STREAM: one warp serves K consecutive ciphertexts, and a wave's 32 candidates go to the current
+// ciphertext only as far as it still has rejected words to fill - the lanes behind them already draw the first
+// candidates of the next ciphertext.  A warp per ciphertext (k_uniform_fix) computes whole waves, so a ciphertext that
+// needs 76 +- 9 candidates (n = 4096, 30-bit primes) pays for 96 and one that needs 250 (n = 16384) for 270-290; here
+// the only partly used wave is the last one of the K-th ciphertext.  Candidates of ciphertext b are still
+// LE32(X(seed_b, c0 + 1 + t, 4)), t = 0, 1, ... consumed in order (sample.c:39-57); candidates drawn beyond the last one
+// consumed are dropped, the counter continues behind the last one consumed.
+template <int K>
+__global__ void __launch_bounds__(128) k_uniform_fix_stream(const uint8_t *__restrict__ seeds, uint32_t *__restrict__ ctr,
+                                                            uint32_t *__restrict__ out, size_t ct_stride, int n,
+                                                            SebModulus mod, uint32_t max_multiple, int batch,
+                                                            const uint16_t *__restrict__ rej_idx,
+                                                            const uint32_t *__restrict__ rej_cnt, uint32_t cap)
+{
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    const int lane  = threadIdx.x & 31;
+    const int first = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * K;
+    if (first >= batch) return;
+    const int last = min(first + K, batch);  // ciphertexts [first, last)
+    const uint32_t below = (1u << lane) - 1u;
+
+    // A = the ciphertext being filled, B = the one behind it (bB == last: none)
+    int bA = first, bB = first;
+    uint32_t seA[8], soA[8], seB[8], soB[8];
+    uint32_t cntA = 0, doneA = 0, cntB = 0, doneB = 0;
+    uint64_t baseA = 0, lastA = 0, baseB = 0, lastB = 0;  // next candidate's counter, counter of the last one consumed
+    // fetches the ciphertext behind B into B; overflowed reject lists (never with SHAKE output and cap = n/8, but it must
+    // stay correct) are served on the spot by the scanning path and skipped
+    auto fetch = [&](int from) {
+        int b = from;
+        while (b < last)
+        {
+            const uint32_t c = rej_cnt[b];
+            if (c <= cap)
+            {
+                cntB = c, doneB = 0;
+                lastB = (uint64_t)ctr[b], baseB = lastB + 1;
+                seb_seed_split_warp(seeds, (size_t)b, lane, seB, soB);
+                break;
+            }
+            seb_uniform_fix_warp(b, lane, seeds, ctr, out, ct_stride, n, mod, max_multiple, rej_idx, rej_cnt, cap);
+            b++;
+        }
+        bB = b;
+    };
+    auto shift = [&]() {  // B becomes A
+        bA = bB, cntA = cntB, doneA = doneB, baseA = baseB, lastA = lastB;
+#pragma unroll
+        for (int i = 0; i < 8; i++) seA[i] = seB[i], soA[i] = soB[i];
+        fetch(bB + 1);
+    };
+    fetch(first);
+    shift();
+    while (bA < last)
+    {
+        if (doneA == cntA)  // warp-uniform: A is served (or had nothing rejected)
+        {
+            __syncwarp();
+            if (lane == 0) ctr[bA] = (uint32_t)(lastA + 1);
+            shift();
+            continue;
+        }
+        const uint32_t s   = min(32u, cntA - doneA);                       // lanes [0, s) draw for A
+        const uint32_t nB  = bB < last ? min(32u - s, cntB - doneB) : 0u;  // lanes [s, s + nB) for B
+        const bool forA    = (uint32_t)lane < s;
+        const bool forB    = !forA && (uint32_t)lane < s + nB;
+        uint32_t se[8], so[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) se[i] = forA ? seA[i] : seB[i], so[i] = forA ? soA[i] : soB[i];
+        const uint64_t counter = forA ? baseA + (uint64_t)lane : baseB + (uint64_t)((uint32_t)lane - s);
+        const uint32_t cand    = seb_prng_word_il(se, so, counter);  // 4 bytes per call
+        const bool ok          = cand < max_multiple;
+        const uint32_t okA     = __ballot_sync(FULL, ok && forA), okB = __ballot_sync(FULL, ok && forB);
+        // every accepted candidate is consumed: A's s lanes never exceed what A still needs, nor do B's nB
+        if (ok && forA)
+            (out + (size_t)bA * ct_stride)[(rej_idx + (size_t)bA * cap)[doneA + (uint32_t)__popc(okA & below)]] =
+                seb_barrett32(cand, mod);
+        if (ok && forB)
+            (out + (size_t)bB * ct_stride)[(rej_idx + (size_t)bB * cap)[doneB + (uint32_t)__popc(okB & below)]] =
+                seb_barrett32(cand, mod);
+        if (okA) lastA = baseA + (uint64_t)(31 - __clz(okA));
+        if (okB) lastB = baseB + (uint64_t)(31 - __clz(okB)) - (uint64_t)s;
+        doneA += (uint32_t)__popc(okA), baseA += s;
+        doneB += (uint32_t)__popc(okB), baseB += nB;
+    }
+}
+
 // The fix-up for a handful of ciphertexts: one CTA per ciphertext, every thread one candidate, so that the ~n/50
 // candidates a polynomial needs come out of ONE round of permutations instead of n/1600 dependent 32-candidate
 // waves (10 at n = 16384: 69 us of a lone call's 85 us per prime).  Ranks are counted across the CTA (ballot per
@@ -1157,8 +1244,41 @@ static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t
             k_uniform_fix_sub<8><<<(batch + 15) / 16, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
                                                                     rej_cnt, rej_cap);
         else
-            k_uniform_fix<<<(batch + 3) / 4, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
-                                                           rej_cnt, rej_cap);
+        {
+            // Ciphertexts per warp of the streamed form: the one partly used wave is shared by K of them, but the warps
+            // must still fill the machine - 2048 warps of 8 ciphertexts (configuration D's 16384-item shard) ran 5 %
+            // SLOWER than 16384 warps of one (3.5 warps per sub-partition, no balancing left).  So the largest K that keeps
+            // >= 12 warps per SM sub-partition; below that for K = 2, a warp per ciphertext.  And only where the unused
+            // half wave is a sizeable part of a ciphertext's candidates: at ~250 of them (n = 16384) the streamed form's
+            // own overhead (two seeds per wave, more registers) cancels the 3 % it saves - 34.06 against 33.96 ms for
+            // configuration D - while at ~76 (n = 4096) it takes 4 % off the whole symmetric step.
+            // knobs.uniform_fix_stream forces K = 8 (1) or the plain form (0).
+            const int sms      = knobs.sms > 0 ? knobs.sms : 148;
+            const int min_warps = 12 * 4 * sms;
+            int K = 1;
+            if (knobs.uniform_fix_stream >= 0)
+                K = knobs.uniform_fix_stream ? 8 : 1;
+            else if (expect <= 160.0)
+                for (int k = 8; k >= 2; k >>= 1)
+                    if (batch / k >= min_warps)
+                    {
+                        K = k;
+                        break;
+                    }
+            const int blocks = ((batch + K - 1) / K + 3) / 4;
+            if (K == 8)
+                k_uniform_fix_stream<8><<<blocks, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                                rej_cnt, rej_cap);
+            else if (K == 4)
+                k_uniform_fix_stream<4><<<blocks, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                                rej_cnt, rej_cap);
+            else if (K == 2)
+                k_uniform_fix_stream<2><<<blocks, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx,
+                                                                rej_cnt, rej_cap);
+            else
+                k_uniform_fix<<<blocks, 128, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch, rej_idx, rej_cnt,
+                                                      rej_cap);
+        }
     }
 }
 

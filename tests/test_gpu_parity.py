@@ -225,21 +225,25 @@ def test_sampler_uniform_pair_kernel(n, np_, batch, seb, torch_cuda, oracle_mod,
         assert ctr[b] == c
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 32])
-@pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3)])
+@pytest.mark.parametrize("lanes", [4, 8, 32, "stream"])
+@pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (16384, 2)])
 def test_sampler_uniform_fixup_lanes(n, np_, lanes, seb, torch_cuda, oracle_mod, orc, ctxs):
     """The fix-up with 4 / 8 / 32 lanes per ciphertext (k_uniform_fix_sub / k_uniform_fix, forced with the
-    "uniform_fix_lanes" option): same polynomials and counters as sample_poly_uniform (sample.c:39-57) whether a
-    ciphertext's rejected words are served in one wave (n = 1024: ~1.5 of them) or in twenty (n = 4096 with 4 lanes),
-    for a batch that leaves the last warp partly empty."""
+    "uniform_fix_lanes" option) and as a stream over 8 ciphertexts per warp (k_uniform_fix_stream, "uniform_fix_stream"):
+    same polynomials and counters as sample_poly_uniform (sample.c:39-57) whether a ciphertext's rejected words are
+    served in one wave (n = 1024: ~1.5 of them), in twenty (n = 4096 with 4 lanes) or by lanes of waves it shares with
+    its neighbours, for a batch that leaves the last warp partly empty."""
     torch = torch_cuda
+    if n == 16384 and lanes in (4, 8):
+        pytest.skip("hundreds of dependent small waves: covered at n = 4096")
     ctx = ctxs(n, np_, False)
     batch = 45
     seeds = oracle_mod.make_seeds(batch, b"uniform-lanes-%d" % n)
     d_seeds = dev(torch, seeds)
     d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
     d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
-    ctx.set_option("uniform_fix_lanes", lanes)
+    ctx.set_option("uniform_fix_lanes", 32 if lanes == "stream" else lanes)
+    ctx.set_option("uniform_fix_stream", 1 if lanes == "stream" else 0)
     ctx.set_option("uniform_fix_wide", 0)
     try:
         for p in range(np_):
@@ -247,6 +251,7 @@ def test_sampler_uniform_fixup_lanes(n, np_, lanes, seb, torch_cuda, oracle_mod,
         torch.cuda.synchronize()
     finally:
         ctx.set_option("uniform_fix_lanes", -1)
+        ctx.set_option("uniform_fix_stream", -1)
         ctx.set_option("uniform_fix_wide", -1)
     out = host(d_out, np.uint32).reshape(batch, np_, n)
     ctr = host(d_ctr, np.uint32)
