@@ -286,17 +286,21 @@ def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert ctr[b] == c
 
 
-@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("wide", ["0", "1", "stream"])
 @pytest.mark.parametrize("cap", ["0", "3", "70"])
 def test_sampler_uniform_list_overflow(cap, wide, seb, torch_cuda, oracle_mod, orc, monkeypatch):
     """The uniform sampler's reject lists have a fixed capacity; ciphertexts that overflow it take the
     scanning fix-up.  Forced here with tiny capacities (none / most / some ciphertexts overflow at
-    n = 4096, where ~76 of 4096 words are rejected per prime) and through the full symmetric path."""
+    n = 4096, where ~76 of 4096 words are rejected per prime) and through the full symmetric path, for the
+    warp-per-ciphertext, the CTA-per-ciphertext and the streamed fix-up (which serves overflowed ciphertexts on the
+    spot, between the ones it streams)."""
     torch = torch_cuda
     monkeypatch.setenv("SEB_UNIFORM_LIST_CAP", cap)
-    monkeypatch.setenv("SEB_UNIFORM_FIX_WIDE", wide)
-    n, np_, batch = 4096, 3, 7
+    monkeypatch.setenv("SEB_UNIFORM_FIX_WIDE", "1" if wide == "1" else "0")
+    n, np_, batch = 4096, 3, 7 if wide != "stream" else 21
     ctx = seb.Context(n, np_, False, device=0)
+    if wide == "stream":
+        ctx.set_option("uniform_fix_stream", 1)
     try:
         seeds = oracle_mod.make_seeds(batch, b"uniform-cap")
         d_seeds = dev(torch, seeds)
