@@ -419,7 +419,10 @@ def run_b200_arm(args) -> None:
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     seb = importlib.import_module("seal-embedded_b200")
     # before any pinned allocation: run next to this rank's GPU (matters for e2e at N > 1)
-    numa = seb.bind_to_gpu_numa(local) if world > 1 else "not bound (single rank)"
+    # (at N = 1 too: a pinned buffer on the far socket costs the D2H copy 10-15 % on a two-socket host; the original
+    # mask is restored before the CPU baselines, which want every core)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = seb.bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -679,6 +682,8 @@ def run_b200_arm(args) -> None:
     # ---- CPU baseline: the reference's own path on this host's cores, bounded sample
     cpu = None
     cpu_others = None
+    if all_cpus is not None and world == 1:
+        os.sched_setaffinity(0, all_cpus)
     if world == 1 and not args.no_cpu:
         arm = CpuArm(items_per_worker=256)
         arm.step()
