@@ -286,6 +286,39 @@ def test_sampler_uniform(n, np_, seb, torch_cuda, oracle_mod, orc, ctxs):
         assert ctr[b] == c
 
 
+@pytest.mark.parametrize("n", [1024, 4096, 16384])
+def test_sampler_uniform_row_alignment(n, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """The bulk squeeze writes each polynomial with 64-bit stores into rows that are only 8-byte aligned in general (rows at
+    an odd multiple of 8 bytes, every other row with a stride of 4k + 2 words), and nothing outside them; a batch above
+    the warp-cooperative kernel's range so that the thread-per-sponge kernel runs.  n / 2 lanes are 30 full blocks + 2
+    lanes at n = 1024, 120 + 8 at n = 4096, 481 + 15 at n = 16384."""
+    torch = torch_cuda
+    ctx = ctxs(n, 1, False)
+    batch = 1500
+    seeds = oracle_mod.make_seeds(batch, b"uniform-align-%d" % n)
+    d_seeds = dev(torch, seeds)
+    ctx.set_option("uniform_coop", 0)
+    ctx.set_option("uniform_pair", 0)
+    try:
+        for offset, stride in ((0, n), (2, n + 2), (0, n + 2), (2, n + 4)):
+            d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+            d_buf = torch.full((batch * stride + 8,), -1, dtype=torch.int32, device="cuda")
+            ctx.sample_uniform_device(d_seeds, d_ctr, 0, batch, d_buf.data_ptr() + 4 * offset, stride)
+            torch.cuda.synchronize()
+            buf = host(d_buf, np.uint32)
+            rows = buf[offset:offset + batch * stride].reshape(batch, stride)
+            for b in list(range(0, batch, 97)) + [1, batch - 1]:
+                exp, c = orc.sample_uniform(n, ctx.primes[0], seeds[b], 0)
+                assert np.array_equal(rows[b, :n], exp), (n, offset, stride, b)
+                assert int(host(d_ctr, np.uint32)[b]) == c
+            # nothing outside the rows was touched
+            assert np.all(rows[:, n:] == 0xFFFFFFFF) and np.all(buf[:offset] == 0xFFFFFFFF)
+            assert np.all(buf[offset + batch * stride:] == 0xFFFFFFFF)
+    finally:
+        ctx.set_option("uniform_coop", -1)
+        ctx.set_option("uniform_pair", -1)
+
+
 @pytest.mark.parametrize("wide", ["0", "1", "stream"])
 @pytest.mark.parametrize("cap", ["0", "3", "70"])
 def test_sampler_uniform_list_overflow(cap, wide, seb, torch_cuda, oracle_mod, orc, monkeypatch):
