@@ -24,7 +24,7 @@ struct SebKnobs
     int uniform_spec     = -1;  // speculative prime chain for lone calls
     int uniform_pair     = -1;  // bulk squeeze by two lanes per sponge (bit-interleaved halves)
     int uniform_fix_lanes = -1; // fix-up lanes per ciphertext: 4, 8 or 32 (-1: by the expected number of rejections)
-    int uniform_fix_stream = -1; // the 32-lane fix-up as a stream over 8 ciphertexts per warp (-1: 2-8 by batch size, or not)
+    int uniform_fix_stream = -1; // the 32-lane fix-up as a stream over 2 / 4 / 8 ciphertexts per warp (2, 4, other > 0; 0: off; -1: by batch size)
     long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
     int sms              = 0;   // SM count of the context's device (kernel selection by machine fill; not an option)
 };

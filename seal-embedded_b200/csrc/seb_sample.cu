@@ -1261,12 +1261,14 @@ static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t
             // half wave is a sizeable part of a ciphertext's candidates: at ~250 of them (n = 16384) the streamed form's
             // own overhead (two seeds per wave, more registers) cancels the 3 % it saves - 34.06 against 33.96 ms for
             // configuration D - while at ~76 (n = 4096) it takes 4 % off the whole symmetric step.
-            // knobs.uniform_fix_stream forces K = 8 (1) or the plain form (0).
+            // knobs.uniform_fix_stream forces K = 2 / 4 / 8 (2, 4, any other positive value) or the plain form (0).
             const int sms      = knobs.sms > 0 ? knobs.sms : 148;
             const int min_warps = 12 * 4 * sms;
             int K = 1;
             if (knobs.uniform_fix_stream >= 0)
-                K = knobs.uniform_fix_stream ? 8 : 1;
+                K = knobs.uniform_fix_stream == 2 || knobs.uniform_fix_stream == 4 ? knobs.uniform_fix_stream
+                    : knobs.uniform_fix_stream                                     ? 8
+                                                                                   : 1;
             else if (expect <= 160.0)
                 for (int k = 8; k >= 2; k >>= 1)
                     if (batch / k >= min_warps)

@@ -225,7 +225,7 @@ def test_sampler_uniform_pair_kernel(n, np_, batch, seb, torch_cuda, oracle_mod,
         assert ctr[b] == c
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 32, "stream"])
+@pytest.mark.parametrize("lanes", [4, 8, 32, "stream2", "stream4", "stream"])
 @pytest.mark.parametrize("n,np_", [(1024, 1), (2048, 1), (4096, 3), (16384, 2)])
 def test_sampler_uniform_fixup_lanes(n, np_, lanes, seb, torch_cuda, oracle_mod, orc, ctxs):
     """The fix-up with 4 / 8 / 32 lanes per ciphertext (k_uniform_fix_sub / k_uniform_fix, forced with the
@@ -242,8 +242,9 @@ def test_sampler_uniform_fixup_lanes(n, np_, lanes, seb, torch_cuda, oracle_mod,
     d_seeds = dev(torch, seeds)
     d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
     d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
-    ctx.set_option("uniform_fix_lanes", 32 if lanes == "stream" else lanes)
-    ctx.set_option("uniform_fix_stream", 1 if lanes == "stream" else 0)
+    stream = {"stream": 8, "stream2": 2, "stream4": 4}.get(lanes, 0)  # ciphertexts per warp of the streamed form
+    ctx.set_option("uniform_fix_lanes", 32 if stream else lanes)
+    ctx.set_option("uniform_fix_stream", stream)
     ctx.set_option("uniform_fix_wide", 0)
     try:
         for p in range(np_):
