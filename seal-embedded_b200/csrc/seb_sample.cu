@@ -66,8 +66,8 @@ __global__ void k_prng_blocks(const uint8_t *__restrict__ seeds, const uint64_t 
 // ---------------------------------------------------------------------------------------------
 // One warp per ciphertext.  The sampler's PRNG counter walk is sequential (block j+1's counter
 // depends on how many redraws blocks <= j needed), but X(seed,c,96) and X(seed,c,1) are the same
-// SHAKE stream, so the warp computes 32 consecutive counters' streams per wave and then walks
-// them in order, deciding per counter whether it was a 96-byte block or a 1-byte redraw.
+// SHAKE stream, so the warp computes 32 consecutive counters' streams per wave and then decides,
+// in the reference's order, which counter was a 96-byte block and which a 1-byte redraw (seb_tern_walk).
 // ---------------------------------------------------------------------------------------------
 // the same sampler, TWO ciphertexts per warp sharing the last wave (n = 4096)
 // ---------------------------------------------------------------------------------------------
@@ -100,13 +100,13 @@ __device__ __forceinline__ uint32_t seb_nth_set96(uint32_t a0, uint32_t a1, uint
     return base + (uint32_t)__ffs(word) - 1u;
 }
 
-// Walk the counters held by lanes [lo, hi) of this wave, in order (sample.c:223-241: a counter is a 96-byte block, or a
-// 1-byte redraw owed to the block before it).  The in-order part is a lean, warp-uniform loop that only ASSIGNS roles -
-// "lane i is block j" / "lane i is the k-th redraw of block j" - from a ballot of the acceptable redraw bytes and one
-// shuffle per block (its number of rejected bytes); the data moves afterwards in parallel: block lanes store their 24
-// packed bytes, redraw lanes look up the k-th rejected position in their block's masks and OR their two bits in.
-// (Round 1 did both in the loop: a shared-memory byte update by lane 0 per redraw, three shuffles and six predicated
-// stores per block - a quarter of the kernel's instructions.)
+// Resolve the counters held by lanes [lo, hi) of this wave in the reference's order (sample.c:223-241: a counter is a
+// 96-byte block, or a 1-byte redraw owed to the block before it).  Two steps: (1) ROLES - "lane i is block j" / "lane i is
+// the k-th redraw of block j" - from a ballot of the acceptable redraw bytes and each lane's number of rejected bytes, by
+// pointer doubling over "next block" links (see inside); (2) DATA, in parallel: block lanes store their 24 packed bytes,
+// redraw lanes look up the k-th rejected position in their block's masks and write their two bits there.
+// (Round 1 walked the lanes one by one and moved the data in the same loop - a shared-memory byte update by lane 0 per
+// redraw, three shuffles and six predicated stores per block: a quarter of the kernel's instructions.)
 __device__ __forceinline__ void seb_tern_walk(SebTernWalk &w, const int lo, const int hi, const int lane, const int n,
                                               const int nblocks, uint32_t *usm, const uint32_t (&packed)[6],
                                               const uint32_t m0, const uint32_t m1, const uint32_t m2, const uint32_t b0)
