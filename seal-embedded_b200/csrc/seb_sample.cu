@@ -1256,21 +1256,21 @@ static void seb_launch_uniform_fix(const uint8_t *seeds, uint32_t *ctr, uint32_t
         {
             // Ciphertexts per warp of the streamed form: the one partly used wave is shared by K of them, but the warps
             // must still fill the machine - 2048 warps of 8 ciphertexts (configuration D's 16384-item shard) ran 5 %
-            // SLOWER than 16384 warps of one (3.5 warps per sub-partition, no balancing left).  So the largest K that keeps
-            // >= 12 warps per SM sub-partition; below that for K = 2, a warp per ciphertext.  And only where the unused
-            // half wave is a sizeable part of a ciphertext's candidates: at ~250 of them (n = 16384) the streamed form's
-            // own overhead (two seeds per wave, more registers) cancels the 3 % it saves - 34.06 against 33.96 ms for
-            // configuration D - while at ~76 (n = 4096) it takes 4 % off the whole symmetric step.
+            // SLOWER than 16384 warps of one (3.5 warps per sub-partition, no balancing left).  profiles/
+            // r02_ab_fix_stream.txt: the best K is the largest of 8 / 4 that keeps ~7 warps per SM sub-partition (K = 2
+            // never pays), and only where the unused half wave is a sizeable part of a ciphertext's candidates: at ~76
+            // of them (n = 4096) the streamed form takes 4 % off the whole sampler at 65536 items, at ~150 (n = 8192)
+            // 1.5 %, at ~250 (n = 16384) nothing - its own overhead (two seeds per wave, more registers) cancels it.
             // knobs.uniform_fix_stream forces K = 2 / 4 / 8 (2, 4, any other positive value) or the plain form (0).
             const int sms      = knobs.sms > 0 ? knobs.sms : 148;
-            const int min_warps = 12 * 4 * sms;
+            const int min_warps = 6 * 4 * sms;
             int K = 1;
             if (knobs.uniform_fix_stream >= 0)
                 K = knobs.uniform_fix_stream == 2 || knobs.uniform_fix_stream == 4 ? knobs.uniform_fix_stream
                     : knobs.uniform_fix_stream                                     ? 8
                                                                                    : 1;
             else if (expect <= 160.0)
-                for (int k = 8; k >= 2; k >>= 1)
+                for (int k = 8; k >= 4; k >>= 1)
                     if (batch / k >= min_warps)
                     {
                         K = k;

@@ -8,21 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 seb = importlib.import_module("seal-embedded_b200")
 
-def run(ctx, stream, n, np_, batch):
-    gen = torch.Generator(device="cuda").manual_seed(3)
-    d_ss = torch.randint(0, 256, (batch, 64), generator=gen, device="cuda", dtype=torch.uint8)
-    d_out = torch.empty((batch, np_, n), dtype=torch.int32, device="cuda")
-    d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
-    def step():
-        d_ctr.zero_()
-        for p in range(np_):
-            ctx.sample_uniform_device(d_ss, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
-    step(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(3): step()
-    e1.record(stream); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / 3, int(d_out.view(-1)[::1031].to(torch.int64).sum().item()) ^ int(d_ctr.to(torch.int64).sum().item())
+from tools.ab_uniform_pair_run import run  # noqa: E402
 
 quick = "--quick" in sys.argv
 for n, np_ in ((4096, 3), (16384, 6)) if quick else ((1024, 1), (4096, 3), (8192, 4), (16384, 6)):
