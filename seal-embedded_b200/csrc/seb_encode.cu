@@ -112,16 +112,22 @@ __global__ void __launch_bounds__((1 << LOGN) / CL / ENC_E, EncOcc<LOGN, CL>::MI
         const double *ore = cluster.map_shared_rank(sre, rank ^ 1u);
         const double *oim = cluster.map_shared_rank(sim, rank ^ 1u);
         const double2 s   = __ldg(tw + 1);
-        // (one element per iteration: issuing eight elements' remote loads before the first use, and skipping the
-        // imaginary parts on rank 0, measured 3.09 against 3.00 ms - the wait ncu shows on the first use of a partner
-        // element is the partner not having arrived yet, not the latency of the load)
-        for (uint32_t k = t; k < (uint32_t)NL; k += T)
+        // Each CTA finishes BOTH outputs (k and k + n/2) for half of the positions k - rank r takes k in [r NL/2,
+        // (r+1) NL/2) - instead of one output for all of them: u is rank 0's element k, v is rank 1's, so a CTA reads
+        // NL/2 partner elements instead of NL (a third less traffic through distributed shared memory, the slowest
+        // access of the kernel).  One element per iteration: issuing eight elements' remote loads before the first use
+        // measured slower (3.09 against 3.00 ms).
+        for (uint32_t k = rank * (NL / 2) + t; k < (rank + 1) * (uint32_t)(NL / 2); k += T)
         {
             double ar, ai, br, bi;
             enc_ld(sre, sim, k, ar, ai);
             enc_ld(ore, oim, k, br, bi);
-            const double re = enc_cross_re(rank, ar, ai, br, bi, s);
-            dst[pos0 + k] = enc_finish(re, n_inv, bad, mx);
+            // own = (ar, ai), partner = (br, bi); rank 0 holds u, rank 1 holds v
+            const double ur = rank == 0 ? ar : br, ui = rank == 0 ? ai : bi;
+            const double vr = rank == 0 ? br : ar, vi = rank == 0 ? bi : ai;
+            dst[k]      = enc_finish(__dadd_rn(ur, vr), n_inv, bad, mx);  // Re(u + v)
+            const double dr = __dsub_rn(ur, vr), di = __dsub_rn(ui, vi);  // u - v
+            dst[NL + k] = enc_finish(__dsub_rn(__dmul_rn(dr, s.x), __dmul_rn(di, s.y)), n_inv, bad, mx);  // Re((u - v) s)
         }
         // the partner may still be reading our shared memory: an execution barrier is enough (its loads have returned by
         // the time it arrives - their values went into its stores), so no release/acquire fence here
