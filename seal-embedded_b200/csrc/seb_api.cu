@@ -220,6 +220,7 @@ struct seb_ctx
     // resident tables
     seb_oct *d_roots    = nullptr;  // [np][seb_table_octs(logn)]: per-pass twiddle tables, 16-coefficient plan (asymmetric kernel)
     seb_oct *d_roots1   = nullptr;  // the same roots in the plan of the one-polynomial kernels (= d_roots below n = 8192)
+    seb_oct *d_roots_sym = nullptr;  // ... in the form the symmetric kernel reads (= d_roots1 except at n = 16384: split form)
     int key1 = 0;                   // seb_ntt_key1(logn)
     double2 *d_tw       = nullptr;  // [n] natural order + [7][n/8] pass-0 copies (seb_encode.cuh)
     uint16_t *d_src_map = nullptr;  // [n]
@@ -376,6 +377,9 @@ static int build_tables(seb_ctx *c)
     // re-ordered per pass into the layout the kernels read with coalesced 256-bit loads
     c->key1 = seb_ntt_key1(c->logn);
     const size_t octs = seb_table_octs(c->logn), octs1 = seb_table_octs(c->key1);
+    const size_t octs_sym = seb_table_octs_sym(c->logn);
+    std::vector<seb_oct> tabs_sym(seb_sym_split(c->logn) ? c->np * octs_sym : 0);
+    if (!tabs_sym.empty()) memset(tabs_sym.data(), 0, tabs_sym.size() * sizeof(seb_oct));
     std::vector<seb_oct> tabs(c->np * octs), tabs1(c->key1 != c->logn ? c->np * octs1 : 0);
     memset(tabs.data(), 0, tabs.size() * sizeof(seb_oct));
     if (!tabs1.empty()) memset(tabs1.data(), 0, tabs1.size() * sizeof(seb_oct));
@@ -391,6 +395,7 @@ static int build_tables(seb_ctx *c)
         }
         seb_host_build_tw(c->logn, roots.data(), tabs.data() + p * octs);
         if (!tabs1.empty()) seb_host_build_tw(c->key1, roots.data(), tabs1.data() + p * octs1);
+        if (!tabs_sym.empty()) seb_host_build_tw_sym(c->logn, roots.data(), tabs_sym.data() + p * octs_sym);
     }
     CU(cudaMalloc(&c->d_roots, tabs.size() * sizeof(seb_oct)));
     CU(cudaMemcpy(c->d_roots, tabs.data(), tabs.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
@@ -400,6 +405,13 @@ static int build_tables(seb_ctx *c)
     {
         CU(cudaMalloc(&c->d_roots1, tabs1.size() * sizeof(seb_oct)));
         CU(cudaMemcpy(c->d_roots1, tabs1.data(), tabs1.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
+    }
+    if (tabs_sym.empty())
+        c->d_roots_sym = c->d_roots1;
+    else
+    {
+        CU(cudaMalloc(&c->d_roots_sym, tabs_sym.size() * sizeof(seb_oct)));
+        CU(cudaMemcpy(c->d_roots_sym, tabs_sym.data(), tabs_sym.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
     }
 
     // inverse roots for the verifier's INTT: iroots[bitrev(i)] = psi^-i, and n^-1
@@ -580,6 +592,7 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaDeviceSynchronize();
     free_scratch(c->dev, c->n);
     for (auto &s : c->hslot) free_scratch(s, c->n);
+    if (c->d_roots_sym != c->d_roots1) cudaFree(c->d_roots_sym);
     if (c->d_roots1 != c->d_roots) cudaFree(c->d_roots1);
     cudaFree(c->d_roots);
     cudaFree(c->d_tw);
@@ -639,7 +652,7 @@ extern "C" double seb_scale(const seb_ctx *c) { return c ? c->scale : 0; }
 extern "C" uint32_t seb_prime(const seb_ctx *c, size_t i) { return (c && i < c->np) ? c->primes[i] : 0; }
 extern "C" uint64_t seb_launch_count(const seb_ctx *c) { return c ? c->launches : 0; }
 
-// key: the plan whose epilogue order the table is laid out in (logn for pk0/pk1, key1 for ntt(s))
+// key: the plan whose epilogue order the table is laid out in (logn for pk0/pk1); < 0: the symmetric kernel's order (ntt(s))
 static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst, int key)
 {
     std::vector<uint2> nat(c->n);
@@ -652,7 +665,10 @@ static int upload_shoup(seb_ctx *c, const uint32_t *host, seb_oct **dst, int key
             if (w >= c->primes[p]) return fail(SE_ERR_INVALD_ARGUMENT, "key coefficient %u >= modulus", w);
             nat[i] = make_uint2(w, shoup(w, c->primes[p]));
         }
-        seb_host_build_epi(key, nat.data(), tab.data() + p * (c->n / 4));
+        if (key < 0)  // the symmetric kernel's order
+            seb_host_build_epi_sym(c->logn, nat.data(), tab.data() + p * (c->n / 4));
+        else
+            seb_host_build_epi(key, nat.data(), tab.data() + p * (c->n / 4));
     }
     if (!*dst) CU(cudaMalloc(dst, tab.size() * sizeof(seb_oct)));
     CU(cudaMemcpy(*dst, tab.data(), tab.size() * sizeof(seb_oct), cudaMemcpyHostToDevice));
@@ -704,7 +720,7 @@ extern "C" int seb_set_secret_key(seb_ctx *c, const uint8_t *sk)
     if (e == cudaSuccess) e = cudaMemcpy(s.data(), d, s.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     wipe_free(d, s.size() * sizeof(uint32_t));
     if (e != cudaSuccess) return fail(SE_ERR_CUDA, "ntt(s): %s", cudaGetErrorString(e));
-    int r = upload_shoup(c, s.data(), &c->d_ntt_s, c->key1);
+    int r = upload_shoup(c, s.data(), &c->d_ntt_s, -1);
     if (r) return r;
     if (!c->d_ntt_s_nat) CU(cudaMalloc(&c->d_ntt_s_nat, s.size() * sizeof(uint32_t)));
     CU(cudaMemcpy(c->d_ntt_s_nat, s.data(), s.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -800,7 +816,7 @@ extern "C" int seb_gen_public_key(seb_ctx *c, const uint8_t *sk_packed, const ui
                            c->mods.m[p], 1, d_rej, d_small + 2, cap, c->knobs, st);
     }
     CUK(cudaGetLastError());
-    CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots1, c->d_ntt_s, c->mods,
+    CUK(seb_launch_encrypt_sym(c->logn, d_pt, d_small, reinterpret_cast<int8_t *>(d_e), c->d_roots_sym, c->d_ntt_s, c->mods,
                                (int)np, d_out + n, d_out, 2 * np * n, 2 * n, 0, 1, st));
     c->launches += 2 + 2 * np;
     std::vector<uint32_t> out(2 * np * n);
@@ -1074,7 +1090,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     prof_mark(c, st, 2);
     if ((r = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, st))) return r;
     prof_mark(c, st, 3);
-    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots1, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
+    CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots_sym, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
                               ct_stride, p_stride, seedct ? 0 : quirk, (int)batch, st));
     prof_mark(c, st, 4);
     prof_next(c, st);

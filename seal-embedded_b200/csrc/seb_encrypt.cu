@@ -75,6 +75,17 @@ __device__ __forceinline__ size_t seb_item() { return (size_t)blockIdx.z * gridD
 // 512-thread CTAs per SM and measures 46.4 % against 48.0 % (profiles/r02_ubench_ntt_plans.txt).  The
 // three-polynomial asymmetric kernel keeps 16 everywhere (3 x 32 values do not fit the register file at any useful
 // occupancy).
+// The SYMMETRIC kernel at n = 16384 runs in the SPLIT form (SEB_SYM14_SPLIT, k_encrypt_sym_split): stage 0 is folded into
+// the LOAD (each CTA of a pair reads the inputs at i and i + n/2 and keeps its own output of that butterfly, so the one
+// multiplication of stage 0 is done twice), after which the two halves are independent 8192-point transforms on the plan
+// of n = 8192 (key 29) with their own root tables: no remote stores, no release/acquire cluster barrier.  5.66 -> 5.50 ms
+// for configuration D's shard.  The NTT-only kernel keeps the 2-CTA cluster form (plan key 30): split, it reads every
+// input twice and measured 49.9 % of the HBM peak against 51.8 %.
+#ifndef SEB_SYM14_SPLIT
+#define SEB_SYM14_SPLIT 1
+#endif
+#define SEB_SPLIT1(logn) (SEB_SYM14_SPLIT && (logn) == 14)
+#define SEB_KEY_SPLIT(logn) SEB_NTT_KEY32((logn) - 1)
 #define SEB_KEY1(logn) ((logn) >= 13 ? SEB_NTT_KEY32(logn) : (logn))
 // ... and at n = 16384 the 512 threads of that plan run as a CLUSTER of two 256-thread CTAs, each holding half of the
 // polynomial in its shared memory (seb_ntt.cuh, "two-CTA cluster form"): four resident CTAs per SM instead of two.
@@ -339,6 +350,95 @@ __global__ void __launch_bounds__(NttCfg<K>::T / CL, (K == SEB_NTT_KEY32(13) ? 3
 }
 
 // ---------------------------------------------------------------------------------------------
+// the SPLIT form of the one-polynomial kernels: a polynomial of 2 * 2^LOGN(K) coefficients as two CTAs
+// ---------------------------------------------------------------------------------------------
+// Stage 0 of the forward transform pairs x[i] with x[i + n/2] under ONE root (roots[1]) and leaves two independent
+// half-size transforms; half r uses, at its local stage s and group j, the root roots[2^(s+1) + r 2^s + j] of the full
+// table (ntt.c:124-166 with the bit-reversed table of ntt.c:40-52).  CTA r = blockIdx.x & 1 loads both inputs of every
+// stage-0 butterfly of its half, keeps output r and runs plan K on it with the table of half r.
+// Table of a prime: [octs(K) of half 0][octs(K) of half 1][one oct whose first two words are roots[1] and its Shoup word].
+template <class Inner>
+struct LoadSplit
+{
+    Inner in;  // the loader of the full polynomial (positions 0 .. 2 NH)
+    uint32_t nh, rank, q, two_q;
+    uint2 w0;
+    __device__ __forceinline__ uint32_t operator()(int poly, uint32_t pos) const
+    {
+        uint32_t a = in(poly, pos), b = in(poly, pos + nh);
+        seb_bfly(a, b, w0, q, two_q);
+        return rank ? b : a;
+    }
+};
+
+// symmetric encrypt in the split form: inputs (pt, e) and outputs (c0; a is read and, with the quirk, rewritten at the
+// thread's own positions) are different buffers, so the two CTAs of a polynomial do not have to meet at all
+template <int K>
+__global__ void __launch_bounds__(NttCfg<K>::T, 3)
+    k_encrypt_sym_split(const int64_t *__restrict__ pt, const uint32_t *__restrict__ mag, const int8_t *__restrict__ e,
+                        const seb_oct *__restrict__ roots, const seb_oct *__restrict__ ntt_s,
+                        const __grid_constant__ SebModuli mods, uint32_t *a_base, uint32_t *c0_base, size_t ct_stride,
+                        size_t p_stride, int quirk, size_t batch)
+{
+    constexpr int NH = 1 << NttCfg<K>::LOGN, N = 2 * NH;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t    = threadIdx.x;
+    const size_t b = seb_item();
+    if (b >= batch) return;
+    const int p         = (int)(blockIdx.x >> 1);
+    const uint32_t rank = blockIdx.x & 1u;
+    const SebModulus m  = mods.m[p];
+    const seb_oct *tab  = roots + (size_t)p * (2 * NttTwSize<K>::OCTS + 1);
+    const seb_oct w0o   = seb_ldg256(tab + 2 * NttTwSize<K>::OCTS);
+    const uint2 w0      = make_uint2(w0o.v[0], w0o.v[1]);
+    const seb_oct *tw   = tab + (size_t)rank * NttTwSize<K>::OCTS;
+
+    uint32_t x[1][NttCfg<K>::E];
+    if (__ldg(mag + b) < m.two_q - SEB_E_BOUND)  // uniform over the ciphertext, see k_encrypt_asym
+    {
+        LoadSplit<LoadSym<true>> ld{LoadSym<true>{e + b * N, pt + b * N, m}, (uint32_t)NH, rank, m.q, m.two_q, w0};
+        seb_ntt_first<K, 1, LoadSplit<LoadSym<true>>, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    else
+    {
+        LoadSplit<LoadSym<false>> ld{LoadSym<false>{e + b * N, pt + b * N, m}, (uint32_t)NH, rank, m.q, m.two_q, w0};
+        seb_ntt_first<K, 1, LoadSplit<LoadSym<false>>, 1>(x, smem, t, tw, m.q, m.two_q, ld);
+    }
+    seb_ntt_rest<K, 1, 1>(x, smem, t, tw, m.q, m.two_q);
+
+    using O           = NttOut<K>;
+    uint32_t *c0      = c0_base + b * ct_stride + (size_t)p * p_stride + rank * NH;
+    uint32_t *c1      = a_base + b * ct_stride + (size_t)p * p_stride + rank * NH;
+    const seb_oct *sk = ntt_s + (size_t)p * (N / 4) + (size_t)rank * (NH / 4);
+#pragma unroll
+    for (int i = 0; i < O::GPL; i++)
+#pragma unroll
+        for (int k = 0; k < O::RUN / 8; k++)
+        {
+            const uint32_t pos = O::pos(t, i) + 8 * k;
+            const int r        = i * O::RUN + 8 * k;
+            const uint4 a0     = *reinterpret_cast<const uint4 *>(c1 + pos);
+            const uint4 a1     = *reinterpret_cast<const uint4 *>(c1 + pos + 4);
+            const uint32_t av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            seb_oct cv, mv;
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+            {
+                const seb_oct s = seb_ldg256(sk + seb_epi_index<K>(t, i, 2 * k + h));
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                {
+                    cv.v[4 * h + c] = mul_sub_final(av[4 * h + c], make_uint2(s.v[2 * c], s.v[2 * c + 1]), x[0][r + 4 * h + c],
+                                                    m.q, m.two_q);
+                    if (quirk) mv.v[4 * h + c] = seb_final_reduce(x[0][r + 4 * h + c], m.q, m.two_q);
+                }
+            }
+            seb_stg256_stream(reinterpret_cast<seb_oct *>(c0 + pos), cv);
+            if (quirk) seb_stg256_stream(reinterpret_cast<seb_oct *>(c1 + pos), mv);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 // grid (np, items) folded into three dimensions: x = prime (fastest, so one item's primes are
@@ -374,6 +474,7 @@ static inline dim3 seb_grid(int np, size_t items)
     }
 
 int seb_ntt_key1(int logn) { return SEB_KEY1(logn); }
+int seb_sym_split(int logn) { return SEB_SPLIT1(logn) ? 1 : 0; }
 
 size_t seb_table_octs(int key)
 {
@@ -397,6 +498,48 @@ void seb_host_build_epi(int key, const uint2 *natural, seb_oct *out)
 #undef BUILD
 }
 
+// The tables of the SYMMETRIC kernel of degree 2^logn: the per-pass root table of a prime from its bit-reversed roots, and
+// ntt(s) in epilogue order.  They are those of plan seb_ntt_key1(logn), except in the split form (seb_sym_split), where
+// both are two half-size tables on the plan of the half (see k_encrypt_sym_split).
+size_t seb_table_octs_sym(int logn)
+{
+    return SEB_SPLIT1(logn) ? 2 * seb_table_octs(SEB_KEY_SPLIT(logn)) + 1 : seb_table_octs(SEB_KEY1(logn));
+}
+void seb_host_build_tw_sym(int logn, const uint2 *roots_bitrev, seb_oct *out)
+{
+    if (!SEB_SPLIT1(logn))
+    {
+        seb_host_build_tw(SEB_KEY1(logn), roots_bitrev, out);
+        return;
+    }
+    const int key = SEB_KEY_SPLIT(logn), lh = logn - 1;
+    const size_t nh = (size_t)1 << lh, o = seb_table_octs(key);
+    uint2 *half = new uint2[nh];
+    for (int r = 0; r < 2; r++)
+    {
+        half[0] = roots_bitrev[0];  // never read: a transform starts at roots[1]
+        for (int s = 0; s < lh; s++)
+            for (size_t j = 0; j < ((size_t)1 << s); j++)
+                half[((size_t)1 << s) + j] = roots_bitrev[((size_t)2 << s) + ((size_t)r << s) + j];
+        seb_host_build_tw(key, half, out + (size_t)r * o);
+    }
+    delete[] half;
+    seb_oct w0 = {};
+    w0.v[0] = roots_bitrev[1].x, w0.v[1] = roots_bitrev[1].y;
+    out[2 * o] = w0;
+}
+void seb_host_build_epi_sym(int logn, const uint2 *natural, seb_oct *out)
+{
+    if (!SEB_SPLIT1(logn))
+    {
+        seb_host_build_epi(SEB_KEY1(logn), natural, out);
+        return;
+    }
+    const size_t nh = (size_t)1 << (logn - 1);
+    for (int r = 0; r < 2; r++)
+        seb_host_build_epi(SEB_KEY_SPLIT(logn), natural + (size_t)r * nh, out + (size_t)r * (nh / 4));
+}
+
 // shared memory of one CTA of a one-polynomial kernel
 template <int K, int CL>
 static constexpr size_t seb_smem1() { return 4 * (size_t)(CL == 2 ? NttSmemHalf<K>::WORDS : NttSmem<K>::WORDS); }
@@ -415,6 +558,9 @@ cudaError_t seb_encrypt_configure(int logn)
     }
     SEB_DISPATCH_LOGN(logn, CFG)
 #undef CFG
+    if (err == cudaSuccess && SEB_SPLIT1(logn))
+        err = cudaFuncSetAttribute(k_encrypt_sym_split<SEB_KEY_SPLIT(14)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)seb_smem1<SEB_KEY_SPLIT(14), 1>());
     return err;
 }
 
@@ -469,13 +615,22 @@ cudaError_t seb_launch_encrypt_asym(int logn, const int64_t *pt, const uint32_t 
     return cudaGetLastError();
 }
 
-// roots / ntt_s: the tables of plan seb_ntt_key1(logn)
+// roots / ntt_s: the symmetric kernel's tables (seb_host_build_tw_sym / seb_host_build_epi_sym)
 cudaError_t seb_launch_encrypt_sym(int logn, const int64_t *pt, const uint32_t *mag, const int8_t *e, const seb_oct *roots,
                                    const seb_oct *ntt_s, const SebModuli &mods, int np, uint32_t *a, uint32_t *c0,
                                    size_t ct_stride, size_t p_stride, int quirk, int batch, cudaStream_t st)
 {
     if (batch <= 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
+    if (SEB_SPLIT1(logn))  // n = 16384: two independent CTAs per (ciphertext, prime), each on the plan of n = 8192
+    {
+        constexpr int KS = SEB_KEY_SPLIT(14);
+        dim3 grid        = seb_grid(np, (size_t)batch);
+        grid.x *= 2;
+        k_encrypt_sym_split<KS><<<grid, NttCfg<KS>::T, seb_smem1<KS, 1>(), st>>>(pt, mag, e, roots, ntt_s, mods, a, c0, ct_stride,
+                                                                                p_stride, quirk, (size_t)batch);
+        return cudaGetLastError();
+    }
 #define RUN(L)                                                                                                       \
     {                                                                                                                \
         constexpr int K1 = SEB_KEY1(L), C1 = SEB_CLUSTER1(L) ? 2 : 1;                                                \

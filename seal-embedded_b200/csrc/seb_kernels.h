@@ -78,6 +78,12 @@ void seb_host_build_enc_tw0(size_t n, double2 *tw);  // tw[0..n) filled on entry
 // roots: per prime, the per-pass twiddle tables of seb_build_tw (seb_table_octs(key) octs each);
 // pk0s/pk1s (key = logn) and ntt_s (key = seb_ntt_key1(logn)): per prime, n/4 octs in the epilogue order of seb_build_epi
 int seb_ntt_key1(int logn);
+// the symmetric kernel's own tables: those of plan seb_ntt_key1(logn), except where it runs as two half-size transforms
+// per polynomial (seb_sym_split: n = 16384)
+int seb_sym_split(int logn);
+size_t seb_table_octs_sym(int logn);  // octs per prime of its root table
+void seb_host_build_tw_sym(int logn, const uint2 *roots_bitrev, seb_oct *out);
+void seb_host_build_epi_sym(int logn, const uint2 *natural, seb_oct *out);  // n coefficients (ntt(s)) in its epilogue order
 size_t seb_table_octs(int key);
 void seb_host_build_tw(int key, const uint2 *roots_bitrev, seb_oct *out);
 void seb_host_build_epi(int key, const uint2 *natural, seb_oct *out);
