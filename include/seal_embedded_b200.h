@@ -169,8 +169,10 @@ void seb_destroy(seb_ctx *ctx);
 uint32_t seb_minimal_psi(size_t n, uint32_t q);
 /* name in {"uniform_coop", "uniform_fix_wide", "uniform_spec", "uniform_pair"}: 0 / 1 force a code path, a negative
  * value restores the automatic choice; "uniform_fix_lanes": 4, 8 or 32 lanes per ciphertext in the uniform sampler's
- * fix-up; "uniform_fix_stream": 2 / 4 / 8 ciphertexts per warp in its streamed form (0: off); "host_chunk": items per
- * chunk of the host-pointer pipeline (<= 0: automatic). */
+ * fix-up; "uniform_fix_stream": 2 / 4 / 8 ciphertexts per warp in its streamed form (0: off); "sym_partition": 0 / 1 the
+ * symmetric path with its sampler chain and its encode / CBD work on disjoint SM partitions (CUDA green contexts; by
+ * itself for batches of ~16k items at n >= 8192), "sym_side_percent": the share of the batch whose encode / CBD run on
+ * the side partition; "host_chunk": items per chunk of the host-pointer pipeline (<= 0: automatic). */
 int seb_set_option(seb_ctx *ctx, const char *name, long value);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own */
 int seb_set_stream(seb_ctx *ctx, void *cuda_stream);

@@ -12,6 +12,8 @@
 
 #include <vector>
 
+#include <cuda.h>  // driver types for the SM partition (green contexts); its functions are fetched at run time
+
 #include "../../include/seal_embedded_b200.h"
 #include "seb_kernels.h"
 
@@ -216,6 +218,13 @@ struct seb_ctx
     uint32_t psis[SEB_MAX_PRIMES]   = {0};
     SebModuli mods;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // SM partition for the symmetric path's latency-bound regime (seb_partition_*): two green contexts, the sampler
+    // chain's and the side work's, each with a stream; created on first use, `part_state` -1 = unavailable
+    int part_state = 0;
+    CUgreenCtx part_ctx[2] = {nullptr, nullptr};
+    cudaStream_t part_stream[2] = {nullptr, nullptr};
+    cudaEvent_t part_ev[3] = {nullptr, nullptr, nullptr};
+    int part_sms[2] = {0, 0};
     uint32_t rej_cap = 0;  // capacity of the uniform sampler's per-ciphertext reject lists (n/8)
     // resident tables
     seb_oct *d_roots    = nullptr;  // [np][seb_table_octs(logn)]: per-pass twiddle tables, 16-coefficient plan (asymmetric kernel)
@@ -585,6 +594,102 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
     return c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// SM partition (CUDA green contexts)
+// ---------------------------------------------------------------------------------------------
+// A symmetric batch of ~16k items at a large degree spends two thirds of its time in the uniform sampler's bulk squeeze:
+// one sequential sponge per (ciphertext, prime), ONE warp per SM sub-partition, and nothing else can share those
+// sub-partitions without stretching the chain (profiles/README.md: every co-residency experiment lost).  But 512 such
+// warps occupy 128 SMs; the other SMs idle for the whole chain.  The device is therefore split into two green contexts -
+// SEB_PART_SIDE_SMS SMs on the side, the rest for the chain - and while the chain runs on the big partition, the encode and
+// the CBD sampler of a share of the batch run on the side partition, where they disturb nobody.  The driver entry points
+// are fetched with cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda; if anything is
+// missing the path simply stays serial.
+#define SEB_PART_SIDE_SMS 16
+typedef CUresult (*pfn_cuDeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType);
+typedef CUresult (*pfn_cuDevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *,
+                                                    unsigned int, unsigned int);
+typedef CUresult (*pfn_cuDevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*pfn_cuGreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int);
+typedef CUresult (*pfn_cuGreenCtxDestroy)(CUgreenCtx);
+typedef CUresult (*pfn_cuDeviceGet)(CUdevice *, int);
+
+template <class F>
+static bool seb_driver_fn(const char *name, F *fn)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    *fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+static void seb_partition_destroy(seb_ctx *c)
+{
+    for (cudaEvent_t &e : c->part_ev)
+        if (e) cudaEventDestroy(e), e = nullptr;
+    for (cudaStream_t &s : c->part_stream)
+        if (s) cudaStreamDestroy(s), s = nullptr;
+    pfn_cuGreenCtxDestroy destroy = nullptr;
+    if ((c->part_ctx[0] || c->part_ctx[1]) && seb_driver_fn("cuGreenCtxDestroy", &destroy))
+        for (CUgreenCtx &g : c->part_ctx)
+            if (g) destroy(g), g = nullptr;
+    c->part_state = 0;
+}
+
+// true when the partition exists (created on the first call); never fails the caller
+static bool seb_partition_ready(seb_ctx *c)
+{
+    if (c->part_state) return c->part_state > 0;
+    c->part_state = -1;
+    pfn_cuDeviceGet dev_get = nullptr;
+    pfn_cuDeviceGetDevResource get_res = nullptr;
+    pfn_cuDevSmResourceSplitByCount split = nullptr;
+    pfn_cuDevResourceGenerateDesc gen_desc = nullptr;
+    pfn_cuGreenCtxCreate ctx_create = nullptr;
+    pfn_cuGreenCtxStreamCreate stream_create = nullptr;
+    if (!seb_driver_fn("cuDeviceGet", &dev_get) || !seb_driver_fn("cuDeviceGetDevResource", &get_res) ||
+        !seb_driver_fn("cuDevSmResourceSplitByCount", &split) || !seb_driver_fn("cuDevResourceGenerateDesc", &gen_desc) ||
+        !seb_driver_fn("cuGreenCtxCreate", &ctx_create) || !seb_driver_fn("cuGreenCtxStreamCreate", &stream_create))
+        return false;
+    CUdevice dev;
+    CUdevResource all, side, rest;
+    unsigned int groups = 1;
+    if (dev_get(&dev, c->device) != CUDA_SUCCESS || get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    if (split(&side, &groups, &all, &rest, 0, SEB_PART_SIDE_SMS) != CUDA_SUCCESS || groups != 1) return false;
+    if (side.sm.smCount == 0 || rest.sm.smCount == 0) return false;
+    CUdevResource *parts[2] = {&rest, &side};  // [0]: the sampler chain's partition, [1]: the side work's
+    for (int i = 0; i < 2; i++)
+    {
+        CUdevResourceDesc desc;
+        CUstream st = nullptr;
+        if (gen_desc(&desc, parts[i], 1) != CUDA_SUCCESS ||
+            ctx_create(&c->part_ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS ||
+            stream_create(&st, c->part_ctx[i], CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS)
+        {
+            seb_partition_destroy(c);
+            c->part_state = -1;
+            return false;
+        }
+        c->part_stream[i] = reinterpret_cast<cudaStream_t>(st);
+        c->part_sms[i]    = (int)parts[i]->sm.smCount;
+    }
+    for (cudaEvent_t &e : c->part_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+        {
+            seb_partition_destroy(c);
+            c->part_state = -1;
+            return false;
+        }
+    c->part_state = 1;
+    return true;
+}
+
 extern "C" void seb_destroy(seb_ctx *c)
 {
     if (!c) return;
@@ -607,6 +712,7 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaFree(c->d_index_map);
     cudaFree(c->d_work);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    seb_partition_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -641,6 +747,8 @@ extern "C" int seb_set_option(seb_ctx *c, const char *name, long value)
     else if (!strcmp(name, "uniform_pair")) c->knobs.uniform_pair = v;
     else if (!strcmp(name, "uniform_fix_lanes")) c->knobs.uniform_fix_lanes = v;
     else if (!strcmp(name, "uniform_fix_stream")) c->knobs.uniform_fix_stream = v;
+    else if (!strcmp(name, "sym_partition")) c->knobs.sym_partition = v;
+    else if (!strcmp(name, "sym_side_percent")) c->knobs.sym_side_percent = value < 0 ? 34 : value > 90 ? 90 : (int)value;
     else if (!strcmp(name, "host_chunk")) c->knobs.host_chunk = value < 0 ? 0 : value;
     else return fail(SE_ERR_INVALD_ARGUMENT, "unknown option '%s'", name);
     return 0;
@@ -1082,13 +1190,60 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     uint32_t *a_base       = seedct ? s.a_buf : d_out + c->n;
     const size_t ct_stride = (seedct ? 1 : 2) * c->np * c->n;
     const size_t p_stride  = (seedct ? 1 : 2) * c->n;
+    // The latency-bound regime of the sampler chain (one thread-per-sponge warp per SM sub-partition of the big partition,
+    // at a degree where the chain is long): chain and encode / CBD on disjoint SMs (seb_partition_ready).  Only for calls
+    // on the context's own scratch (the host-pointer pipeline already overlaps its chunks).
+    int r = 0;
+    bool split = false;
+    if (&s == &c->dev && c->knobs.sym_partition != 0 && c->logn >= 13)
+    {
+        const size_t warps = (batch + 31) / 32;
+        const bool shape   = c->knobs.sms >= 64 && warps <= (size_t)4 * (c->knobs.sms - SEB_PART_SIDE_SMS) &&
+                           warps * 4 >= (size_t)3 * 4 * (c->knobs.sms - SEB_PART_SIDE_SMS);  // 3/4 .. 1 warp per sub-partition
+        split = (c->knobs.sym_partition > 0 || shape) && seb_partition_ready(c);
+    }
     prof_mark(c, st, 0);
-    int r       = run_encode(c, d_values, vlen, batch, s.pt, s.fail, s.mag, st);
-    if (r) return r;
-    prof_mark(c, st, 1);
-    seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
-    prof_mark(c, st, 2);
-    if ((r = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, st))) return r;
+    if (!split)
+    {
+        r = run_encode(c, d_values, vlen, batch, s.pt, s.fail, s.mag, st);
+        if (r) return r;
+        prof_mark(c, st, 1);
+        seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)batch, st);
+        prof_mark(c, st, 2);
+        if ((r = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, st))) return r;
+    }
+    else
+    {
+        // items [0, b1): encode and CBD on the side partition, under the chain; items [b1, batch): on the whole device first
+        const size_t b1 = (batch * (size_t)c->knobs.sym_side_percent / 100) & ~(size_t)7;
+        cudaStream_t sa = c->part_stream[0], sb = c->part_stream[1];
+        if (b1 < batch)
+        {
+            r = run_encode(c, d_values + b1 * vlen, vlen, batch - b1, s.pt + b1 * c->n, s.fail + b1, s.mag + b1, st);
+            if (r) return r;
+        }
+        prof_mark(c, st, 1);
+        if (b1 < batch) seb_launch_sample_cbd(d_seeds + b1 * SEB_SEED_BYTES, nullptr, s.e + b1 * c->n, n, 1, (int)(batch - b1), st);
+        prof_mark(c, st, 2);
+        CU(cudaEventRecord(c->part_ev[0], st));
+        CU(cudaStreamWaitEvent(sa, c->part_ev[0], 0));
+        CU(cudaStreamWaitEvent(sb, c->part_ev[0], 0));
+        const int sms_all = c->knobs.sms;
+        c->knobs.sms      = c->part_sms[0];  // the chain's kernel choices are made for the partition it runs on
+        r                 = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, sa);
+        c->knobs.sms      = sms_all;
+        if (r) return r;
+        CU(cudaEventRecord(c->part_ev[1], sa));
+        if (b1 > 0)
+        {
+            r = run_encode(c, d_values, vlen, b1, s.pt, s.fail, s.mag, sb);
+            if (r) return r;
+            seb_launch_sample_cbd(d_seeds, nullptr, s.e, n, 1, (int)b1, sb);
+        }
+        CU(cudaEventRecord(c->part_ev[2], sb));
+        CU(cudaStreamWaitEvent(st, c->part_ev[1], 0));
+        CU(cudaStreamWaitEvent(st, c->part_ev[2], 0));
+    }
     prof_mark(c, st, 3);
     CU(seb_launch_encrypt_sym(c->logn, s.pt, s.mag, s.e, c->d_roots_sym, c->d_ntt_s, c->mods, (int)c->np, a_base, d_out,
                               ct_stride, p_stride, seedct ? 0 : quirk, (int)batch, st));

@@ -25,6 +25,8 @@ struct SebKnobs
     int uniform_pair     = -1;  // bulk squeeze by two lanes per sponge (bit-interleaved halves)
     int uniform_fix_lanes = -1; // fix-up lanes per ciphertext: 4, 8 or 32 (-1: by the expected number of rejections)
     int uniform_fix_stream = -1; // the 32-lane fix-up as a stream over 2 / 4 / 8 ciphertexts per warp (2, 4, other > 0; 0: off; -1: by batch size)
+    int sym_partition    = -1;  // symmetric path: sampler chain and encode / CBD on disjoint SM partitions (-1: by shape)
+    int sym_side_percent = 34;  // ... share of the batch whose encode / CBD run on the side partition
     long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
     int sms              = 0;   // SM count of the context's device (kernel selection by machine fill; not an option)
 };

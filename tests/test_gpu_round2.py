@@ -503,3 +503,37 @@ def test_measured_ceilings_are_plausible(seb, torch_cuda):
         assert lanes_per_s / 3 / 8 < b < lanes_per_s / 3 * 1.05
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,np_,batch,percent", [(8192, 2, 200, 34), (16384, 2, 96, 50), (8192, 2, 40, 0), (8192, 2, 40, 90)])
+def test_sym_partition_same_ciphertexts(n, np_, batch, percent, seb, torch_cuda, oracle_mod):
+    """The symmetric path with the sampler chain and the encode / CBD work on disjoint SM partitions (green contexts,
+    forced here with the "sym_partition" option; by itself the library does this for ~16k-item batches) produces the same
+    bytes as the serial path, for a side share of none, some, half and most of the batch, and equals the oracle."""
+    torch = torch_cuda
+    ctx = seb.Context(n, np_, False, device=0)
+    try:
+        sk = oracle_mod.make_sk(n)
+        ctx.set_secret_key(sk)
+        vals = oracle_mod.make_values(batch, n // 2, seed=23)
+        sseeds = oracle_mod.make_seeds(batch, b"part-share")
+        seeds = oracle_mod.make_seeds(batch, b"part")
+        d_vals, d_ss, d_s = (torch.from_numpy(x).cuda() for x in (vals, sseeds, seeds))
+        outs = []
+        for mode in (0, 1):
+            ctx.set_option("sym_partition", mode)
+            ctx.set_option("sym_side_percent", percent)
+            d_out = torch.zeros(batch * np_ * 2 * n, dtype=torch.int32, device="cuda")
+            for _ in range(2):  # twice: the partition's streams and events are reused
+                ctx.encrypt_sym_device(d_vals, n // 2, d_ss, d_s, batch, d_out, False)
+            torch.cuda.synchronize()
+            assert ctx.encode_failures() == 0
+            outs.append(d_out.cpu().numpy().view(np.uint32).reshape(batch, np_, 2, n))
+        assert np.array_equal(outs[0], outs[1])
+        orc = oracle_mod.Oracle()
+        for b in (0, batch // 2, batch - 1):
+            ok, exp = orc.encrypt_sym(n, np_, vals[b], sseeds[b], seeds[b], sk)
+            assert ok and np.array_equal(outs[1][b], exp), b
+    finally:
+        ctx.close()
