@@ -748,7 +748,7 @@ extern "C" int seb_set_option(seb_ctx *c, const char *name, long value)
     else if (!strcmp(name, "uniform_fix_lanes")) c->knobs.uniform_fix_lanes = v;
     else if (!strcmp(name, "uniform_fix_stream")) c->knobs.uniform_fix_stream = v;
     else if (!strcmp(name, "sym_partition")) c->knobs.sym_partition = v;
-    else if (!strcmp(name, "sym_side_percent")) c->knobs.sym_side_percent = value < 0 ? 34 : value > 90 ? 90 : (int)value;
+    else if (!strcmp(name, "sym_side_percent")) c->knobs.sym_side_percent = value < 0 ? -1 : value > 90 ? 90 : (int)value;
     else if (!strcmp(name, "host_chunk")) c->knobs.host_chunk = value < 0 ? 0 : value;
     else return fail(SE_ERR_INVALD_ARGUMENT, "unknown option '%s'", name);
     return 0;
@@ -1171,6 +1171,38 @@ static int run_uniform_chain(seb_ctx *c, Scratch &s, const uint8_t *d_sseeds, si
     return 0;
 }
 
+// How many items' encode + CBD go to the side partition: as many as finish there in 90 % of the time the sampler chain takes
+// on the big one (a forced share through the "sym_side_percent" option).  Both times from the measured rates of the kernels
+// (profiles/README.md): a bulk squeeze is 4n/136 sequential permutations of 5.1 us (3.4 us in the two-lane kernel), a fix-up n x (rejection rate of the
+// prime) candidates per item at 4.4 G/s on the whole device; the CBD sampler n/16 permutations per item at 4.41 G/s, the
+// encode 25 / 69 / 160 ns per item at n = 4096 / 8192 / 16384.
+static size_t seb_side_items(const seb_ctx *c, size_t batch)
+{
+    double share;
+    if (c->knobs.sym_side_percent >= 0)
+        share = c->knobs.sym_side_percent / 100.0;
+    else
+    {
+        const double n = (double)c->n, sms = c->knobs.sms, big = c->part_sms[0], side = c->part_sms[1];
+        // a permutation of the chain: 5.1 us in the thread-per-sponge kernel, ~3.4 us where the two-lane kernel still has a
+        // sub-partition per warp (seb_launch_uniform picks it there)
+        const double perm = (double)batch <= 16.0 * 4.0 * big ? 3.4e-6 : 5.1e-6;
+        double chain = 0.0;
+        for (size_t p = 0; p < c->np; p++)
+        {
+            const double q   = c->primes[p];
+            const double rej = (4294967296.0 - floor(4294967296.0 / q) * q) / 4294967296.0;
+            chain += ceil(4.0 * n / 136.0) * perm + (double)batch * n * rej * 1.07 / 4.4e9 * (sms / big);
+        }
+        const double enc = c->logn <= 12 ? 25e-9 * n / 4096.0 : c->logn == 13 ? 69e-9 : 160e-9;
+        const double ec  = (double)batch * (n / 16.0 / 4.41e9 + enc);
+        share            = 0.9 * chain * side / (sms * ec);
+    }
+    if (share > 0.9) share = 0.9;
+    if (share < 0.0) share = 0.0;
+    return (size_t)((double)batch * share) & ~(size_t)7;
+}
+
 // seedct: the seed-compressed form (SE_ENABLE_SYM_SEED_CT, seal_embedded.c:184-194) — `a` goes to
 // scratch instead of the c1 slots and d_out receives c0 only, [batch][np][n]; the receiver regenerates a
 // from the 64-byte shareable seed (seb_expand_seedct_device).
@@ -1197,9 +1229,10 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     bool split = false;
     if (&s == &c->dev && c->knobs.sym_partition != 0 && c->logn >= 13)
     {
+        // at most one thread-per-sponge warp per SM sub-partition of the big partition, and enough items that the
+        // thread / two-lane kernels are the ones that run (below ~2k items the warp-per-sponge kernels fill the machine)
         const size_t warps = (batch + 31) / 32;
-        const bool shape   = c->knobs.sms >= 64 && warps <= (size_t)4 * (c->knobs.sms - SEB_PART_SIDE_SMS) &&
-                           warps * 4 >= (size_t)3 * 4 * (c->knobs.sms - SEB_PART_SIDE_SMS);  // 3/4 .. 1 warp per sub-partition
+        const bool shape   = c->knobs.sms >= 64 && batch >= 2048 && warps <= (size_t)4 * (c->knobs.sms - SEB_PART_SIDE_SMS);
         split = (c->knobs.sym_partition > 0 || shape) && seb_partition_ready(c);
     }
     prof_mark(c, st, 0);
@@ -1215,7 +1248,7 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
     else
     {
         // items [0, b1): encode and CBD on the side partition, under the chain; items [b1, batch): on the whole device first
-        const size_t b1 = (batch * (size_t)c->knobs.sym_side_percent / 100) & ~(size_t)7;
+        const size_t b1 = seb_side_items(c, batch);
         cudaStream_t sa = c->part_stream[0], sb = c->part_stream[1];
         if (b1 < batch)
         {

@@ -26,7 +26,7 @@ struct SebKnobs
     int uniform_fix_lanes = -1; // fix-up lanes per ciphertext: 4, 8 or 32 (-1: by the expected number of rejections)
     int uniform_fix_stream = -1; // the 32-lane fix-up as a stream over 2 / 4 / 8 ciphertexts per warp (2, 4, other > 0; 0: off; -1: by batch size)
     int sym_partition    = -1;  // symmetric path: sampler chain and encode / CBD on disjoint SM partitions (-1: by shape)
-    int sym_side_percent = 34;  // ... share of the batch whose encode / CBD run on the side partition
+    int sym_side_percent = -1;  // ... share of the batch whose encode / CBD run on the side partition (-1: from the kernels' rates)
     long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
     int sms              = 0;   // SM count of the context's device (kernel selection by machine fill; not an option)
 };
