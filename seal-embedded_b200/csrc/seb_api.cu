@@ -586,6 +586,18 @@ extern "C" seb_ctx *seb_create(size_t n, size_t nprimes, const uint32_t *primes,
         return bail("cudaDeviceGetAttribute", e);
     c->verify_ctas = c->sms * (n <= 4096 ? 4 : n <= 8192 ? 2 : 1);
     c->knobs.sms   = c->sms;
+    // the second stream of the mixed bulk squeeze (seb_launch_uniform); without it the squeeze is one kernel
+    if (!asym)
+    {
+        if (cudaStreamCreateWithFlags(&c->knobs.aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->knobs.aux_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->knobs.aux_ev[1], cudaEventDisableTiming) != cudaSuccess)
+        {
+            cudaGetLastError();
+            if (c->knobs.aux_stream) cudaStreamDestroy(c->knobs.aux_stream);
+            c->knobs.aux_stream = nullptr;
+        }
+    }
     if (build_tables(c) != 0)
     {
         seb_destroy(c);
@@ -713,6 +725,9 @@ extern "C" void seb_destroy(seb_ctx *c)
     cudaFree(c->d_work);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     seb_partition_destroy(c);
+    for (cudaEvent_t e : c->knobs.aux_ev)
+        if (e) cudaEventDestroy(e);
+    if (c->knobs.aux_stream) cudaStreamDestroy(c->knobs.aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -747,6 +762,7 @@ extern "C" int seb_set_option(seb_ctx *c, const char *name, long value)
     else if (!strcmp(name, "uniform_pair")) c->knobs.uniform_pair = v;
     else if (!strcmp(name, "uniform_fix_lanes")) c->knobs.uniform_fix_lanes = v;
     else if (!strcmp(name, "uniform_fix_stream")) c->knobs.uniform_fix_stream = v;
+    else if (!strcmp(name, "uniform_mix")) c->knobs.uniform_mix = v;
     else if (!strcmp(name, "sym_partition")) c->knobs.sym_partition = v;
     else if (!strcmp(name, "sym_side_percent")) c->knobs.sym_side_percent = value < 0 ? -1 : value > 90 ? 90 : (int)value;
     else if (!strcmp(name, "host_chunk")) c->knobs.host_chunk = value < 0 ? 0 : value;
@@ -1263,8 +1279,11 @@ static int encrypt_sym_on(seb_ctx *c, Scratch &s, const float *d_values, size_t 
         CU(cudaStreamWaitEvent(sb, c->part_ev[0], 0));
         const int sms_all = c->knobs.sms;
         c->knobs.sms      = c->part_sms[0];  // the chain's kernel choices are made for the partition it runs on
+        cudaStream_t aux  = c->knobs.aux_stream;
+        c->knobs.aux_stream = nullptr;       // ... and nothing of it leaves that partition
         r                 = run_uniform_chain(c, s, d_sseeds, batch, a_base, ct_stride, p_stride, sa);
         c->knobs.sms      = sms_all;
+        c->knobs.aux_stream = aux;
         if (r) return r;
         CU(cudaEventRecord(c->part_ev[1], sa));
         if (b1 > 0)

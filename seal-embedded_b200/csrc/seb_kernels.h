@@ -28,7 +28,11 @@ struct SebKnobs
     int sym_partition    = -1;  // symmetric path: sampler chain and encode / CBD on disjoint SM partitions (-1: by shape)
     int sym_side_percent = -1;  // ... share of the batch whose encode / CBD run on the side partition (-1: from the kernels' rates)
     long host_chunk      = 0;   // items per chunk of the host-pointer pipeline (0 = automatic)
+    int uniform_mix      = -1;  // bulk squeeze: the sponges beyond the last full layer of thread-kernel warps in the two-lane kernel
     int sms              = 0;   // SM count of the context's device (kernel selection by machine fill; not an option)
+    // a second stream and two events of the context (not options): the two kernels of the mixed squeeze run side by side
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ev[2]   = {nullptr, nullptr};
 };
 
 // ---- samplers (seb_sample.cu) ----

@@ -1366,7 +1366,28 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     const int kt       = ((batch + 31) / 32 + subparts - 1) / subparts;
     const int kp       = ((batch + 15) / 16 + subparts - 1) / subparts;
     const bool pair    = knobs.uniform_pair >= 0 ? knobs.uniform_pair != 0 : (!coop && 12.0 * kp + 3.5 < 21.0 * kt + 2.0);
-    if (pair)
+    // The thread kernel's warps come in layers of one per sub-partition, and the launch lasts as long as the sub-partitions
+    // with the most warps: 65536 sponges are 3.46 layers, the machine idles 13 % of the squeeze.  MIXED: the full layers
+    // go to the thread kernel and the sponges beyond them to the two-lane kernel on a second stream - one two-lane warp (16
+    // sponges, 0.6 of a thread warp's time) on top of k thread warps instead of a (k+1)-th thread warp.  Same sponges,
+    // same outputs; knobs.uniform_mix = 0/1 forces it off / on where it applies.
+    const int warps_t = (batch + 31) / 32, layers = warps_t / subparts;
+    const int full    = layers * subparts * 32;  // sponges of the full layers
+    const int rest    = batch - full;
+    const bool mix    = !pair && !coop && knobs.aux_stream && knobs.uniform_mix != 0 && layers >= 1 && rest >= 512 &&
+                     (rest + 15) / 16 <= subparts;
+    if (mix)
+    {
+        cudaEventRecord(knobs.aux_ev[0], st);
+        cudaStreamWaitEvent(knobs.aux_stream, knobs.aux_ev[0], 0);
+        k_uniform_bulk<<<full / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, full, rej_idx, rej_cnt, rej_cap);
+        k_uniform_bulk_pair<<<(2 * rest + 31) / 32, 32, 0, knobs.aux_stream>>>(
+            seeds + (size_t)full * SEB_SEED_BYTES, ctr + full, out + (size_t)full * ct_stride, ct_stride, n, mod, max_multiple,
+            rest, rej_idx + (size_t)full * rej_cap, rej_cnt + full, rej_cap);
+        cudaEventRecord(knobs.aux_ev[1], knobs.aux_stream);
+        cudaStreamWaitEvent(st, knobs.aux_ev[1], 0);
+    }
+    else if (pair)
         k_uniform_bulk_pair<<<(2 * batch + 31) / 32, 32, 0, st>>>(seeds, ctr, out, ct_stride, n, mod, max_multiple, batch,
                                                                   rej_idx, rej_cnt, rej_cap);
     else if (coop)

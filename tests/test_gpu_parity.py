@@ -320,6 +320,36 @@ def test_sampler_uniform_row_alignment(n, seb, torch_cuda, oracle_mod, orc, ctxs
         ctx.set_option("uniform_pair", -1)
 
 
+@pytest.mark.parametrize("n,np_,batch", [(1024, 1, 20000), (4096, 2, 19800)])
+def test_sampler_uniform_mixed_squeeze(n, np_, batch, seb, torch_cuda, oracle_mod, orc, ctxs):
+    """Above one full layer of thread-kernel warps (one per SM sub-partition: 18944 sponges on 148 SMs) the sponges beyond
+    the full layers are squeezed by the two-lane kernel on a second stream ("uniform_mix"): same polynomials, counters and
+    reject handling as the one-kernel squeeze, and as the oracle on rows from both parts."""
+    torch = torch_cuda
+    ctx = ctxs(n, np_, False)
+    seeds = oracle_mod.make_seeds(batch, b"uniform-mix-%d" % n)
+    d_seeds = dev(torch, seeds)
+    res = []
+    try:
+        for mix in (0, 1):
+            ctx.set_option("uniform_mix", mix)
+            d_ctr = torch.zeros(batch, dtype=torch.int32, device="cuda")
+            d_out = torch.zeros(batch * np_ * n, dtype=torch.int32, device="cuda")
+            for p in range(np_):
+                ctx.sample_uniform_device(d_seeds, d_ctr, p, batch, d_out.data_ptr() + 4 * p * n, np_ * n)
+            torch.cuda.synchronize()
+            res.append((host(d_out, np.uint32).reshape(batch, np_, n), host(d_ctr, np.uint32)))
+    finally:
+        ctx.set_option("uniform_mix", -1)
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for b in (0, 18943, 18944, 18945, batch - 1):
+        c = 0
+        for p, q in enumerate(ctx.primes):
+            exp, c = orc.sample_uniform(n, q, seeds[b], c)
+            assert np.array_equal(res[1][0][b, p], exp), (n, b, p)
+        assert res[1][1][b] == c
+
+
 @pytest.mark.parametrize("wide", ["0", "1", "stream"])
 @pytest.mark.parametrize("cap", ["0", "3", "70"])
 def test_sampler_uniform_list_overflow(cap, wide, seb, torch_cuda, oracle_mod, orc, monkeypatch):
