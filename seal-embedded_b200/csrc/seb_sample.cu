@@ -1365,7 +1365,7 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     const int subparts = 4 * (knobs.sms > 0 ? knobs.sms : 148);
     const int kt       = ((batch + 31) / 32 + subparts - 1) / subparts;
     const int kp       = ((batch + 15) / 16 + subparts - 1) / subparts;
-    const bool pair    = knobs.uniform_pair >= 0 ? knobs.uniform_pair != 0 : (!coop && 12.0 * kp + 3.5 < 21.0 * kt + 2.0);
+    bool pair          = knobs.uniform_pair >= 0 ? knobs.uniform_pair != 0 : (!coop && 12.0 * kp + 3.5 < 21.0 * kt + 2.0);
     // The thread kernel's warps come in layers of one per sub-partition, and the launch lasts as long as the sub-partitions
     // with the most warps: 65536 sponges are 3.46 layers, the machine idles 13 % of the squeeze.  MIXED: the full layers
     // go to the thread kernel and the sponges beyond them to the two-lane kernel on a second stream - one two-lane warp (16
@@ -1374,8 +1374,12 @@ void seb_launch_uniform(const uint8_t *seeds, uint32_t *ctr, uint32_t *out, size
     const int warps_t = (batch + 31) / 32, layers = warps_t / subparts;
     const int full    = layers * subparts * 32;  // sponges of the full layers
     const int rest    = batch - full;
-    const bool mix    = !pair && !coop && knobs.aux_stream && knobs.uniform_mix != 0 && layers >= 1 && rest >= 512 &&
-                     (rest + 15) / 16 <= subparts;
+    const int kr      = ((rest + 15) / 16 + subparts - 1) / subparts;  // two-lane warps per sub-partition for the rest
+    // by the same linear fit: `layers` thread warps and kr two-lane warps on the fullest sub-partition
+    const double cost_mix = 21.0 * layers + 12.0 * kr + 3.5;
+    bool mix = !coop && knobs.aux_stream && knobs.uniform_mix != 0 && knobs.uniform_pair < 0 && layers >= 1 && rest >= 512 &&
+               (knobs.uniform_mix > 0 || cost_mix < (pair ? 12.0 * kp + 3.5 : 21.0 * kt + 2.0));
+    if (mix) pair = false;
     if (mix)
     {
         cudaEventRecord(knobs.aux_ev[0], st);
