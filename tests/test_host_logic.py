@@ -211,6 +211,34 @@ def test_ntt_emulation_matches_oracle(key, npoly, E, orc):
             assert np.array_equal(out[p], orc.ntt(n, q, x[p])), (key, q, p)
 
 
+def test_ntt_split_form_matches_oracle(E, orc):
+    """The split form of the symmetric kernel at n = 16384 (k_encrypt_sym_split, seb_host_build_tw_sym): stage 0 pairs x[i]
+    with x[i + n/2] under roots[1]; half r is then an independent 8192-point transform on the plan of n = 8192 whose root
+    at local stage s, group j is roots[2^(s+1) + r 2^s + j] of the full table.  Here: stage 0 in numpy, the two halves through
+    the emulated 32-coefficient plan with those tables, against ntt_inpl on the whole polynomial."""
+    n, nh = 16384, 8192
+    rng = np.random.default_rng(77)
+    for q in (orc.primes(n, 6)[0], orc.primes(n, 13)[-1]):
+        roots = orc.ntt_roots(n, q)
+        x = rng.integers(0, q, n, dtype=np.uint32)
+        x[:4] = (0, 1, q - 1, q - 2)
+        a, b = x[:nh].astype(np.uint64), x[nh:].astype(np.uint64)
+        t = (b * np.uint64(roots[1])) % np.uint64(q)
+        halves = [((a + t) % np.uint64(q)).astype(np.uint32), ((a + np.uint64(q) - t) % np.uint64(q)).astype(np.uint32)]
+        got = np.zeros(n, np.uint32)
+        for r in range(2):
+            rh = np.zeros(nh, np.uint32)
+            rh[0] = roots[0]
+            for s in range(13):
+                rh[(1 << s):(2 << s)] = roots[(2 << s) + (r << s):(2 << s) + (r << s) + (1 << s)]
+            wq = ((rh.astype(np.uint64) << np.uint64(32)) // np.uint64(q)).astype(np.uint32)
+            out = np.zeros((1, nh), np.uint32)
+            xin = halves[r].reshape(1, nh).copy()
+            assert E.emul_ntt(29, 1, _p(xin, C.c_uint32), _p(rh, C.c_uint32), _p(wq, C.c_uint32), q, _p(out, C.c_uint32)) == 0
+            got[r * nh:(r + 1) * nh] = out[0]
+        assert np.array_equal(got, orc.ntt(n, q, x)), q
+
+
 def test_ntt_emulation_lazy_inputs(E, orc):
     """The fused encrypt feeds on-load values anywhere below 4q (e.g. q - 1 + small): inputs in [0,4q)
     must still give the canonical transform of their residues."""
