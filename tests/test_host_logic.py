@@ -451,3 +451,127 @@ def test_ternary_and_cbd_blocks(E, oracle_mod):
         E.emul_cbd_block_plain(_p(seeds[i], C.c_uint8), ctr, _p(o2, C.c_uint32))
         assert np.array_equal(o, o2)
     assert seen_reject > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# ternary sampler: the pointer-doubling resolution of a wave against the in-order walk it replaces
+# ------------------------------------------------------------------------------------------------
+def _walk_sequential(st, lo, hi, acc, need_full, need_last, nblocks):
+    """sample.c:223-241 as the kernel's first version walked it: counter i is a redraw of the current block while it still
+    owes one (consumed whether or not its byte is acceptable), else the next block, else the walk is over."""
+    j, need, cur, served, consumed = st
+    is_blk = is_red = 0
+    owner = -1
+    for i in range(lo, hi):
+        if need > 0:
+            if (acc >> i) & 1:
+                is_red |= 1 << i
+                served += 1
+                need -= 1
+        elif j < nblocks:
+            need = need_last[i] if j == nblocks - 1 else need_full[i]
+            is_blk |= 1 << i
+            owner, cur, served = i, j, 0
+            j += 1
+        else:
+            break
+        consumed += 1
+    return (j, need, cur, served, consumed), is_blk, is_red, owner
+
+
+def _walk_doubling(st, lo, hi, acc, need_full, need_last, nblocks):
+    """seb_tern_walk (seb_sample.cu) restated: carried block first, "next block" links per lane, five doubling rounds."""
+    j, need, cur, served, consumed = st
+    below = lambda p: (1 << min(p, 32)) - 1  # noqa: E731
+    A = acc & below(hi) & ~below(lo)
+
+    def nth_after(mask, k):  # lane after the k-th (1-based) set bit of mask
+        for _ in range(k - 1):
+            mask &= mask - 1
+        return (mask & -mask).bit_length()
+
+    p0, need_c = lo, 0
+    if need > 0:
+        have = bin(A).count("1")
+        if have < need:
+            p0, need_c = 32, need - have
+        else:
+            p0 = nth_after(A, need)
+    is_blk = 0
+    avail = nblocks - j
+    if p0 < hi and avail > 0:
+        nxt = []
+        for lane in range(32):
+            above = A & ~below(lane + 1)
+            if need_full[lane] == 0:
+                e = lane + 1
+            elif bin(above).count("1") < need_full[lane]:
+                e = 32
+            else:
+                e = nth_after(above, need_full[lane])
+            nxt.append(32 if e >= hi else e)
+        is_blk = 1 << p0
+        for _ in range(5):
+            add = 0
+            for lane in range(32):
+                if (is_blk >> lane) & 1 and nxt[lane] < 32:
+                    add |= 1 << nxt[lane]
+            is_blk |= add
+            nxt = [nxt[nxt[lane]] if nxt[lane] < 32 else 32 for lane in range(32)]
+        if bin(is_blk).count("1") > avail:
+            m, keep = is_blk, 0
+            for _ in range(avail):
+                keep |= m & -m
+                m &= m - 1
+            is_blk = keep
+    nb = bin(is_blk).count("1")
+    owner, end = -1, hi
+    j += nb
+    if nb > 0:
+        owner = is_blk.bit_length() - 1
+        n_b = need_last[owner] if j == nblocks else need_full[owner]
+        rest = A & ~below(owner + 1)
+        got = bin(rest).count("1")
+        cur = j - 1
+        if got >= n_b:
+            need, served = 0, n_b
+            if j == nblocks:
+                end = owner + 1 if n_b == 0 else nth_after(rest, n_b)
+        else:
+            need, served = n_b - got, got
+    else:
+        served += bin(A & below(p0)).count("1")
+        need = need_c
+        if need_c == 0 and j == nblocks:
+            end = p0
+    consumed += end - lo
+    return (j, need, cur, served, consumed), is_blk, A & ~is_blk & below(end), owner
+
+
+def test_ternary_walk_doubling_equals_sequential():
+    """Random waves (dense and sparse acceptable bytes, blocks with 0..4 rejections, carried needs, split waves, the
+    ciphertext ending inside the wave) chained over several waves per state: same roles, same state, same counter."""
+    rng = np.random.default_rng(2024)
+    for trial in range(3000):
+        nblocks = int(rng.integers(1, 60))
+        st_a = st_b = (0, 0, 0, 0, 0)
+        if rng.random() < 0.3:  # start in the middle of a ciphertext, possibly owing redraws
+            j0 = int(rng.integers(0, nblocks + 1))
+            st_a = st_b = (j0, int(rng.integers(0, 5)) if j0 > 0 else 0, max(j0 - 1, 0), int(rng.integers(0, 3)), 17)
+        for wave in range(4):
+            p_acc = rng.choice([0.992, 0.9, 0.5])
+            acc = int(sum(1 << i for i in range(32) if rng.random() < p_acc))
+            need_full = [int(v) for v in rng.choice([0, 0, 0, 1, 1, 2, 3, 4], 32)]
+            need_last = [min(v, int(rng.integers(0, 3))) for v in need_full]
+            lo = int(rng.choice([0, 0, 0, 5, 16]))
+            hi = int(rng.choice([32, 32, 32, 11, 20]))
+            if hi <= lo:
+                lo, hi = 0, 32
+            ra = _walk_sequential(st_a, lo, hi, acc, need_full, need_last, nblocks)
+            rb = _walk_doubling(st_b, lo, hi, acc, need_full, need_last, nblocks)
+            assert ra[1] == rb[1] and ra[2] == rb[2], (trial, wave, "roles")
+            sa, sb = ra[0], rb[0]
+            assert (sa[0], sa[1], sa[4]) == (sb[0], sb[1], sb[4]), (trial, wave, sa, sb)
+            if sa[1] > 0:  # the carried block and what it has been served only matter while it still owes something
+                assert (sa[2], sa[3]) == (sb[2], sb[3]) and (ra[3] >= 0) == (rb[3] >= 0), (trial, wave, sa, sb)
+            st_a, st_b = sa, sb
