@@ -575,3 +575,55 @@ def test_ternary_walk_doubling_equals_sequential():
             if sa[1] > 0:  # the carried block and what it has been served only matter while it still owes something
                 assert (sa[2], sa[3]) == (sb[2], sb[3]) and (ra[3] >= 0) == (rb[3] >= 0), (trial, wave, sa, sb)
             st_a, st_b = sa, sb
+
+
+# ------------------------------------------------------------------------------------------------
+# uniform sampler: the streamed fix-up's lane assignment against the per-ciphertext order of sample.c:39-57
+# ------------------------------------------------------------------------------------------------
+def test_uniform_fix_stream_assignment():
+    """k_uniform_fix_stream restated: a warp serves K ciphertexts in turn; a wave gives the current one as many lanes as it
+    still has rejected words and the lanes behind them to the next one.  For every ciphertext the candidates must be
+    examined in counter order without gaps, the i-th accepted one must land in its i-th rejected word, and the counter
+    must end behind the last candidate consumed - exactly what one ciphertext alone would do."""
+    rng = np.random.default_rng(99)
+    for trial in range(300):
+        K = int(rng.choice([2, 4, 8]))
+        cnt = [int(rng.choice([0, 1, 5, 31, 32, 33, 76, 150])) for _ in range(K)]
+        c0 = [int(rng.integers(0, 1000)) for _ in range(K)]
+        p_acc = float(rng.choice([0.98, 0.75]))
+        ok = [rng.random(4 * max(cnt) + 200) < p_acc for _ in range(K)]  # ok[k][t]: candidate c0 + 1 + t acceptable
+        # reference: each ciphertext by itself
+        want_fill, want_ctr = [], []
+        for k in range(K):
+            idx = np.flatnonzero(ok[k])[:cnt[k]]
+            want_fill.append(list(idx))
+            want_ctr.append(c0[k] + 1 + (int(idx[-1]) + 1 if cnt[k] else 0))
+        # the stream
+        fill = [[] for _ in range(K)]
+        ctr = [None] * K
+        done = [0] * K
+        base = [c + 1 for c in c0]
+        last = list(c0)
+        a = 0
+        guard = 0
+        while a < K:
+            guard += 1
+            assert guard < 10000
+            if done[a] == cnt[a]:
+                ctr[a] = last[a] + 1
+                a += 1
+                continue
+            s = min(32, cnt[a] - done[a])
+            b = a + 1
+            nb = min(32 - s, cnt[b] - done[b]) if b < K else 0
+            for k, lanes in ((a, s), (b, nb)):
+                if lanes == 0:
+                    continue
+                t0 = base[k] - (c0[k] + 1)
+                for lane in range(lanes):
+                    if ok[k][t0 + lane]:
+                        fill[k].append(t0 + lane)
+                        last[k] = base[k] + lane
+                done[k] = len(fill[k])
+                base[k] += lanes
+        assert fill == want_fill and ctr == want_ctr, trial
